@@ -1,0 +1,147 @@
+// C-ABI entry points for the block-tridiagonal operators (include/markovflow_b200.h).
+#include <cstdio>
+#include <cstring>
+
+#include "btd_direct.cuh"
+#include "dispatch.cuh"
+
+namespace mf {
+
+static thread_local char g_last_error[256] = "";
+
+void set_last_error(const char* msg) {
+  std::strncpy(g_last_error, msg, sizeof(g_last_error) - 1);
+  g_last_error[sizeof(g_last_error) - 1] = 0;
+}
+
+int check_launch() {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error(cudaGetErrorString(e));
+    return MF_ERR_CUDA;
+  }
+  return MF_OK;
+}
+
+}  // namespace mf
+
+using namespace mf;
+
+extern "C" {
+
+int mf_version(void) { return 100; }
+
+const char* mf_last_cuda_error(void) { return g_last_error; }
+
+int mf_btd_cholesky(int dtype, const void* diag, const void* sub, const void* rhs, void* out_diag,
+                    void* out_sub, void* out_x, void* out_logdet, int32_t* info, int64_t B,
+                    int64_t T, int64_t D, void* stream) {
+  if (B < 0 || T < 1 || D < 1) return MF_ERR_BAD_ARG;
+  if (B == 0) return MF_OK;
+  if (!diag || !out_diag) return MF_ERR_BAD_ARG;
+  if ((sub != nullptr) != (out_sub != nullptr)) return MF_ERR_BAD_ARG;
+  if ((rhs != nullptr) != (out_x != nullptr)) return MF_ERR_BAD_ARG;
+  if (T == 1) { sub = nullptr; out_sub = nullptr; }
+  cudaStream_t s = (cudaStream_t)stream;
+  return dispatch_small(dtype, D, [&](auto tt, auto dd) {
+    using Tp = typename decltype(tt)::type;
+    constexpr int kD = decltype(dd)::value;
+    btd_chol_direct_kernel<Tp, kD><<<grid_for(B, 32), 32, 0, s>>>(
+        (const Tp*)diag, (const Tp*)sub, (const Tp*)rhs, (Tp*)out_diag, (Tp*)out_sub, (Tp*)out_x,
+        (Tp*)out_logdet, info, B, T);
+    return check_launch();
+  });
+}
+
+int mf_btd_solve(int dtype, const void* ld, const void* ls, const void* rhs, void* out,
+                 int64_t n_rhs, int64_t Bm, int64_t T, int64_t D, int transpose, void* stream) {
+  if (n_rhs < 0 || Bm < 1 || T < 1 || D < 1) return MF_ERR_BAD_ARG;
+  if (n_rhs == 0) return MF_OK;
+  if (!ld || !rhs || !out) return MF_ERR_BAD_ARG;
+  if (T == 1) ls = nullptr;
+  cudaStream_t s = (cudaStream_t)stream;
+  return dispatch_small(dtype, D, [&](auto tt, auto dd) {
+    using Tp = typename decltype(tt)::type;
+    constexpr int kD = decltype(dd)::value;
+    btd_solve_direct_kernel<Tp, kD><<<grid_for(n_rhs, 32), 32, 0, s>>>(
+        (const Tp*)ld, (const Tp*)ls, (const Tp*)rhs, (Tp*)out, n_rhs, Bm, T, transpose);
+    return check_launch();
+  });
+}
+
+int mf_btd_inverse_subset(int dtype, const void* ld, const void* ls, void* out_diag,
+                          void* out_sub, int64_t B, int64_t T, int64_t D, void* stream) {
+  if (B < 0 || T < 1 || D < 1) return MF_ERR_BAD_ARG;
+  if (B == 0) return MF_OK;
+  if (!ld || !out_diag) return MF_ERR_BAD_ARG;
+  if (T == 1) { ls = nullptr; out_sub = nullptr; }
+  if (out_sub && !ls) return MF_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  return dispatch_small(dtype, D, [&](auto tt, auto dd) {
+    using Tp = typename decltype(tt)::type;
+    constexpr int kD = decltype(dd)::value;
+    btd_inverse_subset_direct_kernel<Tp, kD><<<grid_for(B, 32), 32, 0, s>>>(
+        (const Tp*)ld, (const Tp*)ls, (Tp*)out_diag, (Tp*)out_sub, B, T);
+    return check_launch();
+  });
+}
+
+int mf_btd_upper_diagonal_lower(int dtype, const void* diag, const void* sub, void* out_u,
+                                void* out_chol_d, int32_t* info, int64_t B, int64_t T, int64_t D,
+                                void* stream) {
+  if (B < 0 || T < 2 || D < 1) return MF_ERR_BAD_ARG;
+  if (B == 0) return MF_OK;
+  if (!diag || !sub || !out_u || !out_chol_d) return MF_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  return dispatch_small(dtype, D, [&](auto tt, auto dd) {
+    using Tp = typename decltype(tt)::type;
+    constexpr int kD = decltype(dd)::value;
+    btd_udu_direct_kernel<Tp, kD><<<grid_for(B, 32), 32, 0, s>>>(
+        (const Tp*)diag, (const Tp*)sub, (Tp*)out_u, (Tp*)out_chol_d, info, B, T);
+    return check_launch();
+  });
+}
+
+int mf_btd_dense_mult(int dtype, const void* diag, const void* sub, const void* right, void* out,
+                      int64_t n_rhs, int64_t Bm, int64_t T, int64_t D, int transpose,
+                      int symmetric, void* stream) {
+  if (n_rhs < 0 || Bm < 1 || T < 1 || D < 1) return MF_ERR_BAD_ARG;
+  if (n_rhs == 0) return MF_OK;
+  if (!diag || !right || !out) return MF_ERR_BAD_ARG;
+  if (T == 1) sub = nullptr;
+  cudaStream_t s = (cudaStream_t)stream;
+  return dispatch_small(dtype, D, [&](auto tt, auto dd) {
+    using Tp = typename decltype(tt)::type;
+    constexpr int kD = decltype(dd)::value;
+    btd_dense_mult_kernel<Tp, kD><<<grid_for(n_rhs * T, 128), 128, 0, s>>>(
+        (const Tp*)diag, (const Tp*)sub, (const Tp*)right, (Tp*)out, n_rhs, Bm, T, transpose,
+        symmetric);
+    return check_launch();
+  });
+}
+
+int mf_btd_abs_log_det(int dtype, const void* ld, void* out, int64_t B, int64_t T, int64_t D,
+                       void* stream) {
+  if (B < 0 || T < 1 || D < 1) return MF_ERR_BAD_ARG;
+  if (B == 0) return MF_OK;
+  if (!ld || !out) return MF_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  return dispatch_dtype(dtype, [&](auto tt) {
+    using Tp = typename decltype(tt)::type;
+    const int64_t seg_len = 8192;
+    int64_t nseg = (T + seg_len - 1) / seg_len;
+    if (nseg > 1) {
+      if (cudaMemsetAsync(out, 0, sizeof(Tp) * B, s) != cudaSuccess) return check_launch();
+    }
+    for (int64_t b0 = 0; b0 < B; b0 += 65535) {
+      const int64_t nb = (B - b0 < 65535) ? B - b0 : 65535;
+      dim3 grid((unsigned)nseg, (unsigned)nb);
+      btd_abs_log_det_kernel<Tp><<<grid, 256, 0, s>>>((const Tp*)ld + b0 * T * D * D,
+                                                      (Tp*)out + b0, T, (int)D, seg_len,
+                                                      nseg > 1 ? 1 : 0);
+    }
+    return check_launch();
+  });
+}
+
+}  // extern "C"

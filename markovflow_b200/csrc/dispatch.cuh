@@ -1,0 +1,43 @@
+// Host-side helpers shared by the C-ABI translation units: dtype / block-size dispatch, launch
+// error capture.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/markovflow_b200.h"
+
+namespace mf {
+
+template <typename T> struct TypeTag { using type = T; };
+template <int N> struct IntTag { static constexpr int value = N; };
+
+void set_last_error(const char* msg);
+int check_launch();  // returns MF_OK or MF_ERR_CUDA after cudaGetLastError()
+
+// Calls f(TypeTag<T>{}, IntTag<D>{}) for dtype in {f32,f64} and 1 <= D <= MF_SMALL_D_MAX.
+template <typename F>
+int dispatch_small(int dtype, int64_t D, F&& f) {
+#define MF_CASE_D(n)                                                        \
+  case n:                                                                   \
+    if (dtype == MF_F64) return f(TypeTag<double>{}, IntTag<n>{});          \
+    return f(TypeTag<float>{}, IntTag<n>{});
+  if (dtype != MF_F32 && dtype != MF_F64) return MF_ERR_BAD_ARG;
+  switch (D) {
+    MF_CASE_D(1) MF_CASE_D(2) MF_CASE_D(3) MF_CASE_D(4)
+    MF_CASE_D(5) MF_CASE_D(6) MF_CASE_D(7) MF_CASE_D(8)
+    default: return MF_ERR_UNSUPPORTED;
+  }
+#undef MF_CASE_D
+}
+
+template <typename F>
+int dispatch_dtype(int dtype, F&& f) {
+  if (dtype == MF_F64) return f(TypeTag<double>{});
+  if (dtype == MF_F32) return f(TypeTag<float>{});
+  return MF_ERR_BAD_ARG;
+}
+
+inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+}  // namespace mf

@@ -1,0 +1,294 @@
+// Register-resident D x D block arithmetic for the thread-per-chain kernels (D <= 8).
+//
+// Every function is fully unrolled on compile-time D so that blocks live in registers; a chain's
+// recurrence state never touches memory.  Matrices are row-major T[D*D].  "Lower" functions read
+// and write only i >= j entries.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace mf {
+
+template <typename T> struct Num;
+template <> struct Num<double> {
+  static __device__ __forceinline__ double rsqrt(double x) { return ::rsqrt(x); }
+  static __device__ __forceinline__ double log(double x) { return ::log(x); }
+  static __device__ __forceinline__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
+  static __device__ __forceinline__ double abs(double x) { return ::fabs(x); }
+  static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+};
+template <> struct Num<float> {
+  static __device__ __forceinline__ float rsqrt(float x) { return 1.0f / ::sqrtf(x); }
+  static __device__ __forceinline__ float log(float x) { return ::logf(x); }
+  static __device__ __forceinline__ float fma(float a, float b, float c) { return ::fmaf(a, b, c); }
+  static __device__ __forceinline__ float abs(float x) { return ::fabsf(x); }
+  static __device__ __forceinline__ float rcp(float x) { return 1.0f / x; }
+};
+
+// In-place Cholesky of the lower triangle of s.  rinv[j] = 1 / L[j][j].
+// Returns false if a pivot is not strictly positive (NaN counts as failure); the factor then holds
+// NaNs from that column on, as a LAPACK-style failure would leave it undefined.
+template <typename T, int D>
+__device__ __forceinline__ bool chol_lower(T* __restrict__ s, T* __restrict__ rinv) {
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    T p = s[j * D + j];
+#pragma unroll
+    for (int q = 0; q < j; ++q) p = Num<T>::fma(-s[j * D + q], s[j * D + q], p);
+    ok = ok && (p > T(0));
+    const T r = Num<T>::rsqrt(p);
+    rinv[j] = r;
+    s[j * D + j] = p * r;
+#pragma unroll
+    for (int i = j + 1; i < D; ++i) {
+      T v = s[i * D + j];
+#pragma unroll
+      for (int q = 0; q < j; ++q) v = Num<T>::fma(-s[i * D + q], s[j * D + q], v);
+      s[i * D + j] = v * r;
+    }
+  }
+  return ok;
+}
+
+// x <- L^{-1} x   (forward substitution, L lower with reciprocal diagonal rinv)
+template <typename T, int D>
+__device__ __forceinline__ void trsv_lower(const T* __restrict__ l, const T* __restrict__ rinv,
+                                           T* __restrict__ x) {
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    T v = x[i];
+#pragma unroll
+    for (int q = 0; q < i; ++q) v = Num<T>::fma(-l[i * D + q], x[q], v);
+    x[i] = v * rinv[i];
+  }
+}
+
+// x <- L^{-T} x   (back substitution with the transpose of a lower factor)
+template <typename T, int D>
+__device__ __forceinline__ void trsv_lower_t(const T* __restrict__ l, const T* __restrict__ rinv,
+                                             T* __restrict__ x) {
+#pragma unroll
+  for (int i = D - 1; i >= 0; --i) {
+    T v = x[i];
+#pragma unroll
+    for (int q = i + 1; q < D; ++q) v = Num<T>::fma(-l[q * D + i], x[q], v);
+    x[i] = v * rinv[i];
+  }
+}
+
+// a <- a L^{-T}   (row-wise: each row r solves  x L^T = a_r, i.e. L x^T = a_r^T)
+template <typename T, int D>
+__device__ __forceinline__ void trsm_right_lower_t(T* __restrict__ a, const T* __restrict__ l,
+                                                   const T* __restrict__ rinv) {
+#pragma unroll
+  for (int r = 0; r < D; ++r) trsv_lower<T, D>(l, rinv, a + r * D);
+}
+
+// a <- a L^{-1}   (row-wise: x L = a_r, i.e. L^T x^T = a_r^T)
+template <typename T, int D>
+__device__ __forceinline__ void trsm_right_lower(T* __restrict__ a, const T* __restrict__ l,
+                                                 const T* __restrict__ rinv) {
+#pragma unroll
+  for (int r = 0; r < D; ++r) trsv_lower_t<T, D>(l, rinv, a + r * D);
+}
+
+// a <- L^{-1} a   (column-wise forward substitution on a full D x D right-hand side)
+template <typename T, int D>
+__device__ __forceinline__ void trsm_left_lower(const T* __restrict__ l, const T* __restrict__ rinv,
+                                                T* __restrict__ a) {
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      T v = a[i * D + c];
+#pragma unroll
+      for (int q = 0; q < i; ++q) v = Num<T>::fma(-l[i * D + q], a[q * D + c], v);
+      a[i * D + c] = v * rinv[i];
+    }
+  }
+}
+
+// a <- L^{-T} a
+template <typename T, int D>
+__device__ __forceinline__ void trsm_left_lower_t(const T* __restrict__ l, const T* __restrict__ rinv,
+                                                  T* __restrict__ a) {
+#pragma unroll
+  for (int i = D - 1; i >= 0; --i) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      T v = a[i * D + c];
+#pragma unroll
+      for (int q = i + 1; q < D; ++q) v = Num<T>::fma(-l[q * D + i], a[q * D + c], v);
+      a[i * D + c] = v * rinv[i];
+    }
+  }
+}
+
+// s(lower) <- s - x x^T
+template <typename T, int D>
+__device__ __forceinline__ void syrk_sub_lower(T* __restrict__ s, const T* __restrict__ x) {
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      T v = s[i * D + j];
+#pragma unroll
+      for (int q = 0; q < D; ++q) v = Num<T>::fma(-x[i * D + q], x[j * D + q], v);
+      s[i * D + j] = v;
+    }
+}
+
+// y <- y - A x
+template <typename T, int D>
+__device__ __forceinline__ void gemv_sub(T* __restrict__ y, const T* __restrict__ a,
+                                         const T* __restrict__ x) {
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    T v = y[i];
+#pragma unroll
+    for (int q = 0; q < D; ++q) v = Num<T>::fma(-a[i * D + q], x[q], v);
+    y[i] = v;
+  }
+}
+
+// y <- y - A^T x
+template <typename T, int D>
+__device__ __forceinline__ void gemv_t_sub(T* __restrict__ y, const T* __restrict__ a,
+                                           const T* __restrict__ x) {
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    T v = y[i];
+#pragma unroll
+    for (int q = 0; q < D; ++q) v = Num<T>::fma(-a[q * D + i], x[q], v);
+    y[i] = v;
+  }
+}
+
+// y <- y + A x
+template <typename T, int D>
+__device__ __forceinline__ void gemv_add(T* __restrict__ y, const T* __restrict__ a,
+                                         const T* __restrict__ x) {
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    T v = y[i];
+#pragma unroll
+    for (int q = 0; q < D; ++q) v = Num<T>::fma(a[i * D + q], x[q], v);
+    y[i] = v;
+  }
+}
+
+// y <- y + A^T x
+template <typename T, int D>
+__device__ __forceinline__ void gemv_t_add(T* __restrict__ y, const T* __restrict__ a,
+                                           const T* __restrict__ x) {
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    T v = y[i];
+#pragma unroll
+    for (int q = 0; q < D; ++q) v = Num<T>::fma(a[q * D + i], x[q], v);
+    y[i] = v;
+  }
+}
+
+// c <- a b      (full D x D)
+template <typename T, int D>
+__device__ __forceinline__ void gemm(T* __restrict__ c, const T* __restrict__ a,
+                                     const T* __restrict__ b) {
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      T v = T(0);
+#pragma unroll
+      for (int q = 0; q < D; ++q) v = Num<T>::fma(a[i * D + q], b[q * D + j], v);
+      c[i * D + j] = v;
+    }
+}
+
+// c <- a^T b
+template <typename T, int D>
+__device__ __forceinline__ void gemm_tn(T* __restrict__ c, const T* __restrict__ a,
+                                        const T* __restrict__ b) {
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      T v = T(0);
+#pragma unroll
+      for (int q = 0; q < D; ++q) v = Num<T>::fma(a[q * D + i], b[q * D + j], v);
+      c[i * D + j] = v;
+    }
+}
+
+// c <- a b^T
+template <typename T, int D>
+__device__ __forceinline__ void gemm_nt(T* __restrict__ c, const T* __restrict__ a,
+                                        const T* __restrict__ b) {
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      T v = T(0);
+#pragma unroll
+      for (int q = 0; q < D; ++q) v = Num<T>::fma(a[i * D + q], b[j * D + q], v);
+      c[i * D + j] = v;
+    }
+}
+
+// Full symmetric  (L L^T)^{-1}  from a lower factor: inverse = L^{-T} L^{-1}.
+// w is D*D scratch; out receives the full symmetric matrix.
+template <typename T, int D>
+__device__ __forceinline__ void chol_inverse(T* __restrict__ out, const T* __restrict__ l,
+                                             const T* __restrict__ rinv) {
+  T w[D * D];  // w = L^{-1}  (lower)
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      if (c > i) { w[i * D + c] = T(0); continue; }
+      T v = (i == c) ? T(1) : T(0);
+#pragma unroll
+      for (int q = c; q < i; ++q) v = Num<T>::fma(-l[i * D + q], w[q * D + c], v);
+      w[i * D + c] = v * rinv[i];
+    }
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      T v = T(0);
+#pragma unroll
+      for (int q = i; q < D; ++q) v = Num<T>::fma(w[q * D + i], w[q * D + j], v);
+      out[i * D + j] = v;
+      out[j * D + i] = v;
+    }
+}
+
+template <typename T, int D>
+__device__ __forceinline__ void zero_upper(T* __restrict__ a) {
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = i + 1; j < D; ++j) a[i * D + j] = T(0);
+}
+
+template <typename T, int D>
+__device__ __forceinline__ void mirror_lower(T* __restrict__ a) {
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = i + 1; j < D; ++j) a[i * D + j] = a[j * D + i];
+}
+
+template <typename T, int N>
+__device__ __forceinline__ void load_vec(T* __restrict__ r, const T* __restrict__ g) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) r[i] = __ldg(g + i);
+}
+
+template <typename T, int N>
+__device__ __forceinline__ void store_vec(T* __restrict__ g, const T* __restrict__ r) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) g[i] = r[i];
+}
+
+}  // namespace mf
