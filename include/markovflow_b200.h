@@ -42,6 +42,9 @@ extern "C" {
 /* Library / build information. */
 int mf_version(void);
 const char* mf_last_cuda_error(void);
+/* Development/tuning knobs (kernel variant selection); knob 0: Cholesky sweep variant
+ * (0 auto, 1 direct global-memory streaming, 2 shared-memory staged), knob 1: steps per stage. */
+int mf_set_tuning(int knob, int value);
 
 /* ---------------------------------------------------------------------------------------------
  * Block-tridiagonal operators (markovflow/block_tri_diag.py)

@@ -3,6 +3,7 @@
 #include <cstring>
 
 #include "btd_direct.cuh"
+#include "btd_staged.cuh"
 #include "dispatch.cuh"
 
 namespace mf {
@@ -27,7 +28,63 @@ int check_launch() {
 
 using namespace mf;
 
+namespace {
+
+// Tuning knobs (mf_set_tuning): 0 = variant of the Cholesky sweep (0 auto, 1 direct, 2 staged),
+// 1 = steps per shared-memory stage for the staged sweep (0 auto).
+int g_tuning[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+constexpr int kSmemBudget = 232448 - 1536;  // 227 KB opt-in maximum minus barrier/alignment slack
+
+template <typename T, int D, bool RHS>
+struct StagedPick {
+  static constexpr int NSI = 3, NSO = 2;
+  static constexpr int ETOT = 2 * D * D + (RHS ? D : 0);
+  static constexpr int per_k(int c) { return (int)sizeof(T) * ETOT * (c + 1) * (NSI + NSO); }
+  static constexpr int C = (2 * per_k(32) <= kSmemBudget) ? 32 : ((2 * per_k(16) <= kSmemBudget) ? 16 : 8);
+  static constexpr int KMAX = kSmemBudget / per_k(C);
+  static constexpr int K = KMAX >= 8 ? 8 : (KMAX >= 4 ? 4 : (KMAX >= 2 ? 2 : 1));
+};
+
+template <typename T, int D, bool RHS, int C, int K, int NSI, int NSO>
+int launch_chol_staged(const void* diag, const void* sub, const void* rhs, void* od, void* os,
+                       void* ox, void* logdet, int32_t* info, int64_t B, int64_t Tn,
+                       cudaStream_t s) {
+  using Cfg = CholStagedCfg<T, D, RHS, C, K, NSI, NSO>;
+  auto kern = btd_chol_staged_kernel<T, D, RHS, C, K, NSI, NSO>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)Cfg::SMEM_BYTES) != cudaSuccess)
+      return check_launch();
+    configured = true;
+  }
+  kern<<<grid_for(B, C), Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(
+      (const T*)diag, (const T*)sub, (const T*)rhs, (T*)od, (T*)os, (T*)ox, (T*)logdet, info, B, Tn);
+  return check_launch();
+}
+
+template <typename T, int D, bool RHS>
+int launch_chol_staged_auto(const void* diag, const void* sub, const void* rhs, void* od, void* os,
+                            void* ox, void* logdet, int32_t* info, int64_t B, int64_t Tn,
+                            cudaStream_t s) {
+  using P = StagedPick<T, D, RHS>;
+  if (P::K >= 8 && g_tuning[1] == 4)
+    return launch_chol_staged<T, D, RHS, P::C, (P::K >= 8 ? 4 : P::K), P::NSI, P::NSO>(
+        diag, sub, rhs, od, os, ox, logdet, info, B, Tn, s);
+  return launch_chol_staged<T, D, RHS, P::C, P::K, P::NSI, P::NSO>(diag, sub, rhs, od, os, ox,
+                                                                  logdet, info, B, Tn, s);
+}
+
+}  // namespace
+
 extern "C" {
+
+int mf_set_tuning(int knob, int value) {
+  if (knob < 0 || knob >= 8) return MF_ERR_BAD_ARG;
+  g_tuning[knob] = value;
+  return MF_OK;
+}
 
 int mf_version(void) { return 100; }
 
@@ -46,6 +103,14 @@ int mf_btd_cholesky(int dtype, const void* diag, const void* sub, const void* rh
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
+    const bool staged = (sub != nullptr) && g_tuning[0] != 1;
+    if (staged) {
+      if (rhs)
+        return launch_chol_staged_auto<Tp, kD, true>(diag, sub, rhs, out_diag, out_sub, out_x,
+                                                     out_logdet, info, B, T, s);
+      return launch_chol_staged_auto<Tp, kD, false>(diag, sub, rhs, out_diag, out_sub, out_x,
+                                                    out_logdet, info, B, T, s);
+    }
     btd_chol_direct_kernel<Tp, kD><<<grid_for(B, 32), 32, 0, s>>>(
         (const Tp*)diag, (const Tp*)sub, (const Tp*)rhs, (Tp*)out_diag, (Tp*)out_sub, (Tp*)out_x,
         (Tp*)out_logdet, info, B, T);

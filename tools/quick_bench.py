@@ -40,6 +40,13 @@ def run(b, t, d, reps=5, dtype=torch.float64):
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
+    for variant, k in ((1, 0), (0, 0), (0, 4)):
+        _lib.lib().mf_set_tuning(0, variant); _lib.lib().mf_set_tuning(1, k)
+        print("variant", variant, "K", k)
+        run(4096, 10000, 3)
+        run(4736, 10000, 3)
+        run(16384, 2500, 3)
+    _lib.lib().mf_set_tuning(0, 0); _lib.lib().mf_set_tuning(1, 0)
     run(4096, 10000, 3)
     run(4096, 2000, 3)
     run(8192, 5000, 3)
