@@ -43,7 +43,8 @@ extern "C" {
 int mf_version(void);
 const char* mf_last_cuda_error(void);
 /* Development/tuning knobs (kernel variant selection); knob 0: Cholesky sweep variant
- * (0 auto, 1 direct global-memory streaming, 2 shared-memory staged), knob 1: steps per stage. */
+ * (0 auto = TMA bulk-copy ring, 1 direct global-memory streaming, 2 cp.async element-staged ring),
+ * knob 1: steps per stage of variant 2. */
 int mf_set_tuning(int knob, int value);
 
 /* ---------------------------------------------------------------------------------------------

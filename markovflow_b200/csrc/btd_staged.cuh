@@ -10,10 +10,16 @@
 //             full_out[NSO] <- compute warp finished a tile (also frees that tile's input stage)
 //             empty_out[NSO]<- copy threads drained an output stage
 #pragma once
+#include "chol_core.cuh"
 #include "pipe.cuh"
-#include "smallmat.cuh"
 
 namespace mf {
+
+// transposed tile: element (s, e) of a stream at  s*ETOT*CP + e*CP  (+ lane)
+template <int ETOT, int CP>
+struct TransposedLayout {
+  static constexpr int SS_M = ETOT * CP, ES_M = CP, SS_V = ETOT * CP, ES_V = CP;
+};
 
 template <typename T, int D, bool RHS, int C, int K, int NSI, int NSO>
 struct CholStagedCfg {
@@ -95,16 +101,10 @@ btd_chol_staged_kernel(const T* __restrict__ diag, const T* __restrict__ sub,
   }
 
   // --------------------------------- compute warp ------------------------------------------
+  using Layout = TransposedLayout<ETOT, CP>;
   const bool valid = (lane < C) && (chain0 + lane < B);
-  T Lp[DD], xp[D], rinv[D];  // previous step's Ls and x
-#pragma unroll
-  for (int i = 0; i < DD; ++i) Lp[i] = T(0);
-#pragma unroll
-  for (int i = 0; i < D; ++i) xp[i] = T(0);
-  T prod = T(1);
-  int esum = 0;
-  int32_t fail = 0;
-
+  CholCore<T, D, RHS, Layout> core;
+  core.init();
   for (int64_t t = 0; t < ntiles; ++t) {
     const int si = (int)(t % NSI), so = (int)(t % NSO);
     mbar_wait(full_in + si, (uint32_t)((t / NSI) & 1));
@@ -113,63 +113,14 @@ btd_chol_staged_kernel(const T* __restrict__ diag, const T* __restrict__ sub,
     T* op = out_tiles + (size_t)so * Cfg::STAGE_ELEMS + lane;
     const int64_t k0 = t * K;
     const int ns = (int)((Tn - k0 < K) ? (Tn - k0) : K);
-    if (valid) {
-      for (int s = 0; s < ns; ++s) {
-        const int64_t k = k0 + s;
-        const T* rec = ip + (size_t)s * ETOT * CP;
-        T* orec = op + (size_t)s * ETOT * CP;
-        T S[DD];
-#pragma unroll
-        for (int i = 0; i < D; ++i)
-#pragma unroll
-          for (int j = 0; j <= i; ++j) S[i * D + j] = rec[(i * D + j) * CP];
-        syrk_sub_lower<T, D>(S, Lp);  // Lp == 0 at k == 0
-        const bool ok = chol_lower<T, D>(S, rinv);
-        if (!ok && fail == 0) fail = (int32_t)(k + 1);
-#pragma unroll
-        for (int i = 0; i < D; ++i)
-#pragma unroll
-          for (int j = 0; j < D; ++j) orec[(i * D + j) * CP] = (j <= i) ? S[i * D + j] : T(0);
-        if (logdet) {
-          T p = S[0];
-#pragma unroll
-          for (int j = 1; j < D; ++j) p *= S[j * D + j];
-          prod *= p;
-          if (sizeof(T) == 8) {
-            const int hi = __double2hiint((double)prod);
-            const int e = ((hi >> 20) & 0x7ff) - 1023;
-            esum += e;
-            prod = (T)__hiloint2double(hi - (e << 20), __double2loint((double)prod));
-          } else {
-            const int bits = __float_as_int((float)prod);
-            const int e = ((bits >> 23) & 0xff) - 127;
-            esum += e;
-            prod = (T)__int_as_float(bits - (e << 23));
-          }
-        }
-        if (RHS) {
-          T r[D];
-#pragma unroll
-          for (int i = 0; i < D; ++i) r[i] = rec[(2 * DD + i) * CP];
-          gemv_sub<T, D>(r, Lp, xp);
-          trsv_lower<T, D>(S, rinv, r);
-#pragma unroll
-          for (int i = 0; i < D; ++i) { xp[i] = r[i]; orec[(2 * DD + i) * CP] = r[i]; }
-        }
-        if (k + 1 < Tn) {
-#pragma unroll
-          for (int i = 0; i < DD; ++i) Lp[i] = rec[(DD + i) * CP];
-          trsm_right_lower_t<T, D>(Lp, S, rinv);
-#pragma unroll
-          for (int i = 0; i < DD; ++i) orec[(DD + i) * CP] = Lp[i];
-        }
-      }
-    }
+    if (valid)
+      core.tile(ip, ip + DD * CP, ip + 2 * DD * CP, op, op + DD * CP, op + 2 * DD * CP, ns, k0, Tn,
+                logdet != nullptr);
     mbar_arrive(full_out + so);
   }
   if (valid) {
-    if (logdet) logdet[chain0 + lane] = Num<T>::log(prod) + T(esum) * T(0.6931471805599453094);
-    if (info) info[chain0 + lane] = fail;
+    if (logdet) logdet[chain0 + lane] = core.log_det();
+    if (info) info[chain0 + lane] = core.fail;
   }
 }
 

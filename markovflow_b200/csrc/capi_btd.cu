@@ -4,6 +4,7 @@
 
 #include "btd_direct.cuh"
 #include "btd_staged.cuh"
+#include "btd_tma.cuh"
 #include "dispatch.cuh"
 
 namespace mf {
@@ -30,7 +31,8 @@ using namespace mf;
 
 namespace {
 
-// Tuning knobs (mf_set_tuning): 0 = variant of the Cholesky sweep (0 auto, 1 direct, 2 staged),
+// Tuning knobs (mf_set_tuning): 0 = variant of the Cholesky sweep (0 auto = TMA, 1 direct,
+// 2 cp.async-staged),
 // 1 = steps per shared-memory stage for the staged sweep (0 auto).
 int g_tuning[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
@@ -76,6 +78,49 @@ int launch_chol_staged_auto(const void* diag, const void* sub, const void* rhs, 
                                                                   logdet, info, B, Tn, s);
 }
 
+// ---- TMA variant: pick chains/CTA and steps/stage so that the ring fits and stays 16B-aligned ----
+template <typename T, int D, bool RHS, int C, int K>
+constexpr bool tma_fits() {
+  using Cfg = CholTmaCfg<T, D, RHS, C, K, 3, 2>;
+  return Cfg::ALIGN_OK && Cfg::SMEM_BYTES <= (size_t)232448;
+}
+
+template <typename T, int D, bool RHS>
+struct TmaPick {
+  static constexpr int C = (tma_fits<T, D, RHS, 32, 4>() || tma_fits<T, D, RHS, 32, 8>())
+                               ? 32
+                               : ((tma_fits<T, D, RHS, 16, 4>() || tma_fits<T, D, RHS, 16, 8>()) ? 16 : 8);
+  static constexpr int K = tma_fits<T, D, RHS, C, 8>() ? 8 : (tma_fits<T, D, RHS, C, 4>() ? 4 : 0);
+};
+
+template <typename T, int D, bool RHS, int C, int K>
+int launch_chol_tma(const void* diag, const void* sub, const void* rhs, void* od, void* os,
+                    void* ox, void* logdet, int32_t* info, int64_t B, int64_t Tn, cudaStream_t s) {
+  using Cfg = CholTmaCfg<T, D, RHS, C, K, 3, 2>;
+  auto kern = btd_chol_tma_kernel<T, D, RHS, C, K, 3, 2>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)Cfg::SMEM_BYTES) != cudaSuccess)
+      return check_launch();
+    configured = true;
+  }
+  kern<<<grid_for(B, C), Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(
+      (const T*)diag, (const T*)sub, (const T*)rhs, (T*)od, (T*)os, (T*)ox, (T*)logdet, info, B, Tn);
+  return check_launch();
+}
+
+template <typename T, int D, bool RHS>
+int launch_chol_fast(const void* diag, const void* sub, const void* rhs, void* od, void* os,
+                     void* ox, void* logdet, int32_t* info, int64_t B, int64_t Tn, cudaStream_t s) {
+  using P = TmaPick<T, D, RHS>;
+  if constexpr (P::K > 0) {
+    if (g_tuning[0] != 2)
+      return launch_chol_tma<T, D, RHS, P::C, P::K>(diag, sub, rhs, od, os, ox, logdet, info, B, Tn, s);
+  }
+  return launch_chol_staged_auto<T, D, RHS>(diag, sub, rhs, od, os, ox, logdet, info, B, Tn, s);
+}
+
 }  // namespace
 
 extern "C" {
@@ -106,10 +151,10 @@ int mf_btd_cholesky(int dtype, const void* diag, const void* sub, const void* rh
     const bool staged = (sub != nullptr) && g_tuning[0] != 1;
     if (staged) {
       if (rhs)
-        return launch_chol_staged_auto<Tp, kD, true>(diag, sub, rhs, out_diag, out_sub, out_x,
-                                                     out_logdet, info, B, T, s);
-      return launch_chol_staged_auto<Tp, kD, false>(diag, sub, rhs, out_diag, out_sub, out_x,
-                                                    out_logdet, info, B, T, s);
+        return launch_chol_fast<Tp, kD, true>(diag, sub, rhs, out_diag, out_sub, out_x,
+                                              out_logdet, info, B, T, s);
+      return launch_chol_fast<Tp, kD, false>(diag, sub, rhs, out_diag, out_sub, out_x,
+                                             out_logdet, info, B, T, s);
     }
     btd_chol_direct_kernel<Tp, kD><<<grid_for(B, 32), 32, 0, s>>>(
         (const Tp*)diag, (const Tp*)sub, (const Tp*)rhs, (Tp*)out_diag, (Tp*)out_sub, (Tp*)out_x,

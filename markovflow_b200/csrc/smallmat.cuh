@@ -263,6 +263,75 @@ __device__ __forceinline__ void chol_inverse(T* __restrict__ out, const T* __res
     }
 }
 
+// s(lower) <- s - t w^T     (t and w full D x D)
+template <typename T, int D>
+__device__ __forceinline__ void gemm_nt_sub_lower(T* __restrict__ s, const T* __restrict__ t,
+                                                  const T* __restrict__ w) {
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      T v = s[i * D + j];
+#pragma unroll
+      for (int q = 0; q < D; ++q) v = Num<T>::fma(-t[i * D + q], w[j * D + q], v);
+      s[i * D + j] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Short-critical-path factorisation step for D <= 3.
+//
+// The textbook Cholesky of a D x D block chains D reciprocal-square-roots (each ~66 cycles of
+// dependent FP64 latency on B200).  Here the pivots d_j of S = L_u diag(d) L_u^T are obtained from
+// the leading principal minors m_j (d_j = m_j / m_{j-1}), so the D rsqrt's q_j = rsqrt(m_j) are
+// INDEPENDENT of each other:
+//     sqrt(d_j) = (m_j q_j) q_{j-1},    1/sqrt(d_j) = q_j (m_{j-1} q_{j-1}),    prod_j d_j = m_D
+// Outputs are the ordinary Cholesky quantities (identical in exact arithmetic; accuracy against a
+// long-double factorisation is the same as the chained form):
+//   lu  unit-lower factor L_u (strict lower part), rs[j] = 1/sqrt(d_j), sq[j] = sqrt(d_j),
+//   det = m_D.  Returns false on a non-positive pivot.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int D>
+__device__ __forceinline__ bool ldl_minors(const T* __restrict__ s, T* __restrict__ lu,
+                                           T* __restrict__ rs, T* __restrict__ sq, T& det) {
+  static_assert(D >= 1 && D <= 3, "minor-based pivots are implemented for D <= 3");
+  const T m1 = s[0];
+  const T q0 = Num<T>::rsqrt(m1);
+  const T sm1 = m1 * q0;  // sqrt(m1)
+  rs[0] = q0;
+  sq[0] = sm1;
+  det = m1;
+  bool ok = m1 > T(0);
+  if (D >= 2) {
+    const T s10 = s[1 * D + 0], s11 = s[1 * D + 1];
+    const T m2 = Num<T>::fma(m1, s11, -(s10 * s10));
+    const T q1 = Num<T>::rsqrt(m2);
+    const T sm2 = m2 * q1;  // sqrt(m2)
+    ok = ok && (m2 > T(0));
+    const T rd0 = q0 * q0;  // 1/d_0
+    rs[1] = q1 * sm1;
+    sq[1] = sm2 * q0;
+    det = m2;
+    lu[1 * D + 0] = s10 * rd0;
+    if (D >= 3) {
+      const T s20 = s[2 * D + 0], s21 = s[2 * D + 1], s22 = s[2 * D + 2];
+      const T c0 = Num<T>::fma(s11, s22, -(s21 * s21));
+      const T c1 = Num<T>::fma(s10, s22, -(s21 * s20));
+      const T c2 = Num<T>::fma(s10, s21, -(s11 * s20));
+      const T m3 = Num<T>::fma(s20, c2, Num<T>::fma(-s10, c1, m1 * c0));
+      const T q2 = Num<T>::rsqrt(m3);
+      ok = ok && (m3 > T(0));
+      rs[2] = q2 * sm2;
+      sq[2] = (m3 * q2) * q1;
+      det = m3;
+      const T rd1 = rs[1] * rs[1];  // 1/d_1
+      lu[2 * D + 0] = s20 * rd0;
+      lu[2 * D + 1] = Num<T>::fma(-lu[2 * D + 0], s10, s21) * rd1;
+    }
+  }
+  return ok;
+}
+
 template <typename T, int D>
 __device__ __forceinline__ void zero_upper(T* __restrict__ a) {
 #pragma unroll
