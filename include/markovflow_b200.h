@@ -23,6 +23,7 @@
 #ifndef MARKOVFLOW_B200_H
 #define MARKOVFLOW_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -44,7 +45,8 @@ int mf_version(void);
 const char* mf_last_cuda_error(void);
 /* Development/tuning knobs (kernel variant selection); knob 0: Cholesky sweep variant
  * (0 auto = TMA bulk-copy ring, 1 direct global-memory streaming, 2 cp.async element-staged ring),
- * knob 1: steps per stage of variant 2. */
+ * knob 1: steps per stage of variant 2; knob 2: Kalman log-likelihood path (0 auto, 1 one thread
+ * per chain, 2 parallel-in-time); knob 3: steps per parallel-in-time segment (0 auto). */
 int mf_set_tuning(int knob, int value);
 
 /* ---------------------------------------------------------------------------------------------
@@ -64,7 +66,8 @@ int mf_btd_cholesky(int dtype, const void* diag, const void* sub, const void* rh
                     int64_t T, int64_t D, void* stream);
 
 /* LowerTriangularBlockTriDiagonal.solve (block_tri_diag.py:339-351; solve_triang_mat :350).
- *   ld [Bm,T,D,D] (lower triangle read), ls [Bm,T-1,D,D] or NULL, rhs/out [n_rhs,T,D].
+ *   ld [Bm,T,D,D] (lower triangle read; NULL = identity diagonal blocks, the a_inv_block of
+ *   state_space_model.py:278-296), ls [Bm,T-1,D,D] or NULL, rhs/out [n_rhs,T,D].
  * Right-hand side chain c uses matrix chain c % Bm (leading sample dims of `right`,
  * block_tri_diag.py:261-287).  transpose != 0 solves with L^T (runs backwards in time). */
 int mf_btd_solve(int dtype, const void* ld, const void* ls, const void* rhs, void* out,
@@ -95,6 +98,107 @@ int mf_btd_dense_mult(int dtype, const void* diag, const void* sub, const void* 
 /* LowerTriangularBlockTriDiagonal.abs_log_det (block_tri_diag.py:353-366): out [B]. */
 int mf_btd_abs_log_det(int dtype, const void* ld, void* out, int64_t B, int64_t T, int64_t D,
                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * StateSpaceModel operators (markovflow/state_space_model.py).  Parameter layout of the reference
+ * (state_space_model.py:74-122), chain-contiguous, T = num_transitions + 1 states:
+ *   mu0 [B,D], chol_p0 [B,D,D], a [B,T-1,D,D], b [B,T-1,D], chol_q [B,T-1,D,D]
+ * ------------------------------------------------------------------------------------------- */
+
+/* StateSpaceModel._build_precision (state_space_model.py:431-483): out_diag [B,T,D,D] (full
+ * symmetric blocks), out_sub [B,T-1,D,D].  With h != NULL the likelihood precision H^T R^-1 H of
+ * BaseKalmanFilter._k_inv_post (kalman_filter.py:85-101) is added in the same pass:
+ *   h [h_batch,T,m,D] (h_batch = 1 or B), r_inv [r_steps,m,m] (r_steps = 1 or T). */
+int mf_ssm_build_precision(int dtype, const void* chol_p0, const void* a, const void* chol_q,
+                           const void* h, const void* r_inv, void* out_diag, void* out_sub,
+                           int64_t B, int64_t T, int64_t D, int64_t m, int64_t h_batch,
+                           int64_t r_steps, void* stream);
+
+/* The affine recurrence behind marginal_means (state_space_model.py:231-251) and sample
+ * (:298-324), i.e. a_inv_block.solve(.) (:278-296):
+ *   x_0 = mu0 + chol_p0 eps_0,   x_k = a_{k-1} x_{k-1} + b_{k-1} + chol_q_{k-1} eps_k
+ * eps [n,T,D] standard-normal draws, or NULL for the means.  out [n,T,D]; trajectory c uses SSM
+ * chain c % Bm (leading sample dims). */
+int mf_ssm_affine_scan(int dtype, const void* mu0, const void* chol_p0, const void* a,
+                       const void* b, const void* chol_q, const void* eps, void* out, int64_t n,
+                       int64_t Bm, int64_t T, int64_t D, void* stream);
+
+/* marginal_means / marginal_covariances / covariance_blocks / subsequent_covariances
+ * (state_space_model.py:231-275,326-341) in one forward sweep:  any of out_mean [B,T,D],
+ * out_cov [B,T,D,D], out_sub [B,T-1,D,D] (= a_k Sigma_kk) may be NULL. */
+int mf_ssm_marginals(int dtype, const void* mu0, const void* chol_p0, const void* a, const void* b,
+                     const void* chol_q, void* out_mean, void* out_cov, void* out_sub, int64_t B,
+                     int64_t T, int64_t D, void* stream);
+
+/* StateSpaceModel.log_pdf (state_space_model.py:485-526): states [n,T,D] -> out [n]; trajectory c
+ * is scored under SSM chain c % Bm. */
+int mf_ssm_log_pdf(int dtype, const void* mu0, const void* chol_p0, const void* a, const void* b,
+                   const void* chol_q, const void* states, void* out, int64_t n, int64_t Bm,
+                   int64_t T, int64_t D, void* stream);
+
+/* StateSpaceModel.kl_divergence (state_space_model.py:528-593): KL(q || p) -> out [B]. */
+int mf_ssm_kl_divergence(int dtype, const void* q_mu0, const void* q_chol_p0, const void* q_a,
+                         const void* q_b, const void* q_chol_q, const void* p_mu0,
+                         const void* p_chol_p0, const void* p_a, const void* p_b,
+                         const void* p_chol_q, void* out, int64_t B, int64_t T, int64_t D,
+                         void* stream);
+
+/* state_space_model_from_covariances.cholesky_or_zero (state_space_model.py:634-656): Cholesky of
+ * n blocks [n,D,D]; all-zero blocks map to zero.  info (one int32, may be NULL) receives 1 + the
+ * largest index of a block that is not positive definite, 0 if none. */
+int mf_block_cholesky_or_zero(int dtype, const void* cov, void* out, int32_t* info, int64_t n,
+                              int64_t D, void* stream);
+
+/* out_k = chol((L_k L_k^T)^-1) for n lower factors [n,D,D]
+ * (posterior_state_space_model, kalman_filter.py:170-174). */
+int mf_block_chol_of_inverse(int dtype, const void* chol, void* out, int64_t n, int64_t D,
+                             void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kalman filter (markovflow/kalman_filter.py)
+ *   h [h_batch,T,m,D] emission matrices (h_batch = 1 or B), obs [B,T,m],
+ *   chol_r [r_steps,m,m] Cholesky factor(s) of the observation covariance (r_steps = 1:
+ *   KalmanFilter, kalman_filter.py:301-348; r_steps = T: KalmanFilterWithSites :436-497).
+ *   m <= 4.  With m = 1 an infinite chol_r entry marks a step without observation
+ *   (KalmanFilterWithSparseSites :500-626).
+ * ------------------------------------------------------------------------------------------- */
+
+/* Scratch needed by the parallel-in-time path for B chains of T steps (bytes; 0 on bad input). */
+size_t mf_kalman_workspace_bytes(int dtype, int64_t B, int64_t T, int64_t D);
+
+/* BaseKalmanFilter.log_likelihood (kalman_filter.py:184-255), per chain: out [B] (the reference
+ * returns their sum).  Many chains: one thread per chain.  Few long chains (and a workspace of at
+ * least mf_kalman_workspace_bytes): parallel-in-time scan.  workspace may be NULL. */
+int mf_kalman_log_likelihood(int dtype, const void* mu0, const void* chol_p0, const void* a,
+                             const void* b, const void* chol_q, const void* h, const void* obs,
+                             const void* chol_r, void* out, int64_t B, int64_t T, int64_t D,
+                             int64_t m, int64_t h_batch, int64_t r_steps, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
+/* Time-sharded evaluation of ONE long series over several GPUs (each rank holds a contiguous
+ * segment of T local steps).  first_is_initial = 1: the segment starts at the prior (mu0, chol_p0)
+ * and a/b/chol_q hold T-1 transitions; first_is_initial = 0: a/b/chol_q hold T transitions, a[k]
+ * leading INTO local step k (mu0/chol_p0 unused).
+ *   1. mf_kalman_segment_summary    -> out_elem [B, 3D^2+2D]: the segment's scan element
+ *      (A, b, C, eta, J) (Sarkka & Garcia-Fernandez 2021); leaves per-thread summaries in workspace
+ *   2. all-gather the elements over ranks (NCCL), mf_kalman_fold_elements joins those of the
+ *      earlier ranks: elems [n,B,3D^2+2D] -> out [B,3D^2+2D]
+ *   3. mf_kalman_log_likelihood_seeded  -> out [B]: this segment's share of the log-likelihood,
+ *      given prefix_elem (NULL on the first rank); summaries_valid = 1 reuses step 1's workspace. */
+int mf_kalman_segment_summary(int dtype, const void* mu0, const void* chol_p0, const void* a,
+                              const void* b, const void* chol_q, const void* h, const void* obs,
+                              const void* chol_r, void* out_elem, int64_t B, int64_t T, int64_t D,
+                              int64_t m, int64_t h_batch, int64_t r_steps, int first_is_initial,
+                              void* workspace, size_t workspace_bytes, void* stream);
+int mf_kalman_fold_elements(int dtype, const void* elems, void* out, int64_t n, int64_t B,
+                            int64_t D, void* stream);
+int mf_kalman_log_likelihood_seeded(int dtype, const void* mu0, const void* chol_p0, const void* a,
+                                    const void* b, const void* chol_q, const void* h,
+                                    const void* obs, const void* chol_r, const void* prefix_elem,
+                                    void* out, int64_t B, int64_t T, int64_t D, int64_t m,
+                                    int64_t h_batch, int64_t r_steps, int first_is_initial,
+                                    int summaries_valid, void* workspace, size_t workspace_bytes,
+                                    void* stream);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,22 @@ from .block_tri_diag import (
     SymmetricBlockTriDiagonal,
 )
 from .config import set_check_numerics
+from .emission_model import EmissionModel
+from .gauss_markov import GaussMarkovDistribution, check_compatible
+from .kalman_filter import (
+    BaseKalmanFilter,
+    GaussianSites,
+    KalmanFilter,
+    KalmanFilterWithSites,
+    KalmanFilterWithSparseSites,
+    UnivariateGaussianSitesNat,
+    kalman_log_likelihood,
+)
+from .state_space_model import (
+    StateSpaceModel,
+    cholesky_or_zero,
+    state_space_model_from_covariances,
+)
 
 __all__ = [
     "BlockTriDiagonal",
@@ -15,4 +31,17 @@ __all__ = [
     "CholeskyError",
     "MarkovflowB200Error",
     "set_check_numerics",
+    "EmissionModel",
+    "GaussMarkovDistribution",
+    "check_compatible",
+    "BaseKalmanFilter",
+    "GaussianSites",
+    "KalmanFilter",
+    "KalmanFilterWithSites",
+    "KalmanFilterWithSparseSites",
+    "UnivariateGaussianSitesNat",
+    "kalman_log_likelihood",
+    "StateSpaceModel",
+    "cholesky_or_zero",
+    "state_space_model_from_covariances",
 ]

@@ -143,7 +143,7 @@ class BlockTriDiagonal(abc.ABC):
         return dense
 
     # -- right-hand-side broadcasting (reference :239-287) -------------------------------------
-    def _prepare_right(self, right):
+    def _prepare_right(self, right, skip_diag: bool = False):
         right = as_torch(right, self._diag.device)
         require_cuda(right, "right")
         t, d = self.outer_dim, self.inner_dim
@@ -166,7 +166,7 @@ class BlockTriDiagonal(abc.ABC):
             if sub is not None:
                 sub = sub.expand(tuple(mat_b) + sub.shape[-3:])
         bm = _prod(mat_b)
-        diag = diag.reshape(bm, t, d, d).contiguous()
+        diag = None if skip_diag else diag.reshape(bm, t, d, d).contiguous()
         if sub is not None:
             sub = sub.reshape(bm, t - 1, d, d).contiguous()
         right = right.expand(tuple(fb) + (t, d)).reshape(_prod(fb), t, d).contiguous()
@@ -204,8 +204,25 @@ class BlockTriDiagonal(abc.ABC):
 class LowerTriangularBlockTriDiagonal(BlockTriDiagonal):
     """Lower-triangular block-bidiagonal matrix (reference ``block_tri_diag.py:291-380``)."""
 
-    def __init__(self, diagonal, sub_diagonal=None) -> None:
+    def __init__(self, diagonal, sub_diagonal=None, unit_diagonal: bool = False) -> None:
         super().__init__(diagonal, symmetric=False, sub_diagonal=sub_diagonal)
+        # unit_diagonal: the diagonal blocks are identities (``a_inv_block``); ``solve`` then skips
+        # reading them (``diagonal`` may be an expanded, unmaterialised view)
+        self._unit_diagonal = bool(unit_diagonal)
+
+    def cholesky_of_block_inverses(self) -> torch.Tensor:
+        """``chol((L_k L_kᵀ)⁻¹)`` for every diagonal block ``L_k`` (``kalman_filter.py:170-174``)."""
+        require_cuda(self._diag, "block diagonal")
+        d = self.inner_dim
+        flat = self._diag.reshape(-1, d, d).contiguous()
+        out = torch.empty_like(flat)
+        check(
+            _lib.lib().mf_block_chol_of_inverse(
+                dtype_code(flat.dtype), ptr(flat), ptr(out), i64(flat.shape[0]), i64(d),
+                current_stream()),
+            "mf_block_chol_of_inverse",
+        )
+        return out.reshape(self._diag.shape)
 
     def block_diagonal_of_inverse(self) -> torch.Tensor:
         """Block diagonal of ``(L Lᵀ)⁻¹`` (reference :318-337)."""
@@ -227,12 +244,12 @@ class LowerTriangularBlockTriDiagonal(BlockTriDiagonal):
 
     def solve(self, right, transpose_left: bool = False) -> torch.Tensor:
         """``L⁻¹ x`` or ``L⁻ᵀ x`` (reference :339-351)."""
-        diag, sub, rhs, fb, bm = self._prepare_right(right)
+        diag, sub, rhs, fb, bm = self._prepare_right(right, skip_diag=self._unit_diagonal)
         t, d = self.outer_dim, self.inner_dim
         out = torch.empty_like(rhs)
         check(
             _lib.lib().mf_btd_solve(
-                dtype_code(diag.dtype), ptr(diag), ptr(sub), ptr(rhs), ptr(out), i64(rhs.shape[0]),
+                dtype_code(rhs.dtype), ptr(diag), ptr(sub), ptr(rhs), ptr(out), i64(rhs.shape[0]),
                 i64(bm), i64(t), i64(d), int(bool(transpose_left)), current_stream(),
             ),
             "mf_btd_solve",
@@ -324,6 +341,6 @@ class SymmetricBlockTriDiagonal(BlockTriDiagonal):
         bs = tuple(self.batch_shape)
         eye = torch.eye(d, dtype=diag.dtype, device=diag.device).expand(bs + (t, d, d))
         return (
-            LowerTriangularBlockTriDiagonal(eye, out_u.reshape(bs + (t - 1, d, d))),
+            LowerTriangularBlockTriDiagonal(eye, out_u.reshape(bs + (t - 1, d, d)), unit_diagonal=True),
             LowerTriangularBlockTriDiagonal(out_cd.reshape(bs + (t, d, d))),
         )

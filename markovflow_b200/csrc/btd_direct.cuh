@@ -86,7 +86,7 @@ btd_solve_direct_kernel(const T* __restrict__ ld, const T* __restrict__ ls,
   if (c >= n_rhs) return;
   constexpr int DD = D * D;
   const int64_t cm = c % Bm;
-  const T* lp = ld + cm * Tn * DD;
+  const T* lp = ld ? ld + cm * Tn * DD : nullptr;
   const T* sp = ls ? ls + cm * (Tn - 1) * DD : nullptr;
   const T* rp = rhs + c * Tn * D;
   T* op = out + c * Tn * D;
@@ -95,30 +95,34 @@ btd_solve_direct_kernel(const T* __restrict__ ld, const T* __restrict__ ls,
   for (int i = 0; i < D; ++i) x[i] = T(0);
   if (!transpose) {
     for (int64_t k = 0; k < Tn; ++k) {
-      load_vec<T, DD>(L, lp + k * DD);
       load_vec<T, D>(r, rp + k * D);
       if (sp && k > 0) {
         load_vec<T, DD>(A, sp + (k - 1) * DD);
         gemv_sub<T, D>(r, A, x);
       }
+      if (ld) {  // ld == nullptr: identity diagonal blocks
+        load_vec<T, DD>(L, lp + k * DD);
 #pragma unroll
-      for (int j = 0; j < D; ++j) rinv[j] = Num<T>::rcp(L[j * D + j]);
-      trsv_lower<T, D>(L, rinv, r);
+        for (int j = 0; j < D; ++j) rinv[j] = Num<T>::rcp(L[j * D + j]);
+        trsv_lower<T, D>(L, rinv, r);
+      }
 #pragma unroll
       for (int i = 0; i < D; ++i) x[i] = r[i];
       store_vec<T, D>(op + k * D, x);
     }
   } else {
     for (int64_t k = Tn - 1; k >= 0; --k) {
-      load_vec<T, DD>(L, lp + k * DD);
       load_vec<T, D>(r, rp + k * D);
       if (sp && k + 1 < Tn) {
         load_vec<T, DD>(A, sp + k * DD);
         gemv_t_sub<T, D>(r, A, x);
       }
+      if (ld) {
+        load_vec<T, DD>(L, lp + k * DD);
 #pragma unroll
-      for (int j = 0; j < D; ++j) rinv[j] = Num<T>::rcp(L[j * D + j]);
-      trsv_lower_t<T, D>(L, rinv, r);
+        for (int j = 0; j < D; ++j) rinv[j] = Num<T>::rcp(L[j * D + j]);
+        trsv_lower_t<T, D>(L, rinv, r);
+      }
 #pragma unroll
       for (int i = 0; i < D; ++i) x[i] = r[i];
       store_vec<T, D>(op + k * D, x);

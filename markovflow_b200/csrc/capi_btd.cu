@@ -35,6 +35,11 @@ namespace {
 // 2 cp.async-staged),
 // 1 = steps per shared-memory stage for the staged sweep (0 auto).
 int g_tuning[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+}  // namespace
+namespace mf {
+int tuning(int knob) { return (knob >= 0 && knob < 8) ? g_tuning[knob] : 0; }
+}  // namespace mf
+namespace {
 
 constexpr int kSmemBudget = 232448 - 1536;  // 227 KB opt-in maximum minus barrier/alignment slack
 
@@ -167,7 +172,7 @@ int mf_btd_solve(int dtype, const void* ld, const void* ls, const void* rhs, voi
                  int64_t n_rhs, int64_t Bm, int64_t T, int64_t D, int transpose, void* stream) {
   if (n_rhs < 0 || Bm < 1 || T < 1 || D < 1) return MF_ERR_BAD_ARG;
   if (n_rhs == 0) return MF_OK;
-  if (!ld || !rhs || !out) return MF_ERR_BAD_ARG;
+  if (!rhs || !out) return MF_ERR_BAD_ARG;  // ld == NULL: identity diagonal blocks
   if (T == 1) ls = nullptr;
   cudaStream_t s = (cudaStream_t)stream;
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {

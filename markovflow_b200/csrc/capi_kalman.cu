@@ -1,0 +1,215 @@
+// C-ABI entry points for the Kalman log-likelihood (include/markovflow_b200.h).
+#include "dispatch.cuh"
+#include "kalman_kernels.cuh"
+
+using namespace mf;
+
+namespace {
+
+struct Plan {
+  bool pscan;
+  int64_t P, L;
+};
+
+// Few long chains -> parallel-in-time (P segments of L steps per chain); many chains -> one thread
+// per chain.  tuning knob 2: 0 auto, 1 sequential, 2 parallel-in-time; knob 3: L override.
+Plan make_plan(int64_t B, int64_t T) {
+  const int64_t target = 148 * 256;
+  int64_t pmax = target / (B > 0 ? B : 1);
+  if (pmax < 1) pmax = 1;
+  int64_t L = (T + pmax - 1) / pmax;
+  if (L < 16) L = 16;
+  if (tuning(3) > 0) L = tuning(3);
+  Plan p;
+  p.L = L;
+  p.P = (T + L - 1) / L;
+  p.pscan = p.P >= 4;
+  if (tuning(2) == 1) p.pscan = false;
+  if (tuning(2) == 2) p.pscan = p.P >= 2;
+  return p;
+}
+
+size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+
+struct Workspace {
+  size_t summaries, seeds, partial, total;
+};
+
+Workspace layout(size_t es, int64_t B, int64_t P, int64_t D) {
+  const size_t N = 3 * D * D + 2 * D;
+  Workspace w;
+  w.summaries = 0;
+  w.seeds = align_up(w.summaries + es * B * P * N);
+  w.partial = align_up(w.seeds + es * B * P * (D + D * D));
+  w.total = align_up(w.partial + es * B * P);
+  return w;
+}
+
+template <typename T>
+KalmanArgs<T> make_args(const void* mu0, const void* chol_p0, const void* a, const void* b,
+                        const void* chol_q, const void* h, const void* obs, const void* chol_r,
+                        int64_t B, int64_t Tn, int64_t m, int64_t h_batch, int64_t r_steps,
+                        int first_is_initial) {
+  KalmanArgs<T> g;
+  g.mu0 = (const T*)mu0; g.chol_p0 = (const T*)chol_p0; g.a = (const T*)a; g.b = (const T*)b;
+  g.chol_q = (const T*)chol_q; g.h = (const T*)h; g.obs = (const T*)obs; g.chol_r = (const T*)chol_r;
+  g.B = B; g.Tn = Tn; g.Bh = h_batch; g.Tr = r_steps; g.m = (int)m;
+  g.first_is_initial = first_is_initial;
+  return g;
+}
+
+int check_args(const void* mu0, const void* chol_p0, const void* a, const void* b,
+               const void* chol_q, const void* h, const void* obs, const void* chol_r, int64_t B,
+               int64_t T, int64_t D, int64_t m, int64_t h_batch, int64_t r_steps,
+               int first_is_initial) {
+  if (B < 0 || T < 1 || D < 1 || m < 1) return MF_ERR_BAD_ARG;
+  if (m > kMaxObsDim) return MF_ERR_UNSUPPORTED;
+  if (!h || !obs || !chol_r) return MF_ERR_BAD_ARG;
+  if (first_is_initial && (!mu0 || !chol_p0)) return MF_ERR_BAD_ARG;
+  if ((T - (first_is_initial ? 1 : 0)) > 0 && (!a || !b || !chol_q)) return MF_ERR_BAD_ARG;
+  if ((h_batch != 1 && h_batch != B) || (r_steps != 1 && r_steps != T)) return MF_ERR_BAD_ARG;
+  return MF_OK;
+}
+
+template <int D> struct ScanThreads { static constexpr int value = D <= 3 ? 128 : (D <= 5 ? 64 : (D <= 7 ? 32 : 16)); };
+
+template <typename T, int D, bool M1>
+int run_summaries(const KalmanArgs<T>& g, const Plan& pl, T* summaries, cudaStream_t s) {
+  dim3 grid(grid_for(pl.P, 128), (unsigned)g.B);
+  kalman_segment_summary_kernel<T, D, M1><<<grid, 128, 0, s>>>(g, summaries, pl.P, pl.L);
+  return check_launch();
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t mf_kalman_workspace_bytes(int dtype, int64_t B, int64_t T, int64_t D) {
+  if (B < 1 || T < 1 || D < 1) return 0;
+  const Plan pl = make_plan(B, T);
+  const size_t es = dtype == MF_F64 ? 8 : 4;
+  const size_t N = 3 * D * D + 2 * D;
+  return layout(es, B, pl.P, D).total + align_up(es * B * N);
+}
+
+int mf_kalman_segment_summary(int dtype, const void* mu0, const void* chol_p0, const void* a,
+                              const void* b, const void* chol_q, const void* h, const void* obs,
+                              const void* chol_r, void* out_elem, int64_t B, int64_t T, int64_t D,
+                              int64_t m, int64_t h_batch, int64_t r_steps, int first_is_initial,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  int st = check_args(mu0, chol_p0, a, b, chol_q, h, obs, chol_r, B, T, D, m, h_batch, r_steps,
+                      first_is_initial);
+  if (st != MF_OK) return st;
+  if (B == 0) return MF_OK;
+  if (!out_elem || !workspace || B > 65535) return MF_ERR_BAD_ARG;
+  if (workspace_bytes < mf_kalman_workspace_bytes(dtype, B, T, D)) return MF_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  return dispatch_small(dtype, D, [&](auto tt, auto dd) {
+    using Tp = typename decltype(tt)::type;
+    constexpr int kD = decltype(dd)::value;
+    const Plan pl = make_plan(B, T);
+    const Workspace w = layout(sizeof(Tp), B, pl.P, kD);
+    char* ws = (char*)workspace;
+    const auto g = make_args<Tp>(mu0, chol_p0, a, b, chol_q, h, obs, chol_r, B, T, m, h_batch,
+                                 r_steps, first_is_initial);
+    int rc = (m == 1) ? run_summaries<Tp, kD, true>(g, pl, (Tp*)(ws + w.summaries), s)
+                      : run_summaries<Tp, kD, false>(g, pl, (Tp*)(ws + w.summaries), s);
+    if (rc != MF_OK) return rc;
+    kalman_summary_scan_kernel<Tp, kD, ScanThreads<kD>::value>
+        <<<(unsigned)B, ScanThreads<kD>::value, 0, s>>>((const Tp*)(ws + w.summaries), nullptr,
+                                                       (Tp*)(ws + w.seeds), (Tp*)out_elem, pl.P);
+    return check_launch();
+  });
+}
+
+int mf_kalman_fold_elements(int dtype, const void* elems, void* out, int64_t n, int64_t B,
+                            int64_t D, void* stream) {
+  if (n < 1 || B < 0 || D < 1 || !elems || !out) return MF_ERR_BAD_ARG;
+  if (B == 0) return MF_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  return dispatch_small(dtype, D, [&](auto tt, auto dd) {
+    using Tp = typename decltype(tt)::type;
+    constexpr int kD = decltype(dd)::value;
+    kalman_fold_elements_kernel<Tp, kD><<<grid_for(B, 32), 32, 0, s>>>((const Tp*)elems, (Tp*)out, n, B);
+    return check_launch();
+  });
+}
+
+int mf_kalman_log_likelihood_seeded(int dtype, const void* mu0, const void* chol_p0, const void* a,
+                                    const void* b, const void* chol_q, const void* h,
+                                    const void* obs, const void* chol_r, const void* prefix_elem,
+                                    void* out, int64_t B, int64_t T, int64_t D, int64_t m,
+                                    int64_t h_batch, int64_t r_steps, int first_is_initial,
+                                    int summaries_valid, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
+  int st = check_args(mu0, chol_p0, a, b, chol_q, h, obs, chol_r, B, T, D, m, h_batch, r_steps,
+                      first_is_initial);
+  if (st != MF_OK) return st;
+  if (B == 0) return MF_OK;
+  if (!out || !workspace || B > 65535) return MF_ERR_BAD_ARG;
+  if (!first_is_initial && !prefix_elem) return MF_ERR_BAD_ARG;
+  if (workspace_bytes < mf_kalman_workspace_bytes(dtype, B, T, D)) return MF_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  return dispatch_small(dtype, D, [&](auto tt, auto dd) {
+    using Tp = typename decltype(tt)::type;
+    constexpr int kD = decltype(dd)::value;
+    const Plan pl = make_plan(B, T);
+    const Workspace w = layout(sizeof(Tp), B, pl.P, kD);
+    char* ws = (char*)workspace;
+    const auto g = make_args<Tp>(mu0, chol_p0, a, b, chol_q, h, obs, chol_r, B, T, m, h_batch,
+                                 r_steps, first_is_initial);
+    int rc = MF_OK;
+    if (!summaries_valid) {
+      rc = (m == 1) ? run_summaries<Tp, kD, true>(g, pl, (Tp*)(ws + w.summaries), s)
+                    : run_summaries<Tp, kD, false>(g, pl, (Tp*)(ws + w.summaries), s);
+      if (rc != MF_OK) return rc;
+    }
+    kalman_summary_scan_kernel<Tp, kD, ScanThreads<kD>::value>
+        <<<(unsigned)B, ScanThreads<kD>::value, 0, s>>>((const Tp*)(ws + w.summaries),
+                                                       (const Tp*)prefix_elem, (Tp*)(ws + w.seeds),
+                                                       nullptr, pl.P);
+    if ((rc = check_launch()) != MF_OK) return rc;
+    dim3 grid(grid_for(pl.P, 128), (unsigned)B);
+    const int have_prefix = prefix_elem != nullptr;
+    if (m == 1)
+      kalman_seeded_filter_kernel<Tp, kD, true><<<grid, 128, 0, s>>>(
+          g, (const Tp*)(ws + w.seeds), (Tp*)(ws + w.partial), pl.P, pl.L, have_prefix);
+    else
+      kalman_seeded_filter_kernel<Tp, kD, false><<<grid, 128, 0, s>>>(
+          g, (const Tp*)(ws + w.seeds), (Tp*)(ws + w.partial), pl.P, pl.L, have_prefix);
+    if ((rc = check_launch()) != MF_OK) return rc;
+    kalman_partial_sum_kernel<Tp><<<(unsigned)B, 256, 0, s>>>((const Tp*)(ws + w.partial), (Tp*)out, pl.P);
+    return check_launch();
+  });
+}
+
+int mf_kalman_log_likelihood(int dtype, const void* mu0, const void* chol_p0, const void* a,
+                             const void* b, const void* chol_q, const void* h, const void* obs,
+                             const void* chol_r, void* out, int64_t B, int64_t T, int64_t D,
+                             int64_t m, int64_t h_batch, int64_t r_steps, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  int st = check_args(mu0, chol_p0, a, b, chol_q, h, obs, chol_r, B, T, D, m, h_batch, r_steps, 1);
+  if (st != MF_OK) return st;
+  if (B == 0) return MF_OK;
+  if (!out) return MF_ERR_BAD_ARG;
+  const Plan pl = make_plan(B, T);
+  if (pl.pscan && workspace && B <= 65535 &&
+      workspace_bytes >= mf_kalman_workspace_bytes(dtype, B, T, D))
+    return mf_kalman_log_likelihood_seeded(dtype, mu0, chol_p0, a, b, chol_q, h, obs, chol_r,
+                                           nullptr, out, B, T, D, m, h_batch, r_steps, 1, 0,
+                                           workspace, workspace_bytes, stream);
+  cudaStream_t s = (cudaStream_t)stream;
+  return dispatch_small(dtype, D, [&](auto tt, auto dd) {
+    using Tp = typename decltype(tt)::type;
+    constexpr int kD = decltype(dd)::value;
+    const auto g = make_args<Tp>(mu0, chol_p0, a, b, chol_q, h, obs, chol_r, B, T, m, h_batch,
+                                 r_steps, 1);
+    if (m == 1)
+      kalman_loglik_chain_kernel<Tp, kD, true><<<grid_for(B, 32), 32, 0, s>>>(g, (Tp*)out);
+    else
+      kalman_loglik_chain_kernel<Tp, kD, false><<<grid_for(B, 32), 32, 0, s>>>(g, (Tp*)out);
+    return check_launch();
+  });
+}
+
+}  // extern "C"

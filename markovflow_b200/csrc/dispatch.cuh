@@ -14,6 +14,7 @@ template <int N> struct IntTag { static constexpr int value = N; };
 
 void set_last_error(const char* msg);
 int check_launch();  // returns MF_OK or MF_ERR_CUDA after cudaGetLastError()
+int tuning(int knob);  // value set through mf_set_tuning (0 = default)
 
 // Calls f(TypeTag<T>{}, IntTag<D>{}) for dtype in {f32,f64} and 1 <= D <= MF_SMALL_D_MAX.
 template <typename F>

@@ -1,0 +1,190 @@
+"""Multi-GPU partitioning of the hot path (one process per GPU, ``torch.distributed``).
+
+* Batches of independent chains (BASELINE configs 2, 4, 5) are split over ranks with NO data-path
+  collective (``batch_shape`` dims are pure broadcasting, ``block_tri_diag.py:110-115``):
+  :func:`shard_bounds` / :func:`shard_batch`.
+* ONE long series (config 3) is split in time.  Each rank reduces its segment to one scan element
+  (``mf_kalman_segment_summary``), the elements are all-gathered (NCCL over NVLink; 8 x 128 B at
+  D = 2), each rank joins the elements of the earlier ranks into its incoming prefix
+  (``mf_kalman_fold_elements``) and runs its seeded local filter
+  (``mf_kalman_log_likelihood_seeded``); a scalar all-reduce sums the shares.
+
+The compute engine is pluggable so that the host logic (slicing, gather order, fold range) is
+testable on CPU with ``gloo``; the default engine is the CUDA library and there is no other engine
+in this package.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, current_stream, dtype_code, i64, ptr
+
+
+def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced ``[lo, hi)`` of ``n`` units for ``rank`` (first ``n % world`` ranks get
+    one extra)."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("need 0 <= rank < world")
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_batch(t: torch.Tensor, rank: int, world: int, dim: int = 0) -> torch.Tensor:
+    """This rank's slice of a batch of independent chains."""
+    lo, hi = shard_bounds(t.shape[dim], rank, world)
+    return t.narrow(dim, lo, hi - lo)
+
+
+@dataclass
+class TimeSegment:
+    """One rank's contiguous time segment of a (batch of) long series, in the kernels' "incoming
+    transition" convention: ``first`` segments carry ``(mu0, chol_p0)`` and ``T-1`` transitions,
+    later segments carry ``T`` transitions (the first one leads into local step 0)."""
+    first: bool
+    mu0: Optional[torch.Tensor]
+    chol_p0: Optional[torch.Tensor]
+    a: torch.Tensor
+    b: torch.Tensor
+    chol_q: torch.Tensor
+    h: torch.Tensor       # [Bh,Tl,m,D]
+    obs: torch.Tensor     # [B,Tl,m]
+    chol_r: torch.Tensor  # [1 or Tl,m,m]
+
+    @property
+    def num_steps(self) -> int:
+        return int(self.obs.shape[-2])
+
+
+def time_segment(mu0, chol_p0, a, b, chol_q, h, obs, chol_r, rank: int, world: int) -> TimeSegment:
+    """Slice rank ``rank``'s segment out of full-series arrays ``a [B,T-1,D,D]`` ... ``obs [B,T,m]``."""
+    t = int(obs.shape[-2])
+    lo, hi = shard_bounds(t, rank, world)
+    if hi - lo < 1:
+        raise ValueError("every rank needs at least one time step")
+    first = lo == 0
+    tlo = 0 if first else lo - 1  # transition k leads into step k+1
+    thi = hi - 1
+    r = chol_r if chol_r.shape[0] == 1 else chol_r[lo:hi]
+    return TimeSegment(
+        first, mu0 if first else None, chol_p0 if first else None,
+        a[:, tlo:thi].contiguous(), b[:, tlo:thi].contiguous(), chol_q[:, tlo:thi].contiguous(),
+        h[:, lo:hi].contiguous(), obs[:, lo:hi].contiguous(), r.contiguous())
+
+
+class CudaKalmanEngine:
+    """The three C-ABI calls of the time-sharded protocol (``include/markovflow_b200.h``)."""
+
+    def __init__(self) -> None:
+        self._ws = None
+        self._ws_bytes = 0
+
+    @staticmethod
+    def elem_size(d: int) -> int:
+        return 3 * d * d + 2 * d
+
+    def _dims(self, seg: TimeSegment):
+        bsz, tl, m = seg.obs.shape
+        d = int(seg.a.shape[-1])
+        return int(bsz), int(tl), int(m), d, int(seg.h.shape[0]), int(seg.chol_r.shape[0])
+
+    def _workspace(self, seg: TimeSegment):
+        bsz, tl, m, d, _, _ = self._dims(seg)
+        lib = _lib.lib()
+        lib.mf_kalman_workspace_bytes.restype = _lib.ctypes.c_size_t
+        n = int(lib.mf_kalman_workspace_bytes(dtype_code(seg.obs.dtype), i64(bsz), i64(tl), i64(d)))
+        if self._ws is None or self._ws_bytes < n or self._ws.device != seg.obs.device:
+            self._ws = torch.empty(max(n, 1), dtype=torch.uint8, device=seg.obs.device)
+            self._ws_bytes = n
+        return self._ws, n
+
+    def segment_summary(self, seg: TimeSegment) -> torch.Tensor:
+        bsz, tl, m, d, hb, rs = self._dims(seg)
+        ws, n = self._workspace(seg)
+        out = torch.empty(bsz, self.elem_size(d), dtype=seg.obs.dtype, device=seg.obs.device)
+        check(
+            _lib.lib().mf_kalman_segment_summary(
+                dtype_code(seg.obs.dtype), ptr(seg.mu0), ptr(seg.chol_p0), ptr(seg.a), ptr(seg.b),
+                ptr(seg.chol_q), ptr(seg.h), ptr(seg.obs), ptr(seg.chol_r), ptr(out), i64(bsz),
+                i64(tl), i64(d), i64(m), i64(hb), i64(rs), int(seg.first), ptr(ws),
+                _lib.ctypes.c_size_t(n), current_stream()),
+            "mf_kalman_segment_summary",
+        )
+        return out
+
+    def fold(self, elems: torch.Tensor, d: int) -> torch.Tensor:
+        """``elems [n,B,N]`` (time order) -> their join ``[B,N]``."""
+        n, bsz, _ = elems.shape
+        elems = elems.contiguous()
+        out = torch.empty(bsz, elems.shape[-1], dtype=elems.dtype, device=elems.device)
+        check(
+            _lib.lib().mf_kalman_fold_elements(
+                dtype_code(elems.dtype), ptr(elems), ptr(out), i64(n), i64(bsz), i64(d),
+                current_stream()),
+            "mf_kalman_fold_elements",
+        )
+        return out
+
+    def seeded_log_likelihood(self, seg: TimeSegment, prefix: Optional[torch.Tensor],
+                              summaries_valid: bool) -> torch.Tensor:
+        bsz, tl, m, d, hb, rs = self._dims(seg)
+        ws, n = self._workspace(seg)
+        out = torch.empty(bsz, dtype=seg.obs.dtype, device=seg.obs.device)
+        check(
+            _lib.lib().mf_kalman_log_likelihood_seeded(
+                dtype_code(seg.obs.dtype), ptr(seg.mu0), ptr(seg.chol_p0), ptr(seg.a), ptr(seg.b),
+                ptr(seg.chol_q), ptr(seg.h), ptr(seg.obs), ptr(seg.chol_r), ptr(prefix), ptr(out),
+                i64(bsz), i64(tl), i64(d), i64(m), i64(hb), i64(rs), int(seg.first),
+                int(bool(summaries_valid)), ptr(ws), _lib.ctypes.c_size_t(n), current_stream()),
+            "mf_kalman_log_likelihood_seeded",
+        )
+        return out
+
+
+def time_sharded_log_likelihood(seg: TimeSegment, group=None, engine=None) -> torch.Tensor:
+    """Per-chain log-likelihood ``[B]`` of the whole series, computed collectively: every rank
+    passes its own :class:`TimeSegment` (rank order == time order)."""
+    import torch.distributed as dist
+
+    engine = engine or CudaKalmanEngine()
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if seg.first != (rank == 0):
+        raise ValueError("rank 0 (and only rank 0) must hold the segment that starts at the prior")
+    d = int(seg.a.shape[-1])
+    elem = engine.segment_summary(seg)
+    prefix = None
+    if world > 1:
+        gathered = [torch.empty_like(elem) for _ in range(world)]
+        dist.all_gather(gathered, elem, group=group)
+        if rank > 0:
+            prefix = engine.fold(torch.stack(gathered[:rank]), d)
+    share = engine.seeded_log_likelihood(seg, prefix, summaries_valid=True)
+    if world > 1:
+        dist.all_reduce(share, op=dist.ReduceOp.SUM, group=group)
+    return share
+
+
+def time_sharded_log_likelihood_local(ssm, emission_matrix, observations, chol_obs_covariance,
+                                      world: int, engine=None) -> torch.Tensor:
+    """The same protocol executed for ``world`` virtual ranks on ONE device (validation, and the
+    single-GPU leg of the scaling bench): returns the per-chain log-likelihood ``[batch]``."""
+    engine = engine or CudaKalmanEngine()
+    mu0, l0, a, b, lq, bsz, t, d = ssm._flat()
+    m = int(emission_matrix.shape[-2])
+    h = emission_matrix.reshape(-1, t, m, d)
+    y = observations.reshape(bsz, t, m)
+    lr = chol_obs_covariance.reshape(-1, m, m)
+    segs: List[TimeSegment] = [time_segment(mu0, l0, a, b, lq, h, y, lr, r, world) for r in range(world)]
+    engines = [engine.__class__() for _ in segs]  # one workspace per virtual rank
+    elems = [e.segment_summary(s) for e, s in zip(engines, segs)]
+    total = None
+    for r, (e, s) in enumerate(zip(engines, segs)):
+        prefix = e.fold(torch.stack(elems[:r]), d) if r > 0 else None
+        share = e.seeded_log_likelihood(s, prefix, summaries_valid=True)
+        total = share if total is None else total + share
+    return total.reshape(tuple(ssm.batch_shape))

@@ -1,0 +1,342 @@
+"""GPU parity of ``markovflow_b200.StateSpaceModel`` and the Kalman filters (CUDA kernels through
+the C ABI) against the numpy oracle, the golden vectors produced by the reference's own
+``NumpyKalmanFilter`` (``tests/golden``) and dense Gaussians.  Mirrors the reference's
+``tests/unit/test_state_space_model.py``, ``tests/unit/test_sampling_from_ssm.py``,
+``tests/integration/test_kalman_filter.py`` and ``test_kalman_filter_with_sites.py``.
+float64 tolerance 1e-10 (max-abs relative), float32 1e-4."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_oracle as O
+from tests.helpers import dense_ssm_mean_cov, max_rel_err, random_ssm_arrays
+from tests.test_oracle_ssm_kalman import GOLDEN, load_kalman_case
+
+pytestmark = pytest.mark.gpu
+TOL = {torch.float64: 1e-10, torch.float32: 1e-4}
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def tt(x, dtype=torch.float64):
+    return torch.as_tensor(np.ascontiguousarray(x), device=dev()).to(dtype)
+
+
+def npy(x):
+    return x.detach().cpu().numpy().astype(np.float64)
+
+
+def make_ssm(arrays, dtype=torch.float64):
+    from markovflow_b200 import StateSpaceModel
+
+    return StateSpaceModel(*(tt(a, dtype) for a in arrays))
+
+
+def to_gpu_ssm(ssm: O.SSM, dtype=torch.float64):
+    return make_ssm((ssm.mu0, ssm.chol_p0, ssm.a_s, ssm.b_s, ssm.chol_q_s), dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# StateSpaceModel
+# ------------------------------------------------------------------------------------------------
+
+def test_rejects_bad_shapes():
+    from markovflow_b200 import StateSpaceModel
+
+    mu0, l0, a, b, lq = (tt(x) for x in random_ssm_arrays((2,), 3, 2))
+    with pytest.raises(ValueError):
+        StateSpaceModel(mu0, l0, a[:, :0], b[:, :0], lq[:, :0])  # num_transitions = 0
+    with pytest.raises(ValueError):
+        StateSpaceModel(mu0[0], l0, a, b, lq)
+    with pytest.raises(ValueError):
+        StateSpaceModel(mu0, l0, a, b[:, :2], lq)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_precision_means_covariances_logdet(batch_shape, state_dim, transitions, dtype):
+    arrays = random_ssm_arrays(batch_shape, transitions, state_dim)
+    ref = O.SSM(*arrays)
+    ssm = make_ssm(arrays, dtype)
+    tol = TOL[dtype]
+    prec = ssm.precision
+    o_d, o_s = O.ssm_build_precision(ref)
+    assert max_rel_err(npy(prec.block_diagonal), o_d) < tol
+    assert max_rel_err(npy(prec.block_sub_diagonal), o_s) < tol
+    mean, cov = ssm.marginals
+    assert max_rel_err(npy(mean), O.ssm_marginal_means(ref)) < tol
+    assert max_rel_err(npy(ssm.marginal_means), O.ssm_marginal_means(ref)) < tol
+    o_cov = O.ssm_marginal_covariances(ref)
+    assert max_rel_err(npy(cov), o_cov) < (1e-8 if dtype == torch.float64 else 1e-3)
+    cov2, sub = ssm.covariance_blocks()
+    assert max_rel_err(npy(sub), O.ssm_subsequent_covariances(ref, o_cov)) < (1e-8 if dtype == torch.float64 else 1e-3)
+    assert max_rel_err(npy(ssm.subsequent_covariances(cov2)), npy(sub)) < tol
+    assert max_rel_err(npy(ssm.log_det_precision()), O.ssm_log_det_precision(ref)) < tol
+    assert tuple(ssm.batch_shape) == batch_shape and ssm.state_dim == state_dim
+    assert ssm.num_transitions == transitions
+
+
+def test_covariances_match_dense_propagation(state_dim, transitions):
+    """The forward recursion is at least as accurate as the reference route (precision ->
+    Cholesky -> inverse subset): compare both with the dense joint covariance."""
+    arrays = random_ssm_arrays((), transitions, state_dim)
+    _, dense_cov = dense_ssm_mean_cov(*arrays)
+    d, t = state_dim, transitions + 1
+    want = np.stack([dense_cov[k * d:(k + 1) * d, k * d:(k + 1) * d] for k in range(t)])
+    cov = npy(make_ssm(arrays).marginal_covariances)
+    assert max_rel_err(cov, want) < 1e-12
+
+
+@pytest.mark.parametrize("sample_shape", [(), (4,), (2, 3)])
+def test_log_pdf(batch_shape, state_dim, transitions, sample_shape):
+    arrays = random_ssm_arrays(batch_shape, transitions, state_dim)
+    ref = O.SSM(*arrays)
+    ssm = make_ssm(arrays)
+    states = np.random.normal(size=sample_shape + batch_shape + (transitions + 1, state_dim))
+    got = npy(ssm.log_pdf(tt(states)))
+    want = O.ssm_log_pdf(ref, states)
+    assert got.shape == sample_shape + batch_shape
+    assert max_rel_err(got, want) < 1e-10
+
+
+def test_log_pdf_long_chain_uses_segments():
+    arrays = random_ssm_arrays((2,), 9000, 2, scale_a=0.3)
+    states = np.random.normal(size=(3, 2, 9001, 2))
+    got = npy(make_ssm(arrays).log_pdf(tt(states)))
+    assert max_rel_err(got, O.ssm_log_pdf(O.SSM(*arrays), states)) < 1e-10
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_kl_divergence(batch_shape, state_dim, transitions, dtype):
+    q_arr = random_ssm_arrays(batch_shape, transitions, state_dim)
+    p_arr = random_ssm_arrays(batch_shape, transitions, state_dim)
+    want = O.ssm_kl_divergence(O.SSM(*q_arr), O.SSM(*p_arr))
+    got = npy(make_ssm(q_arr, dtype).kl_divergence(make_ssm(p_arr, dtype)))
+    assert got.shape == batch_shape
+    assert max_rel_err(got, want) < (1e-9 if dtype == torch.float64 else 1e-3)
+    same = npy(make_ssm(q_arr, dtype).kl_divergence(make_ssm(q_arr, dtype)))
+    assert np.max(np.abs(same)) < (1e-10 if dtype == torch.float64 else 1e-3)
+
+
+@pytest.mark.parametrize("sample_shape", [(5,), (2, 2), ()])
+def test_sample_from_epsilons(batch_shape, state_dim, transitions, sample_shape):
+    arrays = random_ssm_arrays(batch_shape, transitions, state_dim)
+    eps = np.random.normal(size=sample_shape + batch_shape + (transitions + 1, state_dim))
+    got = npy(make_ssm(arrays).sample_from_epsilons(tt(eps)))
+    want = O.ssm_sample_from_epsilons(O.SSM(*arrays), eps)
+    assert max_rel_err(got, want) < 1e-10
+
+
+def test_sample_shapes_and_moments():
+    """tests/unit/test_sampling_from_ssm.py: shapes, and sample moments approach the marginals."""
+    arrays = random_ssm_arrays((2,), 4, 2)
+    ssm = make_ssm(arrays)
+    assert tuple(ssm.sample((3, 2)).shape) == (3, 2, 2, 5, 2)
+    assert tuple(ssm.sample(0).shape) == (0, 2, 5, 2)
+    gen = torch.Generator(device=dev()).manual_seed(1)
+    s = npy(ssm.sample(20000, generator=gen))
+    mean, cov = (npy(x) for x in ssm.marginals)
+    assert np.max(np.abs(s.mean(0) - mean)) < 0.05 * max(1.0, np.abs(mean).max())
+    emp = np.einsum("sbti,sbtj->btij", s - mean, s - mean) / s.shape[0]
+    assert np.max(np.abs(emp - cov)) < 0.08 * np.abs(cov).max()
+
+
+def test_state_space_model_from_covariances_with_zero_blocks():
+    from markovflow_b200 import state_space_model_from_covariances
+
+    mu0, l0, a, b, lq = random_ssm_arrays((3,), 4, 3)
+    p0 = l0 @ np.swapaxes(l0, -1, -2)
+    q = lq @ np.swapaxes(lq, -1, -2)
+    q[1, 2] = 0.0
+    p0[2] = 0.0
+    ssm = state_space_model_from_covariances(tt(mu0), tt(p0), tt(a), tt(b), tt(q))
+    ref = O.ssm_from_covariances(mu0, p0, a, b, q)
+    assert max_rel_err(npy(ssm.cholesky_process_covariances), ref.chol_q_s) < 1e-12
+    assert max_rel_err(npy(ssm.cholesky_initial_covariance), ref.chol_p0) < 1e-12
+    assert max_rel_err(npy(ssm.marginal_means), O.ssm_marginal_means(ref)) < 1e-12
+
+
+def test_normalizer_and_a_inv_block():
+    arrays = random_ssm_arrays((2,), 5, 3)
+    ref = O.SSM(*arrays)
+    ssm = make_ssm(arrays)
+    mu = O.ssm_marginal_means(ref)
+    pd, ps = O.ssm_build_precision(ref)
+    maha = np.sum(mu * O.btd_dense_mult(pd, ps, mu, symmetric=True), axis=(-1, -2))
+    want = 0.5 * (6 * 3 * np.log(2 * np.pi) - O.ssm_log_det_precision(ref) + maha)
+    assert max_rel_err(npy(ssm.normalizer()), want) < 1e-10
+    c = np.random.normal(size=(4, 2, 6, 3))
+    got = npy(ssm.a_inv_block.solve(tt(c)))
+    assert max_rel_err(got, O.affine_recurrence(ref.a_s, c)) < 1e-10
+    got_t = npy(ssm.a_inv_block.solve(tt(c), transpose_left=True))
+    eye = np.broadcast_to(np.eye(3), (2, 6, 3, 3))
+    assert max_rel_err(got_t, O.btd_solve(eye, -ref.a_s, c, transpose_left=True)) < 1e-10
+
+
+# ------------------------------------------------------------------------------------------------
+# Kalman filter: golden vectors of the reference's own numpy filter
+# ------------------------------------------------------------------------------------------------
+
+def _filter_from_golden(tag, dtype=torch.float64):
+    from markovflow_b200 import EmissionModel, KalmanFilter
+
+    g, ssm, h = load_kalman_case(os.path.join(GOLDEN, f"kalman_{tag}.npz"))
+    kf = KalmanFilter(to_gpu_ssm(ssm, dtype), EmissionModel(tt(h, dtype)), tt(g["y"], dtype),
+                      tt(g["chol_R"], dtype))
+    return g, ssm, h, kf
+
+
+@pytest.mark.parametrize("tag", ["b3", "b0", "b21", "d5m1"])
+def test_log_likelihood_matches_reference_kalman_filter(tag):
+    """tests/integration/test_kalman_filter.py:131-139."""
+    g, ssm, h, kf = _filter_from_golden(tag)
+    assert max_rel_err(npy(kf.log_likelihood()), np.sum(g["log_liks"])) < 1e-10
+    per_chain = npy(kf.log_likelihood_per_chain())
+    assert max_rel_err(per_chain, np.sum(g["log_liks"], axis=-1)) < 1e-10
+    # the SpInGP restatement itself carries ~1e-9 of rounding on these ill-conditioned golden
+    # cases (it differs from the reference's numpy filter by that much); the filter form does not
+    want = O.kalman_log_likelihood(ssm, h, g["y"], O._r_inv_from_chol(g["chol_R"]), per_chain=True)
+    assert max_rel_err(per_chain, want) < 1e-8
+
+
+@pytest.mark.parametrize("tag", ["b3", "b0"])
+def test_log_likelihood_float32(tag):
+    g, _, _, kf = _filter_from_golden(tag, torch.float32)
+    assert max_rel_err(npy(kf.log_likelihood()), np.sum(g["log_liks"])) < 1e-4
+
+
+@pytest.mark.parametrize("tag", ["b3", "b0", "b21", "d5m1"])
+def test_posterior_ssm_matches_reference_rts_smoother(tag):
+    """tests/integration/test_kalman_filter.py:105-128."""
+    g, ssm, h, kf = _filter_from_golden(tag)
+    post = kf.posterior_state_space_model()
+    mean, cov = post.marginals
+    assert max_rel_err(npy(mean), g["smooth_means"]) < 1e-9
+    assert max_rel_err(npy(cov), np.broadcast_to(g["smooth_covs"], npy(cov).shape)) < 1e-9
+    ref_post = O.kalman_posterior_ssm(ssm, h, g["y"], O._r_inv_from_chol(g["chol_R"]))
+    assert max_rel_err(npy(post.state_transitions), ref_post.a_s) < 1e-10
+    assert max_rel_err(npy(post.state_offsets), ref_post.b_s) < 1e-10
+    assert max_rel_err(npy(post.cholesky_process_covariances), ref_post.chol_q_s) < 1e-10
+    assert max_rel_err(npy(post.initial_mean), ref_post.mu0) < 1e-10
+
+
+def test_sites_log_likelihood_and_posterior_match_reference():
+    """tests/integration/test_kalman_filter_with_sites.py."""
+    from markovflow_b200 import EmissionModel, KalmanFilterWithSites, UnivariateGaussianSitesNat
+
+    g = np.load(os.path.join(GOLDEN, "kalman_sites_t10.npz"))
+    d, t = g["A"].shape[0], g["nat1"].shape[0]
+    ssm = O.SSM(g["mu0"], g["chol_P0"], np.broadcast_to(g["A"], (t - 1, d, d)).copy(),
+                np.broadcast_to(g["b"], (t - 1, d)).copy(), np.broadcast_to(g["chol_Q"], (t - 1, d, d)).copy())
+    h = np.broadcast_to(g["H"], (t, 1, d)).copy()
+    sites = UnivariateGaussianSitesNat(tt(g["nat1"]), tt(g["nat2"]))
+    kf = KalmanFilterWithSites(to_gpu_ssm(ssm), EmissionModel(tt(h)), sites)
+    assert max_rel_err(npy(kf.log_likelihood()), np.sum(g["log_liks"])) < 1e-10
+    mean, cov = kf.posterior_state_space_model().marginals
+    assert max_rel_err(npy(mean), g["smooth_means"]) < 1e-9
+    assert max_rel_err(npy(cov), g["smooth_covs"]) < 1e-9
+
+
+def test_sparse_sites_equal_dense_filter_on_the_data_points():
+    """KalmanFilterWithSparseSites (kalman_filter.py:500-626): grid points without data carry no
+    observation, so the value equals the oracle filter that skips those steps."""
+    from markovflow_b200 import EmissionModel, KalmanFilterWithSparseSites, UnivariateGaussianSitesNat
+
+    rng = np.random.default_rng(11)
+    k = O.Matern32(0.8, 1.2)
+    t = 30
+    tp = np.cumsum(rng.uniform(0.05, 0.3, size=t))
+    ssm, h = k.state_space_model(tp), k.emission_matrix(tp)
+    idx = np.sort(rng.choice(t, size=12, replace=False))
+    prec = rng.uniform(0.5, 2.0, size=(12, 1, 1))
+    y = rng.standard_normal((12, 1))
+    sites = UnivariateGaussianSitesNat(tt(prec[..., 0] * y), tt(-0.5 * prec))
+    kf = KalmanFilterWithSparseSites(to_gpu_ssm(ssm), EmissionModel(tt(h)), sites, t,
+                                     tt(idx[:, None]).long(), tt(y))
+    # oracle: time-varying filter with a huge variance at the grid points without data
+    r = np.full((t, 1, 1), 1e30)
+    r[idx] = 1.0 / prec
+    obs = np.zeros((t, 1))
+    obs[idx] = y
+    q = ssm.chol_q_s @ np.swapaxes(ssm.chol_q_s, -1, -2)
+    lls, _, _ = O.kalman_filter_time_varying(ssm.mu0, ssm.chol_p0 @ ssm.chol_p0.T, ssm.a_s, ssm.b_s,
+                                             q, h, r, obs)
+    assert max_rel_err(npy(kf.log_likelihood()), np.sum(lls[idx])) < 1e-10
+
+
+@pytest.mark.parametrize("m", [2, 3])
+def test_multi_output_time_varying_batched(m):
+    """output_dim > 1 with a full observation covariance and per-chain emission matrices."""
+    rng = np.random.default_rng(m)
+    b, n, d = 5, 17, 3
+    arrays = random_ssm_arrays((b,), n, d)
+    ref = O.SSM(*arrays)
+    h = rng.standard_normal((b, n + 1, m, d))
+    y = rng.standard_normal((b, n + 1, m))
+    lr = np.tril(rng.standard_normal((m, m))) * 0.3 + np.eye(m)
+    want = O.kalman_log_likelihood(ref, h, y, O._r_inv_from_chol(lr), per_chain=True)
+    from markovflow_b200 import kalman_log_likelihood
+
+    got = npy(kalman_log_likelihood(make_ssm(arrays), tt(h), tt(y), tt(lr)))
+    assert max_rel_err(got, want) < 1e-10
+
+
+# ------------------------------------------------------------------------------------------------
+# parallel-in-time path (few long chains)
+# ------------------------------------------------------------------------------------------------
+
+def _long_case(kernel, t, rng, b=1):
+    tps = [np.cumsum(rng.uniform(0.05, 0.15, size=t)) for _ in range(b)]
+    ssms = [kernel.state_space_model(tp) for tp in tps]
+    stack = lambda name: np.stack([getattr(s, name) for s in ssms])
+    ssm = O.SSM(stack("mu0"), stack("chol_p0"), stack("a_s"), stack("b_s"), stack("chol_q_s"))
+    h = np.stack([kernel.emission_matrix(tp) for tp in tps])
+    y = np.sin(np.stack(tps))[..., None] + 0.1 * rng.standard_normal((b, t, 1))
+    return ssm, h, y
+
+
+@pytest.mark.parametrize("name,t,b", [("m32", 5000, 1), ("m52", 3001, 2), ("m32", 200000, 1), ("sum", 2500, 1)])
+def test_parallel_in_time_equals_sequential_and_oracle(name, t, b):
+    from markovflow_b200 import _lib, kalman_log_likelihood
+
+    rng = np.random.default_rng(t)
+    kern = {"m32": O.Matern32(1.0, 1.0), "m52": O.Matern52(0.9, 1.3),
+            "sum": O.Sum([O.Matern32(1.0, 1.0), O.HarmonicOscillator(0.5, 1.0)], jitter=1e-6)}[name]
+    ssm, h, y = _long_case(kern, t, rng, b)
+    lr = np.array([[0.1]])
+    gssm = to_gpu_ssm(ssm)
+    lib = _lib.lib()
+    try:
+        lib.mf_set_tuning(2, 1)
+        seq = npy(kalman_log_likelihood(gssm, tt(h), tt(y), tt(lr)))
+        lib.mf_set_tuning(2, 2)
+        par = npy(kalman_log_likelihood(gssm, tt(h), tt(y), tt(lr)))
+        lib.mf_set_tuning(3, 37)  # odd segment length, ragged tail
+        par2 = npy(kalman_log_likelihood(gssm, tt(h), tt(y), tt(lr)))
+    finally:
+        lib.mf_set_tuning(2, 0)
+        lib.mf_set_tuning(3, 0)
+    assert max_rel_err(par, seq) < 1e-10
+    assert max_rel_err(par2, seq) < 1e-10
+    if t <= 5000:
+        want = O.kalman_log_likelihood(ssm, h, y, O._r_inv_from_chol(lr), per_chain=True)
+        assert max_rel_err(seq, want) < 1e-10
+        assert max_rel_err(par, want) < 1e-10
+
+
+def test_time_sharded_segments_reproduce_the_whole_series():
+    """The multi-GPU protocol on one device: segment summaries -> fold -> seeded local filters."""
+    from markovflow_b200.parallel import time_sharded_log_likelihood_local
+
+    rng = np.random.default_rng(4)
+    ssm, h, y = _long_case(O.Matern32(1.0, 1.0), 10007, rng)
+    lr = np.array([[0.1]])
+    from markovflow_b200 import kalman_log_likelihood
+
+    whole = npy(kalman_log_likelihood(to_gpu_ssm(ssm), tt(h), tt(y), tt(lr)))
+    for world in (2, 3, 8):
+        got = time_sharded_log_likelihood_local(to_gpu_ssm(ssm), tt(h), tt(y), tt(lr), world)
+        assert max_rel_err(npy(got), whole) < 1e-10
