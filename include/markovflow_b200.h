@@ -200,6 +200,37 @@ int mf_kalman_log_likelihood_seeded(int dtype, const void* mu0, const void* chol
                                     int summaries_valid, void* workspace, size_t workspace_bytes,
                                     void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Natural / expectation parameter transforms (markovflow/ssm_gaussian_transformations.py)
+ *   naturals:     theta_lin [B,T,D], theta_diag [B,T,D,D], theta_sub [B,T-1,D,D]
+ *   expectations: eta_lin, eta_diag, eta_sub with the same shapes
+ *   SSM outputs in the concatenated layout the reference slices: out_a [B,T-1,D,D],
+ *   out_offsets [B,T,D] = [mu0, b_1, ...], out_chols [B,T,D,D] = [chol P0, chol Q_1, ...];
+ *   info [B] = 1-based step of the first non-positive pivot (0 = ok).
+ * ------------------------------------------------------------------------------------------- */
+
+/* naturals_to_ssm_params (ssm_gaussian_transformations.py:332-511), smoothing != 0, as one
+ * backward U D U^T sweep; naturals_to_ssm_params_no_smoothing (:514-593), smoothing == 0. */
+int mf_nat_to_ssm(int dtype, const void* theta_lin, const void* theta_diag, const void* theta_sub,
+                  void* out_a, void* out_offsets, void* out_chols, int32_t* info, int64_t B,
+                  int64_t T, int64_t D, int smoothing, void* stream);
+
+/* ssm_to_naturals (:181-253) / ssm_to_naturals_no_smoothing (:256-329). */
+int mf_ssm_to_naturals(int dtype, const void* mu0, const void* chol_p0, const void* a,
+                       const void* b, const void* chol_q, void* theta_lin, void* theta_diag,
+                       void* theta_sub, int64_t B, int64_t T, int64_t D, int smoothing,
+                       void* stream);
+
+/* ssm_to_expectations (:31-89): one forward sweep. */
+int mf_ssm_to_expectations(int dtype, const void* mu0, const void* chol_p0, const void* a,
+                           const void* b, const void* chol_q, void* eta_lin, void* eta_diag,
+                           void* eta_sub, int64_t B, int64_t T, int64_t D, void* stream);
+
+/* expectations_to_ssm_params (:92-178). */
+int mf_expectations_to_ssm(int dtype, const void* eta_lin, const void* eta_diag,
+                           const void* eta_sub, void* out_a, void* out_offsets, void* out_chols,
+                           int32_t* info, int64_t B, int64_t T, int64_t D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

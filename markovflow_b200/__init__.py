@@ -18,6 +18,14 @@ from .kalman_filter import (
     UnivariateGaussianSitesNat,
     kalman_log_likelihood,
 )
+from .ssm_gaussian_transformations import (
+    expectations_to_ssm_params,
+    naturals_to_ssm_params,
+    naturals_to_ssm_params_no_smoothing,
+    ssm_to_expectations,
+    ssm_to_naturals,
+    ssm_to_naturals_no_smoothing,
+)
 from .state_space_model import (
     StateSpaceModel,
     cholesky_or_zero,
@@ -42,6 +50,12 @@ __all__ = [
     "UnivariateGaussianSitesNat",
     "kalman_log_likelihood",
     "StateSpaceModel",
+    "expectations_to_ssm_params",
+    "naturals_to_ssm_params",
+    "naturals_to_ssm_params_no_smoothing",
+    "ssm_to_expectations",
+    "ssm_to_naturals",
+    "ssm_to_naturals_no_smoothing",
     "cholesky_or_zero",
     "state_space_model_from_covariances",
 ]
