@@ -58,3 +58,79 @@ def matern52_posterior_precision(b: int, t: int, device, seed: int = SEED, r_inv
         del flt, a, q, chol_q, inv_q_a, aqa, chols, inv_q, d
     rhs = torch.randn(b, t, 3, generator=g, dtype=f64, device=device)
     return diag, sub, rhs
+
+
+def matern32_ssm(b: int, t: int, device, seed: int = SEED, dt_lo: float = 0.05, dt_hi: float = 0.15,
+                 jitter_hyper: bool = False, dtype=torch.float64, chunk_t: int = 1 << 21):
+    """Configs 1/3/5: Matern32 (D=2) state-space parameters for ``b`` chains of ``t`` states with
+    dt_k ~ U(dt_lo, dt_hi) (reference closed form ``kernels/matern.py:299-356``).  Returns
+    (mu0 [b,2], chol_p0 [b,2,2], a [b,t-1,2,2], offsets [b,t-1,2], chol_q [b,t-1,2,2], h [1,t,1,2])."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    f64 = torch.float64
+    if jitter_hyper:
+        ell = 0.8 + 0.4 * torch.rand(b, generator=g, dtype=f64, device=device)
+        var = 0.8 + 0.4 * torch.rand(b, generator=g, dtype=f64, device=device)
+    else:
+        ell = torch.ones(b, dtype=f64, device=device)
+        var = torch.ones(b, dtype=f64, device=device)
+    lam = math.sqrt(3.0) / ell
+    a = torch.empty(b, t - 1, 2, 2, dtype=dtype, device=device)
+    chol_q = torch.zeros(b, t - 1, 2, 2, dtype=dtype, device=device)
+    for k0 in range(0, t - 1, chunk_t):
+        n = min(chunk_t, t - 1 - k0)
+        dt = dt_lo + (dt_hi - dt_lo) * torch.rand(b, n, generator=g, dtype=f64, device=device)
+        la = lam[:, None]
+        e = torch.exp(-la * dt)
+        a00, a01 = e * (1.0 + la * dt), e * dt
+        a10, a11 = -e * la * la * dt, e * (1.0 - la * dt)
+        p0, p1 = var[:, None], var[:, None] * la * la  # Pinf = diag(p0, p1)
+        q00 = p0 - (a00 * a00 * p0 + a01 * a01 * p1)
+        q10 = -(a10 * a00 * p0 + a11 * a01 * p1)
+        q11 = p1 - (a10 * a10 * p0 + a11 * a11 * p1)
+        l00 = torch.sqrt(q00)
+        l10 = q10 / l00
+        l11 = torch.sqrt(q11 - l10 * l10)
+        sl = slice(k0, k0 + n)
+        a[:, sl, 0, 0], a[:, sl, 0, 1], a[:, sl, 1, 0], a[:, sl, 1, 1] = (
+            a00.to(dtype), a01.to(dtype), a10.to(dtype), a11.to(dtype))
+        chol_q[:, sl, 0, 0], chol_q[:, sl, 1, 0], chol_q[:, sl, 1, 1] = (
+            l00.to(dtype), l10.to(dtype), l11.to(dtype))
+        del dt, e, a00, a01, a10, a11, q00, q10, q11, l00, l10, l11
+    mu0 = torch.zeros(b, 2, dtype=dtype, device=device)
+    chol_p0 = torch.zeros(b, 2, 2, dtype=dtype, device=device)
+    chol_p0[:, 0, 0] = torch.sqrt(var).to(dtype)
+    chol_p0[:, 1, 1] = (torch.sqrt(var) * lam).to(dtype)
+    offsets = torch.zeros(b, t - 1, 2, dtype=dtype, device=device)
+    h = torch.zeros(1, t, 1, 2, dtype=dtype, device=device)
+    h[..., 0] = 1.0
+    return mu0, chol_p0, a, offsets, chol_q, h
+
+
+def kalman_inputs_config3(t: int, device, seed: int = SEED, noise: float = 0.1):
+    """Config 3: ONE Matern32 series of ``t`` states, observations sampled from the model + noise."""
+    from markovflow_b200 import StateSpaceModel
+
+    mu0, l0, a, off, lq, h = matern32_ssm(1, t, device, seed)
+    ssm = StateSpaceModel(mu0, l0, a, off, lq)
+    g = torch.Generator(device=device).manual_seed(seed + 1)
+    x = ssm.sample((), generator=g)  # [1,t,2]
+    y = x[..., :1] + noise * torch.randn(1, t, 1, generator=g, dtype=torch.float64, device=device)
+    chol_r = torch.tensor([[noise]], dtype=torch.float64, device=device)
+    return ssm, h, y, chol_r
+
+
+def cvi_naturals_config5(b: int, t: int, device, seed: int = SEED, dtype=torch.float64):
+    """Config 5: natural parameters of the CVI posterior: Matern32 prior precision at ``t`` inducing
+    states (linspace grid, per-chain jittered hyper-parameters) + back-projected site naturals
+    (``models/variational_cvi.py:106-135,423-445``).  Returns (theta_lin, theta_diag, theta_sub)."""
+    from markovflow_b200 import StateSpaceModel
+
+    mu0, l0, a, off, lq, h = matern32_ssm(b, t, device, seed, dt_lo=0.1, dt_hi=0.1, jitter_hyper=True)
+    ssm = StateSpaceModel(mu0, l0, a, off, lq)
+    g = torch.Generator(device=device).manual_seed(seed + 2)
+    prec = 0.5 + 1.5 * torch.rand(t, 1, 1, generator=g, dtype=torch.float64, device=device)
+    nat1 = torch.randn(b, t, 1, generator=g, dtype=torch.float64, device=device)
+    pd, ps = ssm._precision_blocks(h[0], prec)  # K^-1 + H^T diag(prec) H
+    theta_lin = torch.zeros(b, t, 2, dtype=torch.float64, device=device)
+    theta_lin[..., 0] = nat1[..., 0]
+    return theta_lin.to(dtype), (-0.5 * pd).to(dtype), (-ps).to(dtype)

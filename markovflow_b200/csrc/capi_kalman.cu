@@ -1,6 +1,7 @@
 // C-ABI entry points for the Kalman log-likelihood (include/markovflow_b200.h).
 #include "dispatch.cuh"
 #include "kalman_kernels.cuh"
+#include "kalman_sweep_api.h"
 
 using namespace mf;
 
@@ -35,8 +36,84 @@ struct Workspace {
   size_t summaries, seeds, partial, total;
 };
 
+// ---- TMA-sweep path (m = 1, D <= kKalmanSweepMaxD; kalman_sweep.cuh) ----------------------------
+// tuning knob 4: 1 disables it (legacy direct-load kernels, kept for A/B measurements).
+struct SweepPlan {
+  bool use;
+  int64_t P, L, nblk;
+};
+
+SweepPlan make_sweep_plan(int64_t B, int64_t T, int64_t D, int64_t m) {
+  SweepPlan p;
+  p.use = (m == 1 && D <= kKalmanSweepMaxD && tuning(4) != 1);
+  p.P = 1; p.L = T; p.nblk = 1;
+  if (!p.use) return p;
+  const int64_t wave = 148 * (int64_t)kalman_sweep_chains_per_cta(D);
+  int64_t ptarget = wave / (B > 0 ? B : 1);
+  if (tuning(2) == 1 || (tuning(2) == 0 && ptarget < 2)) return p;
+  if (ptarget < 2) ptarget = 2;
+  int64_t L = (T + ptarget - 1) / ptarget;
+  if (L < 64) L = 64;
+  L = (L + 7) / 8 * 8;
+  if (tuning(3) > 0) L = tuning(3);
+  p.L = L;
+  p.P = (T + L - 1) / L;
+  const int64_t nt = kalman_sweep_scan_threads(D);
+  p.nblk = (p.P + nt - 1) / nt;
+  return p;
+}
+
+struct SweepWs {
+  size_t elems, block_agg, block_prefix, partial, total;
+};
+
+SweepWs sweep_layout(size_t es, int64_t B, const SweepPlan& pl, int64_t D) {
+  const size_t N = 3 * D * D + 2 * D + 1;
+  SweepWs w;
+  w.elems = 0;
+  w.block_agg = align_up(w.elems + es * B * pl.P * N);
+  w.block_prefix = align_up(w.block_agg + es * B * pl.nblk * N);
+  w.partial = align_up(w.block_prefix + es * B * pl.nblk * N);
+  w.total = align_up(w.partial + es * B * pl.P);
+  return w;
+}
+
+KalmanRawArgs raw_args(int dtype, const void* mu0, const void* chol_p0, const void* a,
+                       const void* b, const void* chol_q, const void* h, const void* obs,
+                       const void* chol_r, int64_t B, int64_t T, int64_t D, int64_t h_batch,
+                       int64_t r_steps, int first_is_initial) {
+  KalmanRawArgs r;
+  r.dtype = dtype; r.mu0 = mu0; r.chol_p0 = chol_p0; r.a = a; r.b = b; r.chol_q = chol_q; r.h = h;
+  r.obs = obs; r.chol_r = chol_r; r.B = B; r.T = T; r.D = D; r.h_batch = h_batch;
+  r.r_steps = r_steps; r.first_is_initial = first_is_initial;
+  return r;
+}
+
+// summaries -> in-place local prefixes + block aggregates
+int sweep_summaries(const KalmanRawArgs& r, const SweepPlan& pl, const SweepWs& w, char* ws,
+                    cudaStream_t s) {
+  int rc = kalman_sweep_launch(1, r, pl.P, pl.L, nullptr, nullptr, pl.nblk, 0, ws + w.elems, s);
+  if (rc != MF_OK) return rc;
+  return kalman_sweep_block_scan(r.dtype, r.D, ws + w.elems, ws + w.block_agg, r.B, pl.P, pl.nblk, s);
+}
+
+int sweep_seeded(const KalmanRawArgs& r, const SweepPlan& pl, const SweepWs& w, char* ws,
+                 const void* prefix_elem, void* out, cudaStream_t s) {
+  int rc = kalman_sweep_top_scan(r.dtype, r.D, ws + w.block_agg, prefix_elem, ws + w.block_prefix,
+                                 nullptr, nullptr, r.B, pl.nblk, s);
+  if (rc != MF_OK) return rc;
+  rc = kalman_sweep_launch(2, r, pl.P, pl.L, ws + w.elems, ws + w.block_prefix, pl.nblk,
+                           prefix_elem != nullptr, ws + w.partial, s);
+  if (rc != MF_OK) return rc;
+  return dispatch_dtype(r.dtype, [&](auto tt) {
+    using Tp = typename decltype(tt)::type;
+    kalman_partial_sum_kernel<Tp><<<(unsigned)r.B, 256, 0, s>>>((const Tp*)(ws + w.partial), (Tp*)out, pl.P);
+    return check_launch();
+  });
+}
+
 Workspace layout(size_t es, int64_t B, int64_t P, int64_t D) {
-  const size_t N = 3 * D * D + 2 * D;
+  const size_t N = 3 * D * D + 2 * D + 1;
   Workspace w;
   w.summaries = 0;
   w.seeds = align_up(w.summaries + es * B * P * N);
@@ -88,8 +165,13 @@ size_t mf_kalman_workspace_bytes(int dtype, int64_t B, int64_t T, int64_t D) {
   if (B < 1 || T < 1 || D < 1) return 0;
   const Plan pl = make_plan(B, T);
   const size_t es = dtype == MF_F64 ? 8 : 4;
-  const size_t N = 3 * D * D + 2 * D;
-  return layout(es, B, pl.P, D).total + align_up(es * B * N);
+  const size_t N = 3 * D * D + 2 * D + 1;
+  size_t legacy = layout(es, B, pl.P, D).total + align_up(es * B * N);
+  if (D <= kKalmanSweepMaxD) {
+    const size_t sweep = sweep_layout(es, B, make_sweep_plan(B, T, D, 1), D).total;
+    if (sweep > legacy) legacy = sweep;
+  }
+  return legacy;
 }
 
 int mf_kalman_segment_summary(int dtype, const void* mu0, const void* chol_p0, const void* a,
@@ -104,6 +186,18 @@ int mf_kalman_segment_summary(int dtype, const void* mu0, const void* chol_p0, c
   if (!out_elem || !workspace || B > 65535) return MF_ERR_BAD_ARG;
   if (workspace_bytes < mf_kalman_workspace_bytes(dtype, B, T, D)) return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  const SweepPlan sp = make_sweep_plan(B, T, D, m);
+  if (sp.use) {
+    if (dtype != MF_F32 && dtype != MF_F64) return MF_ERR_BAD_ARG;
+    const SweepWs w = sweep_layout(dtype == MF_F64 ? 8 : 4, B, sp, D);
+    char* ws = (char*)workspace;
+    const KalmanRawArgs r = raw_args(dtype, mu0, chol_p0, a, b, chol_q, h, obs, chol_r, B, T, D,
+                                     h_batch, r_steps, first_is_initial);
+    int rc = sweep_summaries(r, sp, w, ws, s);
+    if (rc != MF_OK) return rc;
+    return kalman_sweep_top_scan(dtype, D, ws + w.block_agg, nullptr, ws + w.block_prefix, out_elem,
+                                 nullptr, B, sp.nblk, s);
+  }
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
@@ -150,6 +244,19 @@ int mf_kalman_log_likelihood_seeded(int dtype, const void* mu0, const void* chol
   if (!first_is_initial && !prefix_elem) return MF_ERR_BAD_ARG;
   if (workspace_bytes < mf_kalman_workspace_bytes(dtype, B, T, D)) return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  const SweepPlan sp = make_sweep_plan(B, T, D, m);
+  if (sp.use) {
+    if (dtype != MF_F32 && dtype != MF_F64) return MF_ERR_BAD_ARG;
+    const SweepWs w = sweep_layout(dtype == MF_F64 ? 8 : 4, B, sp, D);
+    char* ws = (char*)workspace;
+    const KalmanRawArgs r = raw_args(dtype, mu0, chol_p0, a, b, chol_q, h, obs, chol_r, B, T, D,
+                                     h_batch, r_steps, first_is_initial);
+    if (!summaries_valid) {
+      int rc = sweep_summaries(r, sp, w, ws, s);
+      if (rc != MF_OK) return rc;
+    }
+    return sweep_seeded(r, sp, w, ws, prefix_elem, out, s);
+  }
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
@@ -192,6 +299,28 @@ int mf_kalman_log_likelihood(int dtype, const void* mu0, const void* chol_p0, co
   if (st != MF_OK) return st;
   if (B == 0) return MF_OK;
   if (!out) return MF_ERR_BAD_ARG;
+  const SweepPlan sp = make_sweep_plan(B, T, D, m);
+  if (sp.use) {
+    if (dtype != MF_F32 && dtype != MF_F64) return MF_ERR_BAD_ARG;
+    const bool ws_ok = workspace && B <= 65535 &&
+                       workspace_bytes >= mf_kalman_workspace_bytes(dtype, B, T, D);
+    if (sp.P > 1 && ws_ok) {
+      // parallel in time, ONE pass over the data: per-segment elements, then an ordered reduction
+      // whose ell component is the log-likelihood
+      const SweepWs w = sweep_layout(dtype == MF_F64 ? 8 : 4, B, sp, D);
+      char* ws = (char*)workspace;
+      const KalmanRawArgs r = raw_args(dtype, mu0, chol_p0, a, b, chol_q, h, obs, chol_r, B, T, D,
+                                       h_batch, r_steps, 1);
+      int rc = sweep_summaries(r, sp, w, ws, (cudaStream_t)stream);
+      if (rc != MF_OK) return rc;
+      return kalman_sweep_top_scan(dtype, D, ws + w.block_agg, nullptr, nullptr, nullptr, out, B,
+                                   sp.nblk, (cudaStream_t)stream);
+    }
+    // batched filter: one virtual chain per series (also the no-workspace case)
+    const KalmanRawArgs r = raw_args(dtype, mu0, chol_p0, a, b, chol_q, h, obs, chol_r, B, T, D,
+                                     h_batch, r_steps, 1);
+    return kalman_sweep_launch(0, r, 1, T, nullptr, nullptr, 1, 0, out, (cudaStream_t)stream);
+  }
   const Plan pl = make_plan(B, T);
   if (pl.pscan && workspace && B <= 65535 &&
       workspace_bytes >= mf_kalman_workspace_bytes(dtype, B, T, D))

@@ -14,6 +14,9 @@
 //   ScanElem     (A, b, C, eta, J)                -- the associative element of the parallel-in-time
 //       scan (Sarkka & Garcia-Fernandez 2021): over a range of steps i..j
 //         x_j | x_{i-1}, y_{i:j} ~ N(A x_{i-1} + b, C),   p(y_{i:j} | x_{i-1}) ∝ N_info(x_{i-1}; eta, J)
+//       plus the scalar ell with  p(y_{i:j} | x_{i-1}) = exp(ell - x^T J x / 2 + eta^T x),  so that the
+//       ell of the join of ALL elements of a series (whose first element is the prior) IS the
+//       marginal log-likelihood: one pass over the data and an ordered reduction, no second sweep.
 //       Extending a range by one step is a transition + scalar absorptions (cheap, no inverse);
 //       joining two ranges is elem_combine (one Cholesky of I + L^T J L).
 #pragma once
@@ -31,8 +34,10 @@ struct FilterState {
 
 template <typename T, int D>
 struct ScanElem {
-  static constexpr int N = 3 * D * D + 2 * D;  // doubles per element in memory: A, b, C, eta, J
+  // values per element in memory: A, b, C, eta, J, ell
+  static constexpr int N = 3 * D * D + 2 * D + 1;
   T A[D * D], b[D], C[D * D], eta[D], J[D * D];
+  T ell;  // log-normaliser: p(y_{i:j} | x_{i-1}) = exp(ell - x^T J x / 2 + eta^T x)
 };
 
 // ---- symmetric helpers --------------------------------------------------------------------------
@@ -129,6 +134,7 @@ __device__ __forceinline__ void filter_absorb(FilterState<T, D>& st, const T* __
 
 template <typename T, int D>
 __device__ __forceinline__ void elem_identity(ScanElem<T, D>& e) {
+  e.ell = T(0);
 #pragma unroll
   for (int i = 0; i < D; ++i) {
     e.b[i] = T(0);
@@ -146,6 +152,7 @@ __device__ __forceinline__ void elem_identity(ScanElem<T, D>& e) {
 template <typename T, int D>
 __device__ __forceinline__ void elem_prior(ScanElem<T, D>& e, const T* __restrict__ mu0,
                                            const T* __restrict__ chol_p0) {
+  e.ell = T(0);
 #pragma unroll
   for (int i = 0; i < D; ++i) {
     e.b[i] = mu0[i];
@@ -170,9 +177,11 @@ __device__ __forceinline__ void elem_transition(ScanElem<T, D>& e, const T* __re
   cov_predict<T, D>(e.C, F, Lq);
 }
 
-// Absorb one whitened scalar observation into the range element.
+// Absorb one whitened scalar observation into the range element; the element's ell gains
+// -(v^2/s + log s + log 2 pi)/2, accumulated by the caller as quad += v^2/s, det *= s.
 template <typename T, int D>
-__device__ __forceinline__ void elem_absorb(ScanElem<T, D>& e, const T* __restrict__ h, T y) {
+__device__ __forceinline__ void elem_absorb(ScanElem<T, D>& e, const T* __restrict__ h, T y,
+                                            T& quad, LogProd<T>& det) {
   T g[D], w[D];
   T s = T(1), v = y;
 #pragma unroll
@@ -193,6 +202,8 @@ __device__ __forceinline__ void elem_absorb(ScanElem<T, D>& e, const T* __restri
   }
   const T rs = Num<T>::rcp(s);
   const T vs = v * rs;
+  quad = Num<T>::fma(v, vs, quad);
+  det.mul(s);
 #pragma unroll
   for (int i = 0; i < D; ++i) {
     const T ki = g[i] * rs;
@@ -303,6 +314,23 @@ __device__ __noinline__ void elem_combine(ScanElem<T, D>& out, const ScanElem<T,
 #pragma unroll
   for (int i = 0; i < D; ++i) t1[i] = ej.eta[i];
   gemv_sub<T, D>(t1, ej.J, ei.b);
+  {
+    // ell = ell_i + ell_j + log Int exp(-x^T Jj x/2 + eta_j^T x) N(x; b_i, C_i) dx
+    //     = ... + b_i.(eta_j + t1)/2 - sum log R_kk + |R^{-1} L^T t1|^2 / 2
+    T cz[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) cz[i] = T(0);
+    gemv_t_add<T, D>(cz, L, t1);
+    trsv_lower<T, D>(R, rinv, cz);
+    T f = T(0), rprod = T(1);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      f = Num<T>::fma(ei.b[i], ej.eta[i] + t1[i], f);
+      f = Num<T>::fma(cz[i], cz[i], f);
+      rprod *= rinv[i];
+    }
+    out.ell = ei.ell + ej.ell + T(0.5) * f + Num<T>::log(rprod);
+  }
 #pragma unroll
   for (int i = 0; i < D; ++i) t2[i] = T(0);
   gemv_add<T, D>(t2, Kk, t1);
@@ -335,6 +363,7 @@ __device__ __forceinline__ void elem_store(T* __restrict__ p, const ScanElem<T, 
   for (int i = 0; i < DD; ++i) { p[i] = e.A[i]; p[DD + D + i] = e.C[i]; p[2 * DD + 2 * D + i] = e.J[i]; }
 #pragma unroll
   for (int i = 0; i < D; ++i) { p[DD + i] = e.b[i]; p[2 * DD + D + i] = e.eta[i]; }
+  p[3 * DD + 2 * D] = e.ell;
 }
 
 template <typename T, int D>
@@ -344,6 +373,7 @@ __device__ __forceinline__ void elem_load(ScanElem<T, D>& e, const T* __restrict
   for (int i = 0; i < DD; ++i) { e.A[i] = p[i]; e.C[i] = p[DD + D + i]; e.J[i] = p[2 * DD + 2 * D + i]; }
 #pragma unroll
   for (int i = 0; i < D; ++i) { e.b[i] = p[DD + i]; e.eta[i] = p[2 * DD + D + i]; }
+  e.ell = p[3 * DD + 2 * D];
 }
 
 // ---- observation access: whitening with W = chol(R)^{-1} -------------------------------------------

@@ -129,11 +129,18 @@ struct FilterSink {
 template <typename T, int D>
 struct ElemSink {
   ScanElem<T, D> e;
+  T quad;
+  LogProd<T> det;
+  __device__ __forceinline__ void init() { elem_identity<T, D>(e); quad = T(0); det.init(); }
   __device__ __forceinline__ void start_prior(const T* mu, const T* L0) { elem_prior<T, D>(e, mu, L0); }
   __device__ __forceinline__ void transition(const T* F, const T* u, const T* Lq) {
     elem_transition<T, D>(e, F, u, Lq);
   }
-  __device__ __forceinline__ void absorb(const T* h, T y) { elem_absorb<T, D>(e, h, y); }
+  __device__ __forceinline__ void absorb(const T* h, T y) { elem_absorb<T, D>(e, h, y, quad, det); }
+  // fold the accumulated scalar terms of nobs absorbed observations into the element's ell
+  __device__ __forceinline__ void finalize(T logw, int64_t nobs) {
+    e.ell += T(-0.5) * (quad + det.log_abs()) + logw - T(0.5 * 1.8378770664093454836) * T(nobs);
+  }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -159,11 +166,12 @@ kalman_segment_summary_kernel(KalmanArgs<T> g, T* __restrict__ summaries, int64_
   const int64_t c = blockIdx.y;
   if (p >= P) return;
   ElemSink<T, D> sink;
-  elem_identity<T, D>(sink.e);
+  sink.init();
   const int64_t k0 = p * L;
   const int64_t k1 = (k0 + L < g.Tn) ? k0 + L : g.Tn;
   int64_t nobs = 0;
-  kalman_walk<T, D, M1>(g, c, k0, k1, sink, nobs);
+  const T logw = kalman_walk<T, D, M1>(g, c, k0, k1, sink, nobs);
+  sink.finalize(logw, nobs);
   elem_store<T, D>(summaries + (c * P + p) * ScanElem<T, D>::N, sink.e);
 }
 

@@ -3,11 +3,13 @@
 * Batches of independent chains (BASELINE configs 2, 4, 5) are split over ranks with NO data-path
   collective (``batch_shape`` dims are pure broadcasting, ``block_tri_diag.py:110-115``):
   :func:`shard_bounds` / :func:`shard_batch`.
-* ONE long series (config 3) is split in time.  Each rank reduces its segment to one scan element
-  (``mf_kalman_segment_summary``), the elements are all-gathered (NCCL over NVLink; 8 x 128 B at
-  D = 2), each rank joins the elements of the earlier ranks into its incoming prefix
-  (``mf_kalman_fold_elements``) and runs its seeded local filter
-  (``mf_kalman_log_likelihood_seeded``); a scalar all-reduce sums the shares.
+* ONE long series (config 3) is split in time.  Each rank reduces its segment -- ONE pass over its
+  data -- to one scan element ``(A, b, C, eta, J, ell)`` (``mf_kalman_segment_summary``), the
+  elements are all-gathered (NCCL over NVLink; 8 x 136 B at D = 2) and every rank joins them in time
+  order (``mf_kalman_fold_elements``): the ``ell`` of the join is the log-likelihood of the whole
+  series.  No second sweep and no further collective.  (``mf_kalman_log_likelihood_seeded`` -- a
+  local filter seeded with the prefix of the earlier ranks -- remains available for callers that
+  want per-segment shares.)
 
 The compute engine is pluggable so that the host logic (slicing, gather order, fold range) is
 testable on CPU with ``gloo``; the default engine is the CUDA library and there is no other engine
@@ -85,7 +87,7 @@ class CudaKalmanEngine:
 
     @staticmethod
     def elem_size(d: int) -> int:
-        return 3 * d * d + 2 * d
+        return 3 * d * d + 2 * d + 1
 
     def _dims(self, seg: TimeSegment):
         bsz, tl, m = seg.obs.shape
@@ -147,7 +149,7 @@ class CudaKalmanEngine:
 
 def time_sharded_log_likelihood(seg: TimeSegment, group=None, engine=None) -> torch.Tensor:
     """Per-chain log-likelihood ``[B]`` of the whole series, computed collectively: every rank
-    passes its own :class:`TimeSegment` (rank order == time order)."""
+    passes its own :class:`TimeSegment` (rank order == time order) and receives the same value."""
     import torch.distributed as dist
 
     engine = engine or CudaKalmanEngine()
@@ -157,31 +159,36 @@ def time_sharded_log_likelihood(seg: TimeSegment, group=None, engine=None) -> to
         raise ValueError("rank 0 (and only rank 0) must hold the segment that starts at the prior")
     d = int(seg.a.shape[-1])
     elem = engine.segment_summary(seg)
-    prefix = None
     if world > 1:
         gathered = [torch.empty_like(elem) for _ in range(world)]
         dist.all_gather(gathered, elem, group=group)
-        if rank > 0:
-            prefix = engine.fold(torch.stack(gathered[:rank]), d)
-    share = engine.seeded_log_likelihood(seg, prefix, summaries_valid=True)
-    if world > 1:
-        dist.all_reduce(share, op=dist.ReduceOp.SUM, group=group)
-    return share
+        elem = engine.fold(torch.stack(gathered), d)
+    return elem[:, -1].clone()
 
 
-def time_sharded_log_likelihood_local(ssm, emission_matrix, observations, chol_obs_covariance,
-                                      world: int, engine=None) -> torch.Tensor:
-    """The same protocol executed for ``world`` virtual ranks on ONE device (validation, and the
-    single-GPU leg of the scaling bench): returns the per-chain log-likelihood ``[batch]``."""
-    engine = engine or CudaKalmanEngine()
+def time_sharded_segments(ssm, emission_matrix, observations, chol_obs_covariance,
+                          world: int) -> List[TimeSegment]:
+    """All ``world`` segments of a (batch of) series held on one device."""
     mu0, l0, a, b, lq, bsz, t, d = ssm._flat()
     m = int(emission_matrix.shape[-2])
     h = emission_matrix.reshape(-1, t, m, d)
     y = observations.reshape(bsz, t, m)
     lr = chol_obs_covariance.reshape(-1, m, m)
-    segs: List[TimeSegment] = [time_segment(mu0, l0, a, b, lq, h, y, lr, r, world) for r in range(world)]
+    return [time_segment(mu0, l0, a, b, lq, h, y, lr, r, world) for r in range(world)]
+
+
+def time_sharded_log_likelihood_local(ssm, emission_matrix, observations, chol_obs_covariance,
+                                      world: int, engine=None, seeded: bool = False) -> torch.Tensor:
+    """The same protocol executed for ``world`` virtual ranks on ONE device (validation, and the
+    single-GPU leg of the scaling bench): returns the per-chain log-likelihood ``[batch]``.
+    ``seeded=True`` exercises the alternative protocol (prefix fold + seeded local filters)."""
+    engine = engine or CudaKalmanEngine()
+    d = ssm.state_dim
+    segs = time_sharded_segments(ssm, emission_matrix, observations, chol_obs_covariance, world)
     engines = [engine.__class__() for _ in segs]  # one workspace per virtual rank
     elems = [e.segment_summary(s) for e, s in zip(engines, segs)]
+    if not seeded:
+        return engine.fold(torch.stack(elems), d)[:, -1].reshape(tuple(ssm.batch_shape))
     total = None
     for r, (e, s) in enumerate(zip(engines, segs)):
         prefix = e.fold(torch.stack(elems[:r]), d) if r > 0 else None

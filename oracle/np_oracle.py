@@ -745,6 +745,51 @@ def pscan_log_likelihood(mu0, p0, a_s, b_s, q_s, h, r, obs, segment: int = 7) ->
     return total
 
 
+def pscan_segment_element(a_in, b_in, q_in, h, r, obs, prior=None):
+    """Range element WITH log-normaliser ``(A, b, C, eta, J, ell)`` of a run of steps of ONE chain:
+    ``p(y_run | x_prev) = exp(ell - x'Jx/2 + eta'x)`` and ``x_last | x_prev, y_run ~ N(Ax+b, C)``.
+    ``a_in[k], b_in[k], q_in[k]`` lead INTO step ``k``; with ``prior=(mu0, P0)`` step 0 starts from
+    the prior instead and ``a_in`` has one entry fewer.  The ``ell`` of the join of all elements
+    of a series is its marginal log-likelihood (extended)."""
+    t = obs.shape[0]
+    d = h.shape[-1]
+    a, b, c = np.eye(d), np.zeros(d), np.zeros((d, d))
+    eta, jm, ell = np.zeros(d), np.zeros((d, d)), 0.0
+    off = 0 if prior is None else 1
+    for k in range(t):
+        if k == 0 and prior is not None:
+            a, b, c = np.zeros((d, d)), np.asarray(prior[0], float), np.asarray(prior[1], float)
+        else:
+            f, u, q = a_in[k - off], b_in[k - off], q_in[k - off]
+            a, b, c = f @ a, f @ b + u, f @ c @ f.T + q
+        rk = r if r.ndim == 2 else r[k]
+        w_mat = np.linalg.inv(np.linalg.cholesky(rk))  # whitener
+        hw, yw = w_mat @ h[k], w_mat @ obs[k]
+        ell += np.sum(np.log(np.diag(w_mat)))
+        for i in range(hw.shape[0]):  # absorb one whitened scalar at a time
+            hv, yv = hw[i], yw[i]
+            g = c @ hv
+            s = 1.0 + hv @ g
+            gain = g / s
+            w = a.T @ hv
+            v = yv - hv @ b
+            a, b, c = a - np.outer(gain, w), b + gain * v, c - np.outer(gain, g)
+            eta, jm = eta + w * v / s, jm + np.outer(w, w) / s
+            ell += -0.5 * (np.log(2.0 * np.pi * s) + v * v / s)
+    return a, b, c, eta, jm, ell
+
+
+def pscan_combine_ell(ei, ej):
+    """Join of two range elements with log-normalisers (``ei`` earlier)."""
+    a, b, c, eta, jm = pscan_combine(ei[:5], ej[:5])
+    bi, ci, etaj, jj = ei[1], ei[2], ej[3], ej[4]
+    d = bi.shape[-1]
+    m_mat = np.eye(d) + ci @ jj
+    t1 = etaj - jj @ bi
+    f = 0.5 * bi @ (etaj + t1) - 0.5 * np.linalg.slogdet(m_mat)[1] + 0.5 * t1 @ np.linalg.solve(m_mat, ci @ t1)
+    return a, b, c, eta, jm, ei[5] + ej[5] + f
+
+
 # ----------------------------------------------------------------------------------------------
 # natural / expectation parameter transforms (ssm_gaussian_transformations.py)
 # ----------------------------------------------------------------------------------------------

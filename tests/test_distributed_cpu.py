@@ -29,46 +29,30 @@ class OracleKalmanEngine:
 
     def segment_summary(self, seg):
         a, b, q, h, y, r = self._np(seg)
-        d = a.shape[-1]
+        prior = None
         if seg.first:
             l0 = seg.chol_p0[0].numpy()
-            els = O.pscan_elements(seg.mu0[0].numpy(), l0 @ l0.T, a, b, q, h, r, y)
-            lo = 0
-        else:  # pad a fake step 0 so that element k uses the incoming transition a[k-1]
-            hp = np.concatenate([h[:1], h])
-            yp = np.concatenate([y[:1], y])
-            els = O.pscan_elements(np.zeros(d), np.eye(d), a, b, q, hp, r, yp)
-            lo = 1
-        e = tuple(x[lo] for x in els)
-        for k in range(lo + 1, els[0].shape[0]):
-            e = O.pscan_combine(e, tuple(x[k] for x in els))
-        return torch.from_numpy(np.concatenate([x.reshape(-1) for x in e]))[None]
+            prior = (seg.mu0[0].numpy(), l0 @ l0.T)
+        e = O.pscan_segment_element(a, b, q, h, r, y, prior=prior)
+        return self._pack(e)
+
+    @staticmethod
+    def _pack(e):
+        return torch.from_numpy(np.concatenate([np.reshape(x, -1) for x in e]))[None]
 
     @staticmethod
     def _unpack(v, d):
         v = v.numpy()
         dd = d * d
         return (v[:dd].reshape(d, d), v[dd:dd + d], v[dd + d:2 * dd + d].reshape(d, d),
-                v[2 * dd + d:2 * dd + 2 * d], v[2 * dd + 2 * d:].reshape(d, d))
+                v[2 * dd + d:2 * dd + 2 * d], v[2 * dd + 2 * d:3 * dd + 2 * d].reshape(d, d),
+                float(v[3 * dd + 2 * d]))
 
     def fold(self, elems, d):
         e = self._unpack(elems[0, 0], d)
         for i in range(1, elems.shape[0]):
-            e = O.pscan_combine(e, self._unpack(elems[i, 0], d))
-        return torch.from_numpy(np.concatenate([x.reshape(-1) for x in e]))[None]
-
-    def seeded_log_likelihood(self, seg, prefix, summaries_valid):
-        a, b, q, h, y, r = self._np(seg)
-        d = a.shape[-1]
-        if seg.first:
-            l0 = seg.chol_p0[0].numpy()
-            m0, p0 = seg.mu0[0].numpy(), l0 @ l0.T
-        else:
-            _, fm, fp, _, _ = self._unpack(prefix[0], d)
-            m0, p0 = a[0] @ fm + b[0], a[0] @ fp @ a[0].T + q[0]
-            a, b, q = a[1:], b[1:], q[1:]
-        lls, _, _ = O.kalman_filter_time_varying(m0, p0, a, b, q, h, r, y)
-        return torch.tensor([np.sum(lls)])
+            e = O.pscan_combine_ell(e, self._unpack(elems[i, 0], d))
+        return self._pack(e)
 
 
 def _free_port():
@@ -114,7 +98,7 @@ def test_time_sharded_log_likelihood_gloo(world, t):
         got = [out[r] for r in range(world)]
     ssm, h, y, lr = _case(t)
     want = float(O.kalman_log_likelihood(ssm, h, y, O._r_inv_from_chol(lr)))
-    for g in got:  # every rank holds the all-reduced value
+    for g in got:  # every rank folds the same gathered elements
         assert abs(g - want) < 1e-9 * abs(want)
 
 

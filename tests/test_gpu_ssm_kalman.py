@@ -340,3 +340,27 @@ def test_time_sharded_segments_reproduce_the_whole_series():
     for world in (2, 3, 8):
         got = time_sharded_log_likelihood_local(to_gpu_ssm(ssm), tt(h), tt(y), tt(lr), world)
         assert max_rel_err(npy(got), whole) < 1e-10
+        got = time_sharded_log_likelihood_local(to_gpu_ssm(ssm), tt(h), tt(y), tt(lr), world, seeded=True)
+        assert max_rel_err(npy(got), whole) < 1e-10
+
+
+def test_segment_element_matches_oracle_element():
+    """mf_kalman_segment_summary against the oracle's element with log-normaliser."""
+    from markovflow_b200.parallel import CudaKalmanEngine, time_sharded_segments
+
+    rng = np.random.default_rng(9)
+    ssm, h, y, lr = (*_long_case(O.Matern52(0.9, 1.3), 301, rng), np.array([[0.2]]))
+    segs = time_sharded_segments(to_gpu_ssm(ssm), tt(h), tt(y), tt(lr), 3)
+    q = ssm.chol_q_s @ np.swapaxes(ssm.chol_q_s, -1, -2)
+    lo = 0
+    for r, seg in enumerate(segs):
+        got = npy(CudaKalmanEngine().segment_summary(seg))[0]
+        n = seg.num_steps
+        tlo = 0 if r == 0 else lo - 1
+        prior = (ssm.mu0[0], ssm.chol_p0[0] @ ssm.chol_p0[0].T) if r == 0 else None
+        want = O.pscan_segment_element(ssm.a_s[0, tlo:lo + n - 1], ssm.b_s[0, tlo:lo + n - 1],
+                                       q[0, tlo:lo + n - 1], h[0, lo:lo + n], lr @ lr.T,
+                                       y[0, lo:lo + n], prior=prior)
+        want = np.concatenate([np.reshape(x, -1) for x in want])
+        assert max_rel_err(got, want) < 1e-9
+        lo += n

@@ -1,0 +1,95 @@
+"""Times the non-headline kernels on their BASELINE configurations (device-resident, CUDA events):
+    python tools/bench_paths.py [kalman3] [cvi5] [kalman_batch] [ssm]
+Prints one JSON line per measurement with the HBM-roofline fraction (algorithmic bytes per
+state-step from SURVEY.md §8d)."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import bench_inputs  # noqa: E402
+import markovflow_b200 as mf  # noqa: E402
+from markovflow_b200 import _lib  # noqa: E402
+
+DEV = torch.device("cuda:0")
+PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
+    os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+
+
+def timeit(fn, warm=3, reps=10):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return ts[len(ts) // 2]
+
+
+def report(name, steps, bytes_per_step, ms, **extra):
+    gbs = steps * bytes_per_step / (ms * 1e-3) / 1e9
+    print(json.dumps({"name": name, "ms": round(ms, 4), "state_steps_per_s": steps / (ms * 1e-3),
+                      "GB/s": round(gbs, 1), "frac_of_hbm_peak": round(gbs / PEAK, 4),
+                      "bytes_per_step": bytes_per_step, **extra}), flush=True)
+
+
+def kalman3(t=10_000_000):
+    ssm, h, y, lr = bench_inputs.kalman_inputs_config3(t, DEV)
+    lib = _lib.lib()
+    for mode, label in ((2, "parallel-in-time"),):
+        lib.mf_set_tuning(2, mode)
+        ms = timeit(lambda: mf.kalman_log_likelihood(ssm, h, y, lr))
+        ll = float(mf.kalman_log_likelihood(ssm, h, y, lr))
+        report(f"kalman_loglik config3 T={t} D=2 f64 [{label}]", t, (2 * 4 + 2 + 2 + 1) * 8, ms, loglik=ll)
+    lib.mf_set_tuning(2, 0)
+
+
+def kalman_batch(b=4096, t=10_000):
+    mu0, l0, a, off, lq, h = bench_inputs.matern32_ssm(b, t, DEV, jitter_hyper=True)
+    ssm = mf.StateSpaceModel(mu0, l0, a, off, lq)
+    y = torch.randn(b, t, 1, dtype=torch.float64, device=DEV)
+    lr = torch.tensor([[0.1]], dtype=torch.float64, device=DEV)
+    ms = timeit(lambda: mf.kalman_log_likelihood(ssm, h, y, lr))
+    report(f"kalman_loglik B={b} T={t} D=2 f64 [thread per chain]", b * t, (2 * 4 + 2 + 1) * 8, ms,
+           note="H shared over the batch")
+
+
+def cvi5(b=1024, t=10_000):
+    for dtype, s in ((torch.float64, 8), (torch.float32, 4)):
+        th = bench_inputs.cvi_naturals_config5(b, t, DEV, dtype=dtype)
+        ms = timeit(lambda: mf.naturals_to_ssm_params(*th))
+        report(f"naturals_to_ssm_params config5 B={b} T={t} D=2 {dtype}", b * t, (4 * 4 + 2 * 2) * s, ms)
+        p = mf.naturals_to_ssm_params(*th)
+        q = mf.StateSpaceModel(p[4], p[2], p[0], p[1], p[3])
+        ms = timeit(lambda: mf.ssm_to_expectations(q))
+        report(f"ssm_to_expectations config5 B={b} T={t} D=2 {dtype}", b * t, (4 * 4 + 2 * 2) * s, ms)
+        ms = timeit(lambda: mf.ssm_to_naturals(q))
+        report(f"ssm_to_naturals config5 B={b} T={t} D=2 {dtype}", b * t, (4 * 4 + 2 * 2) * s, ms)
+
+
+def ssm(b=4096, t=10_000):
+    mu0, l0, a, off, lq, h = bench_inputs.matern32_ssm(b, t, DEV, jitter_hyper=True)
+    m = mf.StateSpaceModel(mu0, l0, a, off, lq)
+    report("ssm.marginals B=4096 T=1e4 D=2", b * t, (3 * 4 + 2 * 2) * 8, timeit(lambda: m.marginals))
+    report("ssm.precision B=4096 T=1e4 D=2", b * t, (4 * 4) * 8, timeit(lambda: m.precision))
+    x = m.sample(())
+    report("ssm.sample B=4096 T=1e4 D=2 (incl. randn)", b * t, (2 * 4 + 3 * 2) * 8, timeit(lambda: m.sample(())))
+    report("ssm.log_pdf B=4096 T=1e4 D=2", b * t, (2 * 4 + 2 * 2) * 8, timeit(lambda: m.log_pdf(x)))
+    report("ssm.kl_divergence B=4096 T=1e4 D=2", b * t, (4 * 4 + 2 * 2) * 8, timeit(lambda: m.kl_divergence(m)))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["kalman3", "kalman_batch", "cvi5", "ssm"]
+    for w in which:
+        globals()[w]()
+        torch.cuda.empty_cache()
