@@ -50,14 +50,16 @@ SweepPlan make_sweep_plan(int64_t B, int64_t T, int64_t D, int64_t m) {
   if (!p.use) return p;
   const int64_t wave = 148 * (int64_t)kalman_sweep_chains_per_cta(D);
   int64_t ptarget = wave / (B > 0 ? B : 1);
-  if (tuning(2) == 1 || (tuning(2) == 0 && ptarget < 2)) return p;
-  if (ptarget < 2) ptarget = 2;
+  // segment slots come in whole warps (32), so cutting series pays only when a wave holds >= 32
+  // segments per series; otherwise one chain per series
+  if (tuning(2) == 1 || (tuning(2) == 0 && ptarget < 32)) return p;
+  if (ptarget < 32) ptarget = 32;
   int64_t L = (T + ptarget - 1) / ptarget;
   if (L < 64) L = 64;
   L = (L + 7) / 8 * 8;
   if (tuning(3) > 0) L = tuning(3);
   p.L = L;
-  p.P = (T + L - 1) / L;
+  p.P = ((T + L - 1) / L + 31) / 32 * 32;  // segment slots, padded to whole warps (empty = identity)
   const int64_t nt = kalman_sweep_scan_threads(D);
   p.nblk = (p.P + nt - 1) / nt;
   return p;
@@ -193,10 +195,13 @@ int mf_kalman_segment_summary(int dtype, const void* mu0, const void* chol_p0, c
     char* ws = (char*)workspace;
     const KalmanRawArgs r = raw_args(dtype, mu0, chol_p0, a, b, chol_q, h, obs, chol_r, B, T, D,
                                      h_batch, r_steps, first_is_initial);
-    int rc = sweep_summaries(r, sp, w, ws, s);
+    // one pass: per-warp joins of the segment elements, then an ordered reduction
+    if (sp.P == 1) {
+      return kalman_sweep_launch(1, r, 1, T, nullptr, nullptr, 1, 0, out_elem, s, 0);
+    }
+    int rc = kalman_sweep_launch(1, r, sp.P, sp.L, nullptr, nullptr, sp.nblk, 0, ws + w.elems, s, 1);
     if (rc != MF_OK) return rc;
-    return kalman_sweep_top_scan(dtype, D, ws + w.block_agg, nullptr, ws + w.block_prefix, out_elem,
-                                 nullptr, B, sp.nblk, s);
+    return kalman_sweep_reduce(dtype, D, ws + w.elems, out_elem, nullptr, B, sp.P / 32, s);
   }
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
@@ -251,10 +256,9 @@ int mf_kalman_log_likelihood_seeded(int dtype, const void* mu0, const void* chol
     char* ws = (char*)workspace;
     const KalmanRawArgs r = raw_args(dtype, mu0, chol_p0, a, b, chol_q, h, obs, chol_r, B, T, D,
                                      h_batch, r_steps, first_is_initial);
-    if (!summaries_valid) {
-      int rc = sweep_summaries(r, sp, w, ws, s);
-      if (rc != MF_OK) return rc;
-    }
+    // (mf_kalman_segment_summary leaves only per-warp joins behind: always redo the summaries)
+    int rc = sweep_summaries(r, sp, w, ws, s);
+    if (rc != MF_OK) return rc;
     return sweep_seeded(r, sp, w, ws, prefix_elem, out, s);
   }
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
@@ -311,10 +315,11 @@ int mf_kalman_log_likelihood(int dtype, const void* mu0, const void* chol_p0, co
       char* ws = (char*)workspace;
       const KalmanRawArgs r = raw_args(dtype, mu0, chol_p0, a, b, chol_q, h, obs, chol_r, B, T, D,
                                        h_batch, r_steps, 1);
-      int rc = sweep_summaries(r, sp, w, ws, (cudaStream_t)stream);
+      int rc = kalman_sweep_launch(1, r, sp.P, sp.L, nullptr, nullptr, sp.nblk, 0, ws + w.elems,
+                                   (cudaStream_t)stream, 1);
       if (rc != MF_OK) return rc;
-      return kalman_sweep_top_scan(dtype, D, ws + w.block_agg, nullptr, nullptr, nullptr, out, B,
-                                   sp.nblk, (cudaStream_t)stream);
+      return kalman_sweep_reduce(dtype, D, ws + w.elems, nullptr, out, B, sp.P / 32,
+                                 (cudaStream_t)stream);
     }
     // batched filter: one virtual chain per series (also the no-workspace case)
     const KalmanRawArgs r = raw_args(dtype, mu0, chol_p0, a, b, chol_q, h, obs, chol_r, B, T, D,

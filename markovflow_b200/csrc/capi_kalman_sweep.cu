@@ -4,6 +4,8 @@
 #include "kalman_sweep.cuh"
 #include "kalman_sweep_api.h"
 
+#include <type_traits>
+
 namespace mf {
 
 namespace {
@@ -15,7 +17,7 @@ constexpr bool sweep_fits() { return SweepCfg<Core, C, K, NSI, 2>::FITS; }
 // (K = 16 steps per copy) with two compute warps and a double-buffered ring come first.
 template <class Core>
 struct SweepPick {
-  static constexpr bool A = sweep_fits<Core, 64, 16, 2>();
+  static constexpr bool A = sweep_fits<Core, 64, 16, 2>();  // (96, 8, 2) measured ~10 % faster where it fits
   static constexpr bool B = sweep_fits<Core, 32, 16, 3>();
   static constexpr bool Cc = sweep_fits<Core, 32, 16, 2>();
   static constexpr bool Dd = sweep_fits<Core, 32, 8, 3>();
@@ -41,9 +43,41 @@ int dispatch_sweep(int dtype, int64_t D, F&& f) {
 #undef MF_KS_CASE
 }
 
+template <class Core, int C, int K, int NSI>
+int launch_fixed(const typename Core::Params& prm, int64_t nchains, cudaStream_t s) {
+  if constexpr (SweepCfg<Core, C, K, NSI, 2>::FITS) {
+    cudaError_t e = launch_chain_sweep<Core, C, K, NSI, 2>(prm, nchains, s);
+    if (e != cudaSuccess) {
+      set_last_error(cudaGetErrorString(e));
+      return MF_ERR_CUDA;
+    }
+    return MF_OK;
+  } else {
+    return MF_ERR_UNSUPPORTED;
+  }
+}
+
 template <class Core>
 int launch_core(const typename Core::Params& prm, int64_t nchains, cudaStream_t s) {
   using P = SweepPick<Core>;
+  // experiment hook (tuning knob 5) for the config-3 summary core only
+  if constexpr (std::is_same<Core, KalmanSummaryCore<double, 2, false>>::value) {
+    switch (tuning(5)) {
+      case 1: return launch_fixed<Core, 32, 32, 2>(prm, nchains, s);
+      case 2: return launch_fixed<Core, 128, 8, 2>(prm, nchains, s);
+      case 3: return launch_fixed<Core, 32, 16, 3>(prm, nchains, s);
+      case 4: return launch_fixed<Core, 64, 8, 3>(prm, nchains, s);
+      case 5: return launch_fixed<Core, 96, 8, 2>(prm, nchains, s);
+      case 6: return launch_fixed<Core, 32, 8, 3>(prm, nchains, s);
+      case 7: return launch_fixed<Core, 128, 4, 3>(prm, nchains, s);
+      case 8: return launch_fixed<Core, 192, 4, 2>(prm, nchains, s);
+      case 9: return launch_fixed<Core, 64, 4, 3>(prm, nchains, s);
+      case 10: return launch_fixed<Core, 32, 4, 3>(prm, nchains, s);
+      case 11: return launch_fixed<Core, 64, 8, 2>(prm, nchains, s);
+      case 12: return launch_fixed<Core, 160, 4, 2>(prm, nchains, s);
+      default: break;
+    }
+  }
   cudaError_t e = launch_chain_sweep<Core, P::C, P::K, P::NSI, 2>(prm, nchains, s);
   if (e != cudaSuccess) {
     set_last_error(cudaGetErrorString(e));
@@ -63,7 +97,7 @@ int kalman_sweep_scan_threads(int64_t D) { return D <= 2 ? 256 : (D == 3 ? 128 :
 
 int kalman_sweep_launch(int mode, const KalmanRawArgs& r, int64_t P, int64_t L,
                         const void* local_prefix, const void* block_prefix, int64_t nblk,
-                        int have_prefix, void* out, cudaStream_t s) {
+                        int have_prefix, void* out, cudaStream_t s, int reduce_warp) {
   return dispatch_sweep(r.dtype, r.D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
@@ -73,7 +107,7 @@ int kalman_sweep_launch(int mode, const KalmanRawArgs& r, int64_t P, int64_t L,
     p.g.obs = (const Tp*)r.obs; p.g.chol_r = (const Tp*)r.chol_r;
     p.g.B = r.B; p.g.Tn = r.T; p.g.Bh = r.h_batch; p.g.Tr = r.r_steps; p.g.m = 1;
     p.g.first_is_initial = r.first_is_initial;
-    p.P = P; p.L = L;
+    p.P = P; p.L = L; p.reduce_warp = reduce_warp;
     p.local_prefix = (const Tp*)local_prefix; p.block_prefix = (const Tp*)block_prefix;
     p.nblk = nblk; p.scan_nt = ScanNT<kD>::value; p.have_prefix = have_prefix;
     p.out = (Tp*)out;
@@ -113,6 +147,18 @@ int kalman_sweep_top_scan(int dtype, int64_t D, const void* block_agg, const voi
     kalman_top_scan_kernel<Tp, kD, ScanNT<kD>::value><<<(unsigned)B, ScanNT<kD>::value, 0, s>>>(
         (const Tp*)block_agg, (const Tp*)prefix_in, (Tp*)block_prefix, (Tp*)total_out,
         (Tp*)ell_out, nblk);
+    return check_launch();
+  });
+}
+
+int kalman_sweep_reduce(int dtype, int64_t D, const void* elems, void* total_out, void* ell_out,
+                        int64_t B, int64_t P, cudaStream_t s) {
+  return dispatch_sweep(dtype, D, [&](auto tt, auto dd) {
+    using Tp = typename decltype(tt)::type;
+    constexpr int kD = decltype(dd)::value;
+    constexpr int NT = kD <= 2 ? 512 : 256;
+    kalman_reduce_kernel<Tp, kD, NT><<<(unsigned)B, NT, 0, s>>>((const Tp*)elems, (Tp*)total_out,
+                                                               (Tp*)ell_out, P);
     return check_launch();
   });
 }

@@ -254,8 +254,8 @@ __device__ __forceinline__ void chol_psd(T* __restrict__ l, const T* __restrict_
 // out = ei (earlier range) joined with ej (later range).  out may alias neither input.
 //   M = (I + Ci Jj)^{-1} = I - L (I + L^T Jj L)^{-1} L^T Jj,   Ci = L L^T  (I + L^T Jj L is SPD >= I)
 template <typename T, int D>
-__device__ __noinline__ void elem_combine(ScanElem<T, D>& out, const ScanElem<T, D>& ei,
-                                             const ScanElem<T, D>& ej) {
+__device__ __forceinline__ void elem_combine_inl(ScanElem<T, D>& out, const ScanElem<T, D>& ei,
+                                                 const ScanElem<T, D>& ej) {
   constexpr int DD = D * D;
   T L[DD], G[DD], R[DD], rinv[D], tmp[DD];
   chol_psd<T, D>(L, ei.C);
@@ -354,6 +354,13 @@ __device__ __noinline__ void elem_combine(ScanElem<T, D>& out, const ScanElem<T,
       out.J[i * D + j] = v;
       out.J[j * D + i] = v;
     }
+}
+
+// out-of-line flavour for call sites where code size / compile time matter more than latency
+template <typename T, int D>
+__device__ __noinline__ void elem_combine(ScanElem<T, D>& out, const ScanElem<T, D>& ei,
+                                          const ScanElem<T, D>& ej) {
+  elem_combine_inl<T, D>(out, ei, ej);
 }
 
 template <typename T, int D>

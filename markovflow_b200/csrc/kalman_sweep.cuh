@@ -18,13 +18,31 @@ namespace mf {
 template <typename T>
 struct KalmanSweepParams {
   KalmanArgs<T> g;
-  int64_t P, L;            // segments per series, steps per segment
+  int64_t P, L;            // segment slots per series (multiple of 32 when > 1), steps per segment
+  int reduce_warp;         // summaries: emit one element per 32 consecutive segments (out [B,P/32,N])
   const T* local_prefix;   // [B,P,N]   exclusive prefix of the summaries inside their scan block
   const T* block_prefix;   // [B,nblk,N] exclusive prefix of the scan-block aggregates (+ incoming)
   int64_t nblk, scan_nt;
   int have_prefix;         // an incoming prefix exists (segment of a longer series)
   T* out;                  // summaries [B,P,N] | log-likelihood shares [B,P]
 };
+
+template <typename T, int D>
+__device__ __forceinline__ void elem_shfl_up(ScanElem<T, D>& dst, const ScanElem<T, D>& src, int delta) {
+  constexpr int DD = D * D;
+#pragma unroll
+  for (int i = 0; i < DD; ++i) {
+    dst.A[i] = __shfl_up_sync(0xffffffffu, src.A[i], delta);
+    dst.C[i] = __shfl_up_sync(0xffffffffu, src.C[i], delta);
+    dst.J[i] = __shfl_up_sync(0xffffffffu, src.J[i], delta);
+  }
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    dst.b[i] = __shfl_up_sync(0xffffffffu, src.b[i], delta);
+    dst.eta[i] = __shfl_up_sync(0xffffffffu, src.eta[i], delta);
+  }
+  dst.ell = __shfl_up_sync(0xffffffffu, src.ell, delta);
+}
 
 template <typename T_, int D, bool TVR>
 struct KalmanCoreBase {
@@ -45,6 +63,7 @@ struct KalmanCoreBase {
     const int64_t k0 = seg * p.L;
     int64_t steps = p.g.Tn - k0;
     if (steps > p.L) steps = p.L;
+    if (steps < 0) steps = 0;
     const int fi = p.g.first_is_initial;
     const int64_t nt = p.g.Tn - fi;
     constexpr int ES = (int)sizeof(T);
@@ -84,6 +103,7 @@ struct KalmanCoreBase {
     k0_ = seg * p.L;
     steps_ = p.g.Tn - k0_;
     if (steps_ > p.L) steps_ = p.L;
+    if (steps_ < 0) steps_ = 0;  // padding slot past the end of the series: identity element
     w1_ = TVR ? T(1) : Num<T>::rcp(p.g.chol_r[0]);
     wdet_.init();
     nobs_ = 0;
@@ -96,7 +116,26 @@ struct KalmanCoreBase {
                                             int64_t chain, Sink& sink) {
     int n = ns;
     if (j0 + n > steps_) n = (int)(steps_ - j0);
+    if (n <= 0) return;
+    // records are prefetched one step ahead into registers (shared-memory latency off the chain)
+    T F[DD], u[D], Lq[DD], hv[D], yv, rv = T(1);
+    auto fetch = [&](int j) {
+#pragma unroll
+      for (int i = 0; i < DD; ++i) { F[i] = in[0][j * DD + i]; Lq[i] = in[2][j * DD + i]; }
+#pragma unroll
+      for (int i = 0; i < D; ++i) { u[i] = in[1][j * D + i]; hv[i] = in[3][j * D + i]; }
+      yv = in[4][j];
+      if (TVR) rv = in[5][j];
+    };
+    fetch(0);
     for (int j = 0; j < n; ++j) {
+      T cF[DD], cu[D], cLq[DD], ch[D];
+      const T cy = yv, cr = rv;
+#pragma unroll
+      for (int i = 0; i < DD; ++i) { cF[i] = F[i]; cLq[i] = Lq[i]; }
+#pragma unroll
+      for (int i = 0; i < D; ++i) { cu[i] = u[i]; ch[i] = hv[i]; }
+      if (j + 1 < n) fetch(j + 1);
       if (j0 + j == 0 && prior_start_) {
         const int64_t c = chain / p.P;
         T mu[D], L0[DD];
@@ -104,21 +143,15 @@ struct KalmanCoreBase {
         load_vec<T, DD>(L0, p.g.chol_p0 + c * DD);
         sink.start_prior(mu, L0);
       } else {
-        T F[DD], u[D], Lq[DD];
-#pragma unroll
-        for (int i = 0; i < DD; ++i) { F[i] = in[0][j * DD + i]; Lq[i] = in[2][j * DD + i]; }
-#pragma unroll
-        for (int i = 0; i < D; ++i) u[i] = in[1][j * D + i];
-        sink.transition(F, u, Lq);
+        sink.transition(cF, cu, cLq);
       }
       T w = w1_;
-      if (TVR) w = Num<T>::rcp(in[5][j]);
+      if (TVR) w = Num<T>::rcp(cr);
       if (w != T(0)) {  // infinite noise scale: step without observation
-        T hv[D];
 #pragma unroll
-        for (int i = 0; i < D; ++i) hv[i] = in[3][j * D + i] * w;
+        for (int i = 0; i < D; ++i) ch[i] *= w;
         if (TVR) wdet_.mul(w);
-        sink.absorb(hv, in[4][j] * w);
+        sink.absorb(ch, cy * w);
         ++nobs_;
       }
     }
@@ -141,9 +174,24 @@ struct KalmanSummaryCore : KalmanCoreBase<T_, D, TVR> {
   __device__ __forceinline__ void tile(const Params& p, const T* const* in, T* const*, int64_t j0, int ns) {
     this->walk_tile(p, in, j0, ns, chain_, sink);
   }
-  __device__ __forceinline__ void finish(const Params& p, int64_t chain) {
-    sink.finalize(this->log_whiteners(), this->nobs_);
-    elem_store<T, D>(p.out + chain * ScanElem<T, D>::N, sink.e);
+  __device__ __forceinline__ void finish(const Params& p, int64_t chain, bool valid) {
+    if (valid) sink.finalize(this->log_whiteners(), this->nobs_); else sink.init();
+    if (!p.reduce_warp) {
+      if (valid) elem_store<T, D>(p.out + chain * ScanElem<T, D>::N, sink.e);
+      return;
+    }
+    // the 32 segments of a warp are consecutive in time (P is a multiple of 32): join them here
+    const int lane = threadIdx.x & 31;
+    ScanElem<T, D> other, tmp;
+#pragma unroll 1
+    for (int delta = 1; delta < 32; delta <<= 1) {
+      elem_shfl_up<T, D>(other, sink.e, delta);
+      if (lane >= delta) {
+        if (D <= 2) elem_combine_inl<T, D>(tmp, other, sink.e); else elem_combine<T, D>(tmp, other, sink.e);
+        sink.e = tmp;
+      }
+    }
+    if (lane == 31 && valid) elem_store<T, D>(p.out + (chain / 32) * ScanElem<T, D>::N, sink.e);
   }
 };
 
@@ -178,29 +226,12 @@ struct KalmanFilterCore : KalmanCoreBase<T_, D, TVR> {
   __device__ __forceinline__ void tile(const Params& p, const T* const* in, T* const*, int64_t j0, int ns) {
     this->walk_tile(p, in, j0, ns, chain_, sink);
   }
-  __device__ __forceinline__ void finish(const Params& p, int64_t chain) {
-    p.out[chain] = sink.loglik(this->log_whiteners(), this->nobs_);
+  __device__ __forceinline__ void finish(const Params& p, int64_t chain, bool valid) {
+    if (valid) p.out[chain] = sink.loglik(this->log_whiteners(), this->nobs_);
   }
 };
 
 // ---- scans over range elements ----------------------------------------------------------------
-
-template <typename T, int D>
-__device__ __forceinline__ void elem_shfl_up(ScanElem<T, D>& dst, const ScanElem<T, D>& src, int delta) {
-  constexpr int DD = D * D;
-#pragma unroll
-  for (int i = 0; i < DD; ++i) {
-    dst.A[i] = __shfl_up_sync(0xffffffffu, src.A[i], delta);
-    dst.C[i] = __shfl_up_sync(0xffffffffu, src.C[i], delta);
-    dst.J[i] = __shfl_up_sync(0xffffffffu, src.J[i], delta);
-  }
-#pragma unroll
-  for (int i = 0; i < D; ++i) {
-    dst.b[i] = __shfl_up_sync(0xffffffffu, src.b[i], delta);
-    dst.eta[i] = __shfl_up_sync(0xffffffffu, src.eta[i], delta);
-  }
-  dst.ell = __shfl_up_sync(0xffffffffu, src.ell, delta);
-}
 
 // Inclusive warp scan (in time order: lower lanes are earlier).
 template <typename T, int D>
@@ -299,6 +330,60 @@ kalman_top_scan_kernel(const T* __restrict__ block_agg, const T* __restrict__ pr
   if (total_out && threadIdx.x == 0) elem_store<T, D>(total_out + c * N, carry_local);
   // the ell of the join of a whole series (prior first) is its marginal log-likelihood
   if (ell_out && threadIdx.x == 0) ell_out[c] = prefix_in ? carry.ell : carry_local.ell;
+}
+
+// grid (B): ordered reduction of the P elements of one series; ell_out[c] = log-normaliser of the
+// join = the marginal log-likelihood when the first element starts at the prior.  total_out [B,N]
+// optional.  Thread t folds the run [t*r, (t+1)*r) sequentially, then warp-shuffle scans join the
+// NT partial results in time order.
+template <typename T, int D, int NT>
+__global__ void __launch_bounds__(NT)
+kalman_reduce_kernel(const T* __restrict__ elems, T* __restrict__ total_out,
+                     T* __restrict__ ell_out, int64_t P) {
+  constexpr int N = ScanElem<T, D>::N, NW = NT / 32;
+  __shared__ T smem[NW * N];
+  const int64_t c = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r = (P + NT - 1) / NT;
+  const int64_t p0 = threadIdx.x * r;
+  const int64_t p1 = (p0 + r < P) ? p0 + r : P;
+  const T* sp = elems + c * P * N;
+  ScanElem<T, D> acc, nxt, tmp;
+  elem_identity<T, D>(acc);
+  if (p0 < p1) {
+    elem_load<T, D>(acc, sp + p0 * N);
+    for (int64_t p = p0 + 1; p < p1; ++p) {
+      elem_load<T, D>(nxt, sp + p * N);
+      if (D <= 2) elem_combine_inl<T, D>(tmp, acc, nxt); else elem_combine<T, D>(tmp, acc, nxt);
+      acc = tmp;
+    }
+  }
+  // inclusive warp scan (time order); lane 31 then holds the warp's join
+#pragma unroll 1
+  for (int delta = 1; delta < 32; delta <<= 1) {
+    elem_shfl_up<T, D>(nxt, acc, delta);
+    if (lane >= delta) {
+      if (D <= 2) elem_combine_inl<T, D>(tmp, nxt, acc); else elem_combine<T, D>(tmp, nxt, acc);
+      acc = tmp;
+    }
+  }
+  if (lane == 31) elem_store<T, D>(smem + warp * N, acc);
+  __syncthreads();
+  if (warp == 0) {
+    if (lane < NW) elem_load<T, D>(acc, smem + lane * N); else elem_identity<T, D>(acc);
+#pragma unroll 1
+    for (int delta = 1; delta < NW; delta <<= 1) {
+      elem_shfl_up<T, D>(nxt, acc, delta);
+      if (lane >= delta) {
+        if (D <= 2) elem_combine_inl<T, D>(tmp, nxt, acc); else elem_combine<T, D>(tmp, nxt, acc);
+        acc = tmp;
+      }
+    }
+    if (lane == NW - 1) {
+      if (total_out) elem_store<T, D>(total_out + c * N, acc);
+      if (ell_out) ell_out[c] = acc.ell;
+    }
+  }
 }
 
 }  // namespace mf

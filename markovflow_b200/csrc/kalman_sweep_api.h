@@ -23,11 +23,12 @@ int kalman_sweep_chains_per_cta(int64_t D);
 int kalman_sweep_scan_threads(int64_t D);
 
 // mode 0: plain filter, P == 1 (out [B])
-// mode 1: summaries     (out = elems [B,P,N])
+// mode 1: summaries     (out = elems [B,P,N]; with reduce_warp != 0 and P a multiple of 32:
+//                        out = [B,P/32,N], the joins of 32 consecutive segments)
 // mode 2: seeded filter (out = partial [B,P]; needs local/block prefix)
 int kalman_sweep_launch(int mode, const KalmanRawArgs& g, int64_t P, int64_t L,
                         const void* local_prefix, const void* block_prefix, int64_t nblk,
-                        int have_prefix, void* out, cudaStream_t s);
+                        int have_prefix, void* out, cudaStream_t s, int reduce_warp = 0);
 
 // in-place block scan of elems [B,P,N] -> local exclusive prefixes, block_agg [B,nblk,N]
 int kalman_sweep_block_scan(int dtype, int64_t D, void* elems, void* block_agg, int64_t B,
@@ -37,5 +38,9 @@ int kalman_sweep_block_scan(int dtype, int64_t D, void* elems, void* block_agg, 
 int kalman_sweep_top_scan(int dtype, int64_t D, const void* block_agg, const void* prefix_in,
                           void* block_prefix, void* total_out, void* ell_out, int64_t B,
                           int64_t nblk, cudaStream_t s);
+
+// ordered reduction of elems [B,P,N]: total_out [B,N] or NULL, ell_out [B] or NULL
+int kalman_sweep_reduce(int dtype, int64_t D, const void* elems, void* total_out, void* ell_out,
+                        int64_t B, int64_t P, cudaStream_t s);
 
 }  // namespace mf

@@ -31,7 +31,7 @@
 //   __device__ void tile(const Params&, const T* const* in, T* const* out, int64_t j0, int ns)
 //       in[i] / out[i] point at local step j0 of stream i (entries outside the stream's valid
 //       range hold garbage and must not be used); process steps j0..j0+ns-1 (descending if BACKWARD)
-//   __device__ void finish(const Params&, int64_t chain)
+//   __device__ void finish(const Params&, int64_t chain, bool valid)   called by ALL compute threads
 #pragma once
 #include "pipe.cuh"
 
@@ -119,7 +119,7 @@ __device__ __forceinline__ uint32_t sweep_ranges(const SweepSeg& sg, int E, int6
 }
 
 template <class Core, int C, int K, int NSI, int NSO>
-__global__ void __launch_bounds__(SweepCfg<Core, C, K, NSI, NSO>::THREADS, 1)
+__global__ void __launch_bounds__(SweepCfg<Core, C, K, NSI, NSO>::THREADS)
 chain_sweep_kernel(const typename Core::Params prm) {
   using Cfg = SweepCfg<Core, C, K, NSI, NSO>;
   using T = typename Core::T;
@@ -273,7 +273,7 @@ chain_sweep_kernel(const typename Core::Params prm) {
       mbar_arrive(full_out + so);
     }
   }
-  if (valid) core.finish(prm, chain);
+  core.finish(prm, chain, valid);  // all compute threads: cores may use warp collectives here
 }
 
 // Host-side launcher: configures dynamic shared memory once per instantiation.
