@@ -13,8 +13,9 @@
  *   - return MF_OK or an MF_ERR_* status; numerical failure (non-positive pivot) is reported per
  *     chain through `info[b]` = 1-based block index of the first failing pivot (0 = success),
  *     LAPACK convention, replacing TF's "Banded Cholesky decomposition failure" error;
- *   - support dtype MF_F32 / MF_F64 and any D >= 1 (thread-per-chain register kernels for
- *     D <= MF_SMALL_D_MAX, a cooperative shared-memory path above that).
+ *   - support dtype MF_F32 / MF_F64 and 1 <= D <= MF_SMALL_D_MAX (thread-per-chain register
+ *     kernels); mf_btd_cholesky and mf_btd_solve also take MF_SMALL_D_MAX < D <= MF_BIG_D_MAX
+ *     (one warp per chain, rows in registers) -- MF_ERR_UNSUPPORTED otherwise.
  *
  * The mf_host_* variants take HOST pointers and perform the host<->device copies themselves
  * (chunked over the batch and pipelined on internal streams); they are what a host-resident
@@ -38,7 +39,8 @@ extern "C" {
 #define MF_F32 0
 #define MF_F64 1
 
-#define MF_SMALL_D_MAX 8
+#define MF_SMALL_D_MAX 8 /* thread-per-chain register kernels: every entry point */
+#define MF_BIG_D_MAX 32  /* warp-per-chain kernels: mf_btd_cholesky, mf_btd_solve */
 
 /* Library / build information. */
 int mf_version(void);

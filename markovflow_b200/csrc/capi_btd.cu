@@ -150,6 +150,8 @@ int mf_btd_cholesky(int dtype, const void* diag, const void* sub, const void* rh
   if ((rhs != nullptr) != (out_x != nullptr)) return MF_ERR_BAD_ARG;
   if (T == 1) { sub = nullptr; out_sub = nullptr; }
   cudaStream_t s = (cudaStream_t)stream;
+  if (D > MF_SMALL_D_MAX)
+    return big_cholesky(dtype, diag, sub, rhs, out_diag, out_sub, out_x, out_logdet, info, B, T, D, s);
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
@@ -175,6 +177,7 @@ int mf_btd_solve(int dtype, const void* ld, const void* ls, const void* rhs, voi
   if (!rhs || !out) return MF_ERR_BAD_ARG;  // ld == NULL: identity diagonal blocks
   if (T == 1) ls = nullptr;
   cudaStream_t s = (cudaStream_t)stream;
+  if (D > MF_SMALL_D_MAX) return big_solve(dtype, ld, ls, rhs, out, n_rhs, Bm, T, D, transpose, s);
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;

@@ -39,6 +39,13 @@ int dispatch_dtype(int dtype, F&& f) {
   return MF_ERR_BAD_ARG;
 }
 
+// large-block implementations (capi_big.cu)
+int big_cholesky(int dtype, const void* diag, const void* sub, const void* rhs, void* out_diag,
+                 void* out_sub, void* out_x, void* out_logdet, int32_t* info, int64_t B, int64_t T,
+                 int64_t D, cudaStream_t s);
+int big_solve(int dtype, const void* ld, const void* ls, const void* rhs, void* out, int64_t n_rhs,
+              int64_t Bm, int64_t T, int64_t D, int transpose, cudaStream_t s);
+
 inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
 }  // namespace mf
