@@ -134,3 +134,56 @@ def cvi_naturals_config5(b: int, t: int, device, seed: int = SEED, dtype=torch.f
     theta_lin = torch.zeros(b, t, 2, dtype=torch.float64, device=device)
     theta_lin[..., 0] = nat1[..., 0]
     return theta_lin.to(dtype), (-0.5 * pd).to(dtype), (-ps).to(dtype)
+
+
+def sum_kernel_posterior_precision(b: int, t: int, device, seed: int = SEED, r_inv: float = 100.0,
+                                   jitter: float = 1e-6, chunk: int = 8):
+    """Config 4: Sum([Matern52(1,1)] + [HarmonicOscillator(0.5**j, 1/j) for j=1..7], jitter) => D=17,
+    dt ~ U(0.05, 0.15); returns the posterior precision K^-1 + H^T R^-1 H as blocks
+    (diag [b,t,17,17], sub [b,t-1,17,17]) and a N(0,1) right-hand side [b,t,17], float64
+    (``kernels/sde_kernel.py:540-687``, ``kernels/periodic.py:27-187``)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    f64 = torch.float64
+    d = 17
+    diag = torch.empty(b, t, d, d, dtype=f64, device=device)
+    sub = torch.empty(b, t - 1, d, d, dtype=f64, device=device)
+    eye3 = torch.eye(3, dtype=f64, device=device)
+    eye = torch.eye(d, dtype=f64, device=device)
+    lam = math.sqrt(5.0)
+    feedback = torch.tensor([[0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [-lam ** 3, -3 * lam ** 2, -3 * lam]],
+                            dtype=f64, device=device)
+    pinf = torch.zeros(d, d, dtype=f64, device=device)
+    pinf[:3, :3] = torch.tensor([[1.0, 0.0, -lam ** 2 / 3], [0.0, lam ** 2 / 3, 0.0],
+                                 [-lam ** 2 / 3, 0.0, lam ** 4]], dtype=f64, device=device)
+    h = torch.zeros(d, dtype=f64, device=device)
+    h[0] = 1.0
+    for j in range(1, 8):
+        o = 3 + 2 * (j - 1)
+        pinf[o, o] = pinf[o + 1, o + 1] = 0.5 ** j
+        h[o] = 1.0
+    hrh = r_inv * torch.outer(h, h)
+    chol_p0 = torch.linalg.cholesky(pinf)
+    for b0 in range(0, b, chunk):
+        nb = min(chunk, b - b0)
+        dt = 0.05 + 0.1 * torch.rand(nb, t - 1, generator=g, dtype=f64, device=device)
+        a = torch.zeros(nb, t - 1, d, d, dtype=f64, device=device)
+        flt = (feedback + lam * eye3) * dt[..., None, None]
+        a[..., :3, :3] = torch.exp(-lam * dt)[..., None, None] * (eye3 + flt + flt @ flt / 2.0)
+        for j in range(1, 8):
+            o = 3 + 2 * (j - 1)
+            ang = dt * (2.0 * math.pi * j)
+            c, s = torch.cos(ang), torch.sin(ang)
+            a[..., o, o], a[..., o, o + 1], a[..., o + 1, o], a[..., o + 1, o + 1] = c, -s, s, c
+        q = pinf - a @ pinf @ a.transpose(-1, -2) + jitter * eye
+        chol_q = torch.linalg.cholesky(q)
+        inv_q_a = torch.cholesky_solve(a, chol_q)
+        aqa = a.transpose(-1, -2) @ inv_q_a
+        chols = torch.cat([chol_p0.expand(nb, 1, d, d), chol_q], dim=1)
+        dd = torch.cholesky_solve(eye.expand(nb, t, d, d), chols)
+        dd[:, :-1] += aqa
+        dd += hrh
+        diag[b0:b0 + nb] = dd
+        sub[b0:b0 + nb] = -inv_q_a
+        del dt, a, flt, q, chol_q, inv_q_a, aqa, chols, dd
+    rhs = torch.randn(b, t, d, generator=g, dtype=f64, device=device)
+    return diag, sub, rhs

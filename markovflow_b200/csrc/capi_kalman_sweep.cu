@@ -78,12 +78,12 @@ int launch_core(const typename Core::Params& prm, int64_t nchains, cudaStream_t 
       default: break;
     }
   }
-  cudaError_t e = launch_chain_sweep<Core, P::C, P::K, P::NSI, 2>(prm, nchains, s);
-  if (e != cudaSuccess) {
-    set_last_error(cudaGetErrorString(e));
-    return MF_ERR_CUDA;
+  // few chains: one compute warp per CTA so that more SMs get a CTA
+  if constexpr (P::C > 32 && (sweep_fits<Core, 32, 16, 3>() || sweep_fits<Core, 32, 16, 2>())) {
+    if (nchains <= (int64_t)148 * 48)
+      return launch_fixed<Core, 32, 16, sweep_fits<Core, 32, 16, 3>() ? 3 : 2>(prm, nchains, s);
   }
-  return MF_OK;
+  return launch_fixed<Core, P::C, P::K, P::NSI>(prm, nchains, s);
 }
 
 }  // namespace

@@ -2,6 +2,7 @@
 // (include/markovflow_b200.h; reference markovflow/ssm_gaussian_transformations.py).
 #include "dispatch.cuh"
 #include "nat_kernels.cuh"
+#include "ssm_sweep_api.h"
 
 using namespace mf;
 
@@ -15,6 +16,11 @@ int mf_nat_to_ssm(int dtype, const void* theta_lin, const void* theta_diag, cons
   if (!theta_lin || !theta_diag || !out_offsets || !out_chols) return MF_ERR_BAD_ARG;
   if (T > 1 && (!theta_sub || !out_a)) return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (smoothing && D <= kSsmSweepMaxD && T > 1 && tuning(4) != 1) {
+    const int rc = nat_sweep_to_ssm(dtype, D, theta_lin, theta_diag, theta_sub, out_a, out_offsets,
+                                    out_chols, info, B, T, s);
+    if (rc != MF_ERR_UNSUPPORTED) return rc;
+  }
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
@@ -60,6 +66,11 @@ int mf_ssm_to_expectations(int dtype, const void* mu0, const void* chol_p0, cons
   if (!mu0 || !chol_p0 || !eta_lin || !eta_diag) return MF_ERR_BAD_ARG;
   if (T > 1 && (!a || !b || !chol_q || !eta_sub)) return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (D <= kSsmSweepMaxD && T > 1 && tuning(4) != 1) {
+    const int rc = ssm_sweep_moments(dtype, D, 1, mu0, chol_p0, a, b, chol_q, eta_lin, eta_diag,
+                                     eta_sub, B, T, s);
+    if (rc != MF_ERR_UNSUPPORTED) return rc;
+  }
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;

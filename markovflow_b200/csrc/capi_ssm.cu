@@ -1,6 +1,7 @@
 // C-ABI entry points for the StateSpaceModel operators (include/markovflow_b200.h).
 #include "dispatch.cuh"
 #include "ssm_kernels.cuh"
+#include "ssm_sweep_api.h"
 
 using namespace mf;
 
@@ -35,6 +36,10 @@ int mf_ssm_affine_scan(int dtype, const void* mu0, const void* chol_p0, const vo
   if (!mu0 || !out || (T > 1 && (!a || !b))) return MF_ERR_BAD_ARG;
   if (eps && (!chol_p0 || (T > 1 && !chol_q))) return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (D <= kSsmSweepMaxD && T > 1 && tuning(4) != 1) {
+    const int rc = ssm_sweep_affine(dtype, D, mu0, chol_p0, a, b, chol_q, eps, out, n, Bm, T, s);
+    if (rc != MF_ERR_UNSUPPORTED) return rc;
+  }
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
@@ -52,6 +57,11 @@ int mf_ssm_marginals(int dtype, const void* mu0, const void* chol_p0, const void
   if (B == 0) return MF_OK;
   if (!mu0 || !chol_p0 || (T > 1 && (!a || !b || !chol_q))) return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (D <= kSsmSweepMaxD && T > 1 && tuning(4) != 1) {
+    const int rc = ssm_sweep_moments(dtype, D, 0, mu0, chol_p0, a, b, chol_q, out_mean, out_cov,
+                                     out_sub, B, T, s);
+    if (rc != MF_ERR_UNSUPPORTED) return rc;
+  }
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
@@ -98,6 +108,11 @@ int mf_ssm_kl_divergence(int dtype, const void* q_mu0, const void* q_chol_p0, co
   if (!q_mu0 || !q_chol_p0 || !p_mu0 || !p_chol_p0 || !out) return MF_ERR_BAD_ARG;
   if (T > 1 && (!q_a || !q_b || !q_chol_q || !p_a || !p_b || !p_chol_q)) return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (D <= kSsmSweepMaxD && T > 1 && tuning(4) != 1) {
+    const int rc = ssm_sweep_kl(dtype, D, q_mu0, q_chol_p0, q_a, q_b, q_chol_q, p_mu0, p_chol_p0,
+                                p_a, p_b, p_chol_q, out, B, T, s);
+    if (rc != MF_ERR_UNSUPPORTED) return rc;
+  }
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;

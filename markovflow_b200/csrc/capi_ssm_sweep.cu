@@ -1,0 +1,93 @@
+// TMA-sweep implementations of the sequential StateSpaceModel / natural-parameter recurrences
+// (ssm_sweep.cuh); called from capi_ssm.cu and capi_nat.cu through ssm_sweep_api.h.
+#include "dispatch.cuh"
+#include "ssm_sweep.cuh"
+#include "ssm_sweep_api.h"
+
+namespace mf {
+
+namespace {
+
+template <class F>
+int dispatch_ssm_sweep(int dtype, int64_t D, F&& f) {
+  if (dtype != MF_F32 && dtype != MF_F64) return MF_ERR_BAD_ARG;
+#define MF_SS_CASE(n)                                                 \
+  case n:                                                             \
+    if (dtype == MF_F64) return f(TypeTag<double>{}, IntTag<n>{});    \
+    return f(TypeTag<float>{}, IntTag<n>{});
+  switch (D) {
+    MF_SS_CASE(1) MF_SS_CASE(2) MF_SS_CASE(3) MF_SS_CASE(4)
+    default: return MF_ERR_UNSUPPORTED;
+  }
+#undef MF_SS_CASE
+}
+
+template <class Core>
+int run(const typename Core::Params& p, int64_t nchains, cudaStream_t s) {
+  if constexpr (SweepAuto<Core>::ok) {
+    cudaError_t e = SweepAuto<Core>::launch(p, nchains, s);
+    if (e != cudaSuccess) {
+      set_last_error(cudaGetErrorString(e));
+      return MF_ERR_CUDA;
+    }
+    return MF_OK;
+  } else {
+    return MF_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace
+
+int ssm_sweep_moments(int dtype, int64_t D, int expectations, const void* mu0, const void* chol_p0,
+                      const void* a, const void* b, const void* chol_q, void* o_vec, void* o_diag,
+                      void* o_sub, int64_t B, int64_t T, cudaStream_t s) {
+  return dispatch_ssm_sweep(dtype, D, [&](auto tt, auto dd) {
+    using Tp = typename decltype(tt)::type;
+    constexpr int kD = decltype(dd)::value;
+    SsmMomentsParams<Tp> p{(const Tp*)mu0, (const Tp*)chol_p0, (const Tp*)a, (const Tp*)b,
+                           (const Tp*)chol_q, (Tp*)o_vec, (Tp*)o_diag, (Tp*)o_sub, B, T};
+    if (expectations) return run<SsmMomentsCore<Tp, kD, true>>(p, B, s);
+    return run<SsmMomentsCore<Tp, kD, false>>(p, B, s);
+  });
+}
+
+int ssm_sweep_affine(int dtype, int64_t D, const void* mu0, const void* chol_p0, const void* a,
+                     const void* b, const void* chol_q, const void* eps, void* out, int64_t n,
+                     int64_t Bm, int64_t T, cudaStream_t s) {
+  return dispatch_ssm_sweep(dtype, D, [&](auto tt, auto dd) {
+    using Tp = typename decltype(tt)::type;
+    constexpr int kD = decltype(dd)::value;
+    SsmAffineParams<Tp> p{(const Tp*)mu0, (const Tp*)chol_p0, (const Tp*)a, (const Tp*)b,
+                          (const Tp*)chol_q, (const Tp*)eps, (Tp*)out, n, Bm, T};
+    if (eps) return run<SsmAffineCore<Tp, kD, true>>(p, n, s);
+    return run<SsmAffineCore<Tp, kD, false>>(p, n, s);
+  });
+}
+
+int ssm_sweep_kl(int dtype, int64_t D, const void* q_mu0, const void* q_chol_p0, const void* q_a,
+                 const void* q_b, const void* q_chol_q, const void* p_mu0, const void* p_chol_p0,
+                 const void* p_a, const void* p_b, const void* p_chol_q, void* out, int64_t B,
+                 int64_t T, cudaStream_t s) {
+  return dispatch_ssm_sweep(dtype, D, [&](auto tt, auto dd) {
+    using Tp = typename decltype(tt)::type;
+    constexpr int kD = decltype(dd)::value;
+    SsmKlParams<Tp> p{(const Tp*)q_mu0, (const Tp*)q_chol_p0, (const Tp*)q_a, (const Tp*)q_b,
+                      (const Tp*)q_chol_q, (const Tp*)p_mu0, (const Tp*)p_chol_p0, (const Tp*)p_a,
+                      (const Tp*)p_b, (const Tp*)p_chol_q, (Tp*)out, B, T};
+    return run<SsmKlCore<Tp, kD>>(p, B, s);
+  });
+}
+
+int nat_sweep_to_ssm(int dtype, int64_t D, const void* th_lin, const void* th_diag,
+                     const void* th_sub, void* out_a, void* out_off, void* out_chol, int32_t* info,
+                     int64_t B, int64_t T, cudaStream_t s) {
+  return dispatch_ssm_sweep(dtype, D, [&](auto tt, auto dd) {
+    using Tp = typename decltype(tt)::type;
+    constexpr int kD = decltype(dd)::value;
+    NatToSsmParams<Tp> p{(const Tp*)th_lin, (const Tp*)th_diag, (const Tp*)th_sub, (Tp*)out_a,
+                         (Tp*)out_off, (Tp*)out_chol, info, B, T};
+    return run<NatToSsmCore<Tp, kD>>(p, B, s);
+  });
+}
+
+}  // namespace mf

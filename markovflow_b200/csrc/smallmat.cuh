@@ -17,7 +17,7 @@ template <> struct Num<double> {
   static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
 };
 template <> struct Num<float> {
-  static __device__ __forceinline__ float rsqrt(float x) { return 1.0f / ::sqrtf(x); }
+  static __device__ __forceinline__ float rsqrt(float x) { return ::rsqrtf(x); }
   static __device__ __forceinline__ float log(float x) { return ::logf(x); }
   static __device__ __forceinline__ float fma(float a, float b, float c) { return ::fmaf(a, b, c); }
   static __device__ __forceinline__ float abs(float x) { return ::fabsf(x); }
