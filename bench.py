@@ -139,6 +139,125 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _timed(fn, warm=3, reps=10):
+    import torch
+
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(reps):
+        a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        z.record()
+        evs.append((a, z))
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(z) for a, z in evs)
+    return ts[len(ts) // 2]
+
+
+def extra_measurements(dev, rank, world, dist, peak):
+    """The other BASELINE configurations (not the headline line): Kalman log-likelihood of ONE long
+    series (config 3; time-sharded over the ranks when world > 1), the CVI parameter transforms
+    (config 5, f64 and f32) and the large-block factorisation (config 4 at reduced T).  Device-
+    resident inputs, CUDA-event timing, median of 10; roofline on SURVEY.md §8d's algorithmic bytes."""
+    import torch
+
+    import bench_inputs
+    import markovflow_b200 as mf
+    from markovflow_b200 import _lib
+    from markovflow_b200.parallel import CudaKalmanEngine, time_segment
+
+    out = {}
+
+    def entry(steps, bytes_per_step, ms, **kw):
+        gbs = steps * bytes_per_step / (ms * 1e-3) / 1e9
+        return {"state_steps_per_s": steps / (ms * 1e-3), "ms": ms, "bytes_per_state_step": bytes_per_step,
+                "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peak, **kw}
+
+    # ---- config 3: one Matern32 series, T = 1e7, float64 Kalman log-likelihood -------------------
+    t3 = 10_000_000
+    ssm, h, y, lr = bench_inputs.kalman_inputs_config3(t3, dev)
+    if world == 1:
+        ms = _timed(lambda: mf.kalman_log_likelihood(ssm, h, y, lr))
+        ll = float(mf.kalman_log_likelihood(ssm, h, y, lr))
+        out["config3_kalman_loglik"] = entry(
+            t3, 104, ms, workload="Matern32 D=2, single series T=1e7, f64, parallel-in-time "
+            "(one pass: per-segment scan elements + ordered reduction)", loglik=ll, scaling="single GPU")
+    else:
+        mu0, l0, a, b, lq, bsz, t, d = ssm._flat()
+        seg = time_segment(mu0, l0, a, b, lq, h.reshape(1, t, 1, d), y.reshape(1, t, 1),
+                           lr.reshape(1, 1, 1), rank, world)
+        eng = CudaKalmanEngine()
+
+        def sharded():
+            elem = eng.segment_summary(seg)
+            gathered = [torch.empty_like(elem) for _ in range(world)]
+            dist.all_gather(gathered, elem)
+            return eng.fold(torch.stack(gathered), d)[:, -1]
+
+        ms = _timed(sharded)
+        tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ll = float(sharded()[0])
+        ref = float(mf.kalman_log_likelihood(ssm, h, y, lr)) if rank == 0 else None
+        out["config3_kalman_loglik"] = entry(
+            t3, 104, float(tms.item()), workload=f"Matern32 D=2, single series T=1e7, f64, time-sharded "
+            f"over {world} GPUs: local segment element, NCCL all-gather of {world} x 136 B, ordered fold",
+            loglik=ll, loglik_single_gpu=ref, scaling="strong",
+            frac_note="fraction of the AGGREGATE peak = frac_of_hbm_peak / n_gpus")
+    del ssm, h, y
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return out
+
+    # ---- config 5: CVI site update, B = 1024 chains x M = 1e4 inducing states, D = 2 ---------------
+    b5, t5 = 1024, 10_000
+    th64 = bench_inputs.cvi_naturals_config5(b5, t5, dev, dtype=torch.float64)
+    ref = mf.naturals_to_ssm_params(*th64)
+    for dtype, es, tag in ((torch.float64, 8, "f64"), (torch.float32, 4, "f32")):
+        th = tuple(x.to(dtype) for x in th64)
+        ms = _timed(lambda: mf.naturals_to_ssm_params(*th))
+        got = mf.naturals_to_ssm_params(*th)
+        err = max(float((g.double() - r).abs().max() / r.abs().max()) for g, r in zip(got, ref))
+        out[f"config5_naturals_to_ssm_params_{tag}"] = entry(
+            b5 * t5, 20 * es, ms, workload="Matern32 prior + sites, B=1024 x M=1e4, D=2",
+            max_rel_err_vs_f64=err)
+        q = mf.StateSpaceModel(got[4], got[2], got[0], got[1], got[3])
+        ms = _timed(lambda: mf.ssm_to_expectations(q))
+        out[f"config5_ssm_to_expectations_{tag}"] = entry(b5 * t5, 20 * es, ms)
+    del th64, ref, th, got, q
+    torch.cuda.empty_cache()
+
+    # ---- config 4 at reduced T: D = 17 sum kernel, B = 256, in-place Cholesky + solve -------------
+    b4, t4 = 256, 4000
+    diag, sub, rhs = bench_inputs.sum_kernel_posterior_precision(b4, t4, dev)
+    d0, s0 = diag.clone(), sub.clone()
+    x = torch.empty_like(rhs)
+    info = torch.empty(b4, dtype=torch.int32, device=dev)
+    lib = _lib.lib()
+    ts = []
+    for _ in range(4):
+        diag.copy_(d0)
+        sub.copy_(s0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.mf_btd_cholesky(_lib.MF_F64, _lib.ptr(diag), _lib.ptr(sub), _lib.ptr(rhs),
+                                       _lib.ptr(diag), _lib.ptr(sub), _lib.ptr(x), None, _lib.ptr(info),
+                                       _lib.i64(b4), _lib.i64(t4), _lib.i64(17), _lib.current_stream()),
+                   "mf_btd_cholesky")
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    assert int(info.abs().max()) == 0
+    out["config4_cholesky_solve_d17"] = entry(
+        b4 * t4, 9520, sorted(ts[1:])[1], workload=f"Matern52 + 7 harmonics (D=17), B=256 x T={t4} "
+        "(full config: T=1e5), f64, in place, one warp per chain")
+    return out
+
+
 def run_gpu(args):
     import torch
 
@@ -195,10 +314,10 @@ def run_gpu(args):
             z.record()
         e1.record()
         barrier()
-        if args.steps * 4 < 400:  # keep the sampled window long enough for a few clock samples
-            for _ in range(60):
-                step()
-            torch.cuda.synchronize()
+        # keep the sampled window long enough (~1.5 s) for several nvidia-smi samples under load
+        for _ in range(max(0, 450 - args.steps)):
+            step()
+        torch.cuda.synchronize()
     total_ms = max_over_ranks(e0.elapsed_time(e1))
     kernel_ms = statistics.mean(a.elapsed_time(z) for a, z in evs)
     assert int(info.max()) == 0, "synthetic precision was not positive definite"
@@ -251,12 +370,18 @@ def run_gpu(args):
         if rank == 0:
             assert torch.equal(out[0][::512], od[::512].cpu()), "e2e result differs from device-resident result"
 
+    peak, peak_src = measured_peak()
+    extras = None
+    if not args.no_extras:
+        del diag, sub, rhs, od, os_, ox
+        torch.cuda.empty_cache()
+        extras = extra_measurements(dev, rank, world, dist, peak)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    peak, peak_src = measured_peak()
     achieved = ALGO_BYTES_PER_STEP * b * T / (kernel_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -281,7 +406,7 @@ def run_gpu(args):
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "kernel": "btd_chol_tma_kernel<double,3,rhs>", "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_state_step": ALGO_BYTES_PER_STEP},
-        "cpu_baseline": cpu, "clocks": clocks.summary(),
+        "cpu_baseline": cpu, "clocks": clocks.summary(), "extra": extras,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -296,6 +421,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config 3/4/5 measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
