@@ -150,6 +150,8 @@ int mf_btd_cholesky(int dtype, const void* diag, const void* sub, const void* rh
   if ((rhs != nullptr) != (out_x != nullptr)) return MF_ERR_BAD_ARG;
   if (T == 1) { sub = nullptr; out_sub = nullptr; }
   cudaStream_t s = (cudaStream_t)stream;
+  if (tuning(6) > 0 && D == 3 && dtype == MF_F64 && sub && rhs && T > 1)
+    return exp_chol_d3(tuning(6) - 1, diag, sub, rhs, out_diag, out_sub, out_x, out_logdet, info, B, T, s);
   if (D > MF_SMALL_D_MAX)
     return big_cholesky(dtype, diag, sub, rhs, out_diag, out_sub, out_x, out_logdet, info, B, T, D, s);
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {

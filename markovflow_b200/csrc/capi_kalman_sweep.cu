@@ -17,13 +17,16 @@ constexpr bool sweep_fits() { return SweepCfg<Core, C, K, NSI, 2>::FITS; }
 // (K = 16 steps per copy) with two compute warps and a double-buffered ring come first.
 template <class Core>
 struct SweepPick {
-  static constexpr bool A = sweep_fits<Core, 64, 16, 2>();  // (96, 8, 2) measured ~10 % faster where it fits
+  // measured on config 3 (ping-pong prefetch cores): (64, 16, 2) 0.213 ms < (64, 12, 2) 0.236 <
+  // (96, 10, 2) 0.253 < (96, 8, 2) 0.267 < (128, 6, 2) 0.298: long tiles win (TMA issue per copy)
+  static constexpr bool Z = sweep_fits<Core, 96, 8, 2>();
+  static constexpr bool A = sweep_fits<Core, 64, 16, 2>();
   static constexpr bool B = sweep_fits<Core, 32, 16, 3>();
   static constexpr bool Cc = sweep_fits<Core, 32, 16, 2>();
   static constexpr bool Dd = sweep_fits<Core, 32, 8, 3>();
-  static constexpr int C = A ? 64 : 32;
-  static constexpr int K = (A || B || Cc) ? 16 : (Dd ? 8 : 4);
-  static constexpr int NSI = A ? 2 : (B ? 3 : (Cc ? 2 : 3));
+  static constexpr int C = A ? 64 : (Z ? 96 : 32);
+  static constexpr int K = A ? 16 : (Z ? 8 : ((B || Cc) ? 16 : (Dd ? 8 : 4)));
+  static constexpr int NSI = A ? 2 : (Z ? 2 : (B ? 3 : (Cc ? 2 : 3)));
   static_assert(sweep_fits<Core, C, K, NSI>(), "no sweep configuration fits");
 };
 
@@ -57,9 +60,17 @@ int launch_fixed(const typename Core::Params& prm, int64_t nchains, cudaStream_t
   }
 }
 
+}  // namespace
+int exp_kalman_summary_d2(int variant, const KalmanSweepParams<double>& p, int64_t nchains,
+                          cudaStream_t s);
+namespace {
+
 template <class Core>
 int launch_core(const typename Core::Params& prm, int64_t nchains, cudaStream_t s) {
   using P = SweepPick<Core>;
+  if constexpr (std::is_same<Core, KalmanSummaryCore<double, 2, false>>::value) {
+    if (tuning(6) > 0) return exp_kalman_summary_d2(tuning(6) - 1, prm, nchains, s);
+  }
   // experiment hook (tuning knob 5) for the config-3 summary core only
   if constexpr (std::is_same<Core, KalmanSummaryCore<double, 2, false>>::value) {
     switch (tuning(5)) {
@@ -75,6 +86,10 @@ int launch_core(const typename Core::Params& prm, int64_t nchains, cudaStream_t 
       case 10: return launch_fixed<Core, 32, 4, 3>(prm, nchains, s);
       case 11: return launch_fixed<Core, 64, 8, 2>(prm, nchains, s);
       case 12: return launch_fixed<Core, 160, 4, 2>(prm, nchains, s);
+      case 13: return launch_fixed<Core, 96, 10, 2>(prm, nchains, s);
+      case 14: return launch_fixed<Core, 128, 6, 2>(prm, nchains, s);
+      case 15: return launch_fixed<Core, 64, 16, 2>(prm, nchains, s);
+      case 16: return launch_fixed<Core, 64, 12, 2>(prm, nchains, s);
       default: break;
     }
   }

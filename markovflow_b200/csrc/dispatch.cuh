@@ -46,6 +46,10 @@ int big_cholesky(int dtype, const void* diag, const void* sub, const void* rhs, 
 int big_solve(int dtype, const void* ld, const void* ls, const void* rhs, void* out, int64_t n_rhs,
               int64_t Bm, int64_t T, int64_t D, int transpose, cudaStream_t s);
 
+// experimental engine variants (capi_exp.cu), selected with mf_set_tuning knob 6 (> 0: variant - 1)
+int exp_chol_d3(int variant, const void* diag, const void* sub, const void* rhs, void* od, void* os,
+                void* ox, void* logdet, int32_t* info, int64_t B, int64_t T, cudaStream_t s);
+
 inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
 }  // namespace mf

@@ -116,7 +116,7 @@ __device__ __forceinline__ void filter_absorb(FilterState<T, D>& st, const T* __
   const T rs = Num<T>::rcp(s);
   const T vs = v * rs;
   quad = Num<T>::fma(v, vs, quad);
-  det.mul(s);
+  det.mul_lazy(s);  // caller peels (at least every few absorptions)
 #pragma unroll
   for (int i = 0; i < D; ++i) {
     st.m[i] = Num<T>::fma(g[i], vs, st.m[i]);
@@ -203,7 +203,7 @@ __device__ __forceinline__ void elem_absorb(ScanElem<T, D>& e, const T* __restri
   const T rs = Num<T>::rcp(s);
   const T vs = v * rs;
   quad = Num<T>::fma(v, vs, quad);
-  det.mul(s);
+  det.mul_lazy(s);  // caller peels (at least every few absorptions)
 #pragma unroll
   for (int i = 0; i < D; ++i) {
     const T ki = g[i] * rs;

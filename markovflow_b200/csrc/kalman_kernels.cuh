@@ -104,6 +104,7 @@ __device__ __forceinline__ T kalman_walk(const KalmanArgs<T>& g, int64_t c, int6
         ++nobs;
       }
     }
+    sink.det.peel();
   }
   logw = wdet.log_abs();
   return logw;

@@ -117,43 +117,59 @@ struct KalmanCoreBase {
     int n = ns;
     if (j0 + n > steps_) n = (int)(steps_ - j0);
     if (n <= 0) return;
-    // records are prefetched one step ahead into registers (shared-memory latency off the chain)
-    T F[DD], u[D], Lq[DD], hv[D], yv, rv = T(1);
-    auto fetch = [&](int j) {
-#pragma unroll
-      for (int i = 0; i < DD; ++i) { F[i] = in[0][j * DD + i]; Lq[i] = in[2][j * DD + i]; }
-#pragma unroll
-      for (int i = 0; i < D; ++i) { u[i] = in[1][j * D + i]; hv[i] = in[3][j * D + i]; }
-      yv = in[4][j];
-      if (TVR) rv = in[5][j];
+    // Records are prefetched one step ahead into two ping-pong register sets (shared-memory latency
+    // off the dependent chain, no register-to-register copies).
+    struct Rec {
+      T F[DD], u[D], Lq[DD], h[D], y, r;
     };
-    fetch(0);
-    for (int j = 0; j < n; ++j) {
-      T cF[DD], cu[D], cLq[DD], ch[D];
-      const T cy = yv, cr = rv;
+    auto fetch = [&](Rec& rec, int j) {
 #pragma unroll
-      for (int i = 0; i < DD; ++i) { cF[i] = F[i]; cLq[i] = Lq[i]; }
+      for (int i = 0; i < DD; ++i) { rec.F[i] = in[0][j * DD + i]; rec.Lq[i] = in[2][j * DD + i]; }
 #pragma unroll
-      for (int i = 0; i < D; ++i) { cu[i] = u[i]; ch[i] = hv[i]; }
-      if (j + 1 < n) fetch(j + 1);
-      if (j0 + j == 0 && prior_start_) {
+      for (int i = 0; i < D; ++i) { rec.u[i] = in[1][j * D + i]; rec.h[i] = in[3][j * D + i]; }
+      rec.y = in[4][j];
+      rec.r = TVR ? in[5][j] : T(1);
+    };
+    auto step = [&](Rec& rec, bool from_prior) {
+      if (from_prior) {
         const int64_t c = chain / p.P;
         T mu[D], L0[DD];
         load_vec<T, D>(mu, p.g.mu0 + c * D);
         load_vec<T, DD>(L0, p.g.chol_p0 + c * DD);
         sink.start_prior(mu, L0);
       } else {
-        sink.transition(cF, cu, cLq);
+        sink.transition(rec.F, rec.u, rec.Lq);
       }
       T w = w1_;
-      if (TVR) w = Num<T>::rcp(cr);
-      if (w != T(0)) {  // infinite noise scale: step without observation
+      if (TVR) w = Num<T>::rcp(rec.r);
+      if (!TVR || w != T(0)) {  // per-step noise: an infinite scale marks a step without observation
 #pragma unroll
-        for (int i = 0; i < D; ++i) ch[i] *= w;
+        for (int i = 0; i < D; ++i) rec.h[i] *= w;
         if (TVR) wdet_.mul(w);
-        sink.absorb(ch, cy * w);
+        sink.absorb(rec.h, rec.y * w);
         ++nobs_;
       }
+    };
+    Rec ra, rb;
+    fetch(ra, 0);
+    int j = 0;
+    if (j0 == 0 && prior_start_) {  // the chain's very first step starts from the prior
+      if (n > 1) fetch(rb, 1);
+      step(ra, true);
+      sink.det.peel();
+      j = 1;
+      if (n > 1) ra = rb;
+    }
+    for (; j + 1 < n; j += 2) {
+      fetch(rb, j + 1);
+      step(ra, false);
+      if (j + 2 < n) fetch(ra, j + 2);
+      step(rb, false);
+      sink.det.peel();  // two pivots multiplied per renormalisation
+    }
+    if (j < n) {
+      step(ra, false);
+      sink.det.peel();
     }
   }
 };

@@ -19,8 +19,13 @@ struct LogProd {
   T prod;
   int esum;
   __device__ __forceinline__ void init() { prod = T(1); esum = 0; }
+  // multiply without renormalising: the caller must peel() before the product can overflow
+  __device__ __forceinline__ void mul_lazy(T v) { prod *= v; }
   __device__ __forceinline__ void mul(T v) {
     prod *= v;
+    peel();
+  }
+  __device__ __forceinline__ void peel() {
     if (sizeof(T) == 8) {
       const int hi = __double2hiint((double)prod);
       const int e = ((hi >> 20) & 0x7ff) - 1023;

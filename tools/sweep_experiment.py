@@ -12,14 +12,13 @@ dev = torch.device("cuda:0")
 t = 10_000_000
 ssm, h, y, lr = bench_inputs.kalman_inputs_config3(t, dev)
 lib = _lib.lib()
-names = {0: "C64 K16 S2", 5: "C96 K8 S2", 6: "C32 K8 S3", 7: "C128 K4 S3", 8: "C192 K4 S2", 9: "C64 K4 S3",
-         10: "C32 K4 S3", 11: "C64 K8 S2", 12: "C160 K4 S2"}
-cpw = {0: 64, 5: 96, 6: 64, 7: 128, 8: 192, 9: 128, 10: 128, 11: 128, 12: 160}
+names = {0: "default C96 K8 S2", 13: "C96 K10 S2", 14: "C128 K6 S2", 15: "C64 K16 S2", 16: "C64 K12 S2"}
+cpw = {0: 96, 13: 96, 14: 128, 15: 64, 16: 64}
 for knob, name in names.items():
-    for waves in (1, 2, 3):
+    for waves in (1,):
         lib.mf_set_tuning(5, knob)
         L = -(-t // (148 * cpw[knob] * waves))
-        L = (L + 31) // 32 * 32
+        L = (L + 7) // 8 * 8
         lib.mf_set_tuning(3, L)
         lib.mf_set_tuning(2, 2)
         try:
