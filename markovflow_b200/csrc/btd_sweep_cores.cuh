@@ -1,0 +1,233 @@
+// The remaining sequential block-tridiagonal recurrences on the TMA chain sweep (sweep.cuh): the
+// arithmetic of the thread-per-chain kernels of btd_direct.cuh with every per-step record streamed
+// through the shared-memory ring instead of being read from global memory on the critical path.
+//
+//   BtdSolveCore      forward / backward : LowerTriangularBlockTriDiagonal.solve
+//                                          (reference block_tri_diag.py:339-351, solve_triang_mat :350)
+//   BtdInvSubsetCore  backward           : block_diagonal_of_inverse + sub-diagonal blocks
+//                                          (:318-337, inverse_from_cholesky_band :331)
+//   BtdUduCore        backward           : upper_diagonal_lower (:438-545)
+#pragma once
+#include "ssm_sweep.cuh"
+
+namespace mf {
+
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct BtdSolveParams {
+  const T *ld, *ls, *rhs;
+  T* out;
+  int64_t n, Bm, Tn;
+};
+
+// forward : x_k = Ld_k^{-1} (b_k - Ls_{k-1} x_{k-1});  backward: x_k = Ld_k^{-T} (b_k - Ls_k^T x_{k+1}).
+// UNIT: identity diagonal blocks (ld == NULL);  SUB: a sub-diagonal exists.
+template <typename T_, int D, bool TRANSPOSE, bool UNIT, bool SUB>
+struct BtdSolveCore {
+  using T = T_;
+  using Params = BtdSolveParams<T>;
+  static constexpr int DD = D * D;
+  static constexpr int NIN = 1 + (UNIT ? 0 : 1) + (SUB ? 1 : 0), NOUT = 1;
+  static constexpr bool BACKWARD = TRANSPOSE;
+  static constexpr int I_LD = UNIT ? -1 : 1, I_LS = SUB ? (UNIT ? 1 : 2) : -1;
+  static constexpr int ein(int i) { return i == 0 ? D : DD; }
+  static constexpr int eout(int) { return D; }
+  static __device__ __forceinline__ int64_t num_chains(const Params& p) { return p.n; }
+  static __device__ __forceinline__ int64_t max_steps(const Params& p) { return p.Tn; }
+  static __device__ __forceinline__ StreamGeom in_geom(const Params& p, int i, int64_t c) {
+    if (i == 0) return geom_states<T>(p.rhs, c, p.Tn, D);
+    if (i == I_LD) return geom_states<T>(p.ld, c % p.Bm, p.Tn, DD);
+    // forward needs Ls_{k-1} at step k (incoming), backward needs Ls_k at step k (outgoing)
+    return TRANSPOSE ? geom_outgoing<T>(p.ls, c % p.Bm, p.Tn, DD) : geom_incoming<T>(p.ls, c % p.Bm, p.Tn, DD);
+  }
+  static __device__ __forceinline__ StreamGeom out_geom(const Params& p, int, int64_t c) {
+    return geom_states<T>(p.out, c, p.Tn, D);
+  }
+  T x[D];
+  int64_t Tn_;
+  __device__ __forceinline__ void init(const Params& p, int64_t) {
+    Tn_ = p.Tn;
+#pragma unroll
+    for (int i = 0; i < D; ++i) x[i] = T(0);
+  }
+  __device__ __forceinline__ void step(const T* const* in, T* const* out, int j, int64_t k) {
+    T r[D];
+    ld_s<T, D>(r, in[0] + j * D);
+    if (SUB) {
+      const bool coupled = TRANSPOSE ? (k + 1 < Tn_) : (k > 0);
+      if (coupled) {
+        T A[DD];
+        ld_s<T, DD>(A, in[I_LS < 0 ? 0 : I_LS] + j * DD);
+        if (TRANSPOSE) gemv_t_sub<T, D>(r, A, x);
+        else gemv_sub<T, D>(r, A, x);
+      }
+    }
+    if (!UNIT) {
+      T L[DD], rinv[D];
+      ld_s<T, DD>(L, in[I_LD < 0 ? 0 : I_LD] + j * DD);
+#pragma unroll
+      for (int q = 0; q < D; ++q) rinv[q] = Num<T>::rcp(L[q * D + q]);
+      if (TRANSPOSE) trsv_lower_t<T, D>(L, rinv, r);
+      else trsv_lower<T, D>(L, rinv, r);
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) x[i] = r[i];
+    st_s<T, D>(out[0] + j * D, x);
+  }
+  __device__ __forceinline__ void tile(const Params&, const T* const* in, T* const* out, int64_t j0,
+                                       int ns) {
+    if (TRANSPOSE) {
+      for (int j = ns - 1; j >= 0; --j) step(in, out, j, j0 + j);
+    } else {
+      for (int j = 0; j < ns; ++j) step(in, out, j, j0 + j);
+    }
+  }
+  __device__ __forceinline__ void finish(const Params&, int64_t, bool) {}
+};
+
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct BtdInvSubsetParams {
+  const T *ld, *ls;
+  T *od, *os;
+  int64_t B, Tn;
+};
+
+// Sigma_{T-1,T-1} = (Ld Ld^T)^{-1};  J_k = Ls_k Ld_k^{-1};  Sigma_{k+1,k} = -Sigma_{k+1,k+1} J_k;
+// Sigma_kk = (Ld_k Ld_k^T)^{-1} - J_k^T Sigma_{k+1,k}
+template <typename T_, int D, bool WANT_SUB>
+struct BtdInvSubsetCore {
+  using T = T_;
+  using Params = BtdInvSubsetParams<T>;
+  static constexpr int DD = D * D;
+  static constexpr int NIN = 2, NOUT = WANT_SUB ? 2 : 1;
+  static constexpr bool BACKWARD = true;
+  static constexpr int ein(int) { return DD; }
+  static constexpr int eout(int) { return DD; }
+  static __device__ __forceinline__ int64_t num_chains(const Params& p) { return p.B; }
+  static __device__ __forceinline__ int64_t max_steps(const Params& p) { return p.Tn; }
+  static __device__ __forceinline__ StreamGeom in_geom(const Params& p, int i, int64_t c) {
+    if (i == 0) return geom_states<T>(p.ld, c, p.Tn, DD);
+    return geom_outgoing<T>(p.ls, c, p.Tn, DD);
+  }
+  static __device__ __forceinline__ StreamGeom out_geom(const Params& p, int i, int64_t c) {
+    if (i == 0) return geom_states<T>(p.od, c, p.Tn, DD);
+    return geom_outgoing<T>(p.os, c, p.Tn, DD);
+  }
+  T sig[DD];
+  int64_t Tn_;
+  __device__ __forceinline__ void init(const Params& p, int64_t) {
+    Tn_ = p.Tn;
+#pragma unroll
+    for (int i = 0; i < DD; ++i) sig[i] = T(0);
+  }
+  __device__ __forceinline__ void tile(const Params&, const T* const* in, T* const* out, int64_t j0,
+                                       int ns) {
+    for (int j = ns - 1; j >= 0; --j) {
+      const int64_t k = j0 + j;
+      T L[DD], loc[DD], rinv[D];
+      ld_s<T, DD>(L, in[0] + j * DD);
+#pragma unroll
+      for (int q = 0; q < D; ++q) rinv[q] = Num<T>::rcp(L[q * D + q]);
+      chol_inverse<T, D>(loc, L, rinv);
+      if (k + 1 < Tn_) {
+        T J[DD], ssub[DD];
+        ld_s<T, DD>(J, in[1] + j * DD);
+        trsm_right_lower<T, D>(J, L, rinv);  // J = Ls Ld^{-1}
+        gemm<T, D>(ssub, sig, J);            // Sigma_{k+1,k+1} J
+#pragma unroll
+        for (int i = 0; i < DD; ++i) ssub[i] = -ssub[i];
+        if (WANT_SUB) st_s<T, DD>(out[WANT_SUB ? 1 : 0] + j * DD, ssub);
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int q = 0; q <= i; ++q) {
+            T v = loc[i * D + q];
+#pragma unroll
+            for (int s = 0; s < D; ++s) v = Num<T>::fma(-J[s * D + i], ssub[s * D + q], v);
+            loc[i * D + q] = v;
+          }
+        mirror_lower<T, D>(loc);
+      }
+      st_s<T, DD>(out[0] + j * DD, loc);
+#pragma unroll
+      for (int i = 0; i < DD; ++i) sig[i] = loc[i];
+    }
+  }
+  __device__ __forceinline__ void finish(const Params&, int64_t, bool) {}
+};
+
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct BtdUduParams {
+  const T *diag, *sub;
+  T *ou, *ocd;
+  int32_t* info;
+  int64_t B, Tn;
+};
+
+// cholD_{T-1} = chol(K_{T-1,T-1});  U_k^T = D_{k+1}^{-1} K_{k+1,k};  D_k = K_kk - K_{k+1,k}^T U_k^T
+template <typename T_, int D>
+struct BtdUduCore {
+  using T = T_;
+  using Params = BtdUduParams<T>;
+  static constexpr int DD = D * D;
+  static constexpr int NIN = 2, NOUT = 2;
+  static constexpr bool BACKWARD = true;
+  static constexpr int ein(int) { return DD; }
+  static constexpr int eout(int) { return DD; }
+  static __device__ __forceinline__ int64_t num_chains(const Params& p) { return p.B; }
+  static __device__ __forceinline__ int64_t max_steps(const Params& p) { return p.Tn; }
+  static __device__ __forceinline__ StreamGeom in_geom(const Params& p, int i, int64_t c) {
+    if (i == 0) return geom_states<T>(p.diag, c, p.Tn, DD);
+    return geom_outgoing<T>(p.sub, c, p.Tn, DD);
+  }
+  static __device__ __forceinline__ StreamGeom out_geom(const Params& p, int i, int64_t c) {
+    if (i == 0) return geom_outgoing<T>(p.ou, c, p.Tn, DD);
+    return geom_states<T>(p.ocd, c, p.Tn, DD);
+  }
+  T C[DD], rinv[D];
+  int32_t fail;
+  int64_t Tn_;
+  __device__ __forceinline__ void init(const Params& p, int64_t) {
+    Tn_ = p.Tn;
+    fail = 0;
+  }
+  __device__ __forceinline__ void tile(const Params&, const T* const* in, T* const* out, int64_t j0,
+                                       int ns) {
+    for (int j = ns - 1; j >= 0; --j) {
+      const int64_t k = j0 + j;
+      T Dk[DD];
+      ld_s<T, DD>(Dk, in[0] + j * DD);
+      if (k + 1 < Tn_) {
+        T K[DD], X[DD];
+        ld_s<T, DD>(K, in[1] + j * DD);
+#pragma unroll
+        for (int i = 0; i < DD; ++i) X[i] = K[i];
+        trsm_left_lower<T, D>(C, rinv, X);
+        trsm_left_lower_t<T, D>(C, rinv, X);  // X = D_{k+1}^{-1} K_{k+1,k}
+        st_s<T, DD>(out[0] + j * DD, X);
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int q = 0; q <= i; ++q) {
+            T v = Dk[i * D + q];
+#pragma unroll
+            for (int s = 0; s < D; ++s) v = Num<T>::fma(-K[s * D + i], X[s * D + q], v);
+            Dk[i * D + q] = v;
+          }
+      }
+#pragma unroll
+      for (int i = 0; i < DD; ++i) C[i] = Dk[i];
+      const bool ok = chol_lower<T, D>(C, rinv);
+      if (!ok && fail == 0) fail = (int32_t)(k + 1);
+      zero_upper<T, D>(C);
+      st_s<T, DD>(out[1] + j * DD, C);
+    }
+  }
+  __device__ __forceinline__ void finish(const Params& p, int64_t c, bool valid) {
+    if (valid && p.info) p.info[c] = fail;
+  }
+};
+
+}  // namespace mf

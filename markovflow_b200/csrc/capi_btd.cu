@@ -6,6 +6,7 @@
 #include "btd_staged.cuh"
 #include "btd_tma.cuh"
 #include "dispatch.cuh"
+#include "ssm_sweep_api.h"
 
 namespace mf {
 
@@ -180,6 +181,10 @@ int mf_btd_solve(int dtype, const void* ld, const void* ls, const void* rhs, voi
   if (T == 1) ls = nullptr;
   cudaStream_t s = (cudaStream_t)stream;
   if (D > MF_SMALL_D_MAX) return big_solve(dtype, ld, ls, rhs, out, n_rhs, Bm, T, D, transpose, s);
+  if (D <= kSsmSweepMaxD && T > 1 && tuning(4) != 1) {
+    const int rc = btd_sweep_solve(dtype, D, ld, ls, rhs, out, n_rhs, Bm, T, transpose, s);
+    if (rc != MF_ERR_UNSUPPORTED) return rc;
+  }
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
@@ -197,6 +202,10 @@ int mf_btd_inverse_subset(int dtype, const void* ld, const void* ls, void* out_d
   if (T == 1) { ls = nullptr; out_sub = nullptr; }
   if (out_sub && !ls) return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (D <= kSsmSweepMaxD && T > 1 && tuning(4) != 1) {
+    const int rc = btd_sweep_inverse_subset(dtype, D, ld, ls, out_diag, out_sub, B, T, s);
+    if (rc != MF_ERR_UNSUPPORTED) return rc;
+  }
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
@@ -213,6 +222,10 @@ int mf_btd_upper_diagonal_lower(int dtype, const void* diag, const void* sub, vo
   if (B == 0) return MF_OK;
   if (!diag || !sub || !out_u || !out_chol_d) return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (D <= kSsmSweepMaxD && tuning(4) != 1) {
+    const int rc = btd_sweep_udu(dtype, D, diag, sub, out_u, out_chol_d, info, B, T, s);
+    if (rc != MF_ERR_UNSUPPORTED) return rc;
+  }
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;

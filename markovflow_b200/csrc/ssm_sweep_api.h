@@ -24,4 +24,12 @@ int nat_sweep_to_ssm(int dtype, int64_t D, const void* th_lin, const void* th_di
                      const void* th_sub, void* out_a, void* out_off, void* out_chol, int32_t* info,
                      int64_t B, int64_t T, cudaStream_t s);
 
+// block-tridiagonal recurrences (capi_btd_sweep.cu)
+int btd_sweep_solve(int dtype, int64_t D, const void* ld, const void* ls, const void* rhs, void* out,
+                    int64_t n, int64_t Bm, int64_t T, int transpose, cudaStream_t s);
+int btd_sweep_inverse_subset(int dtype, int64_t D, const void* ld, const void* ls, void* od, void* os,
+                             int64_t B, int64_t T, cudaStream_t s);
+int btd_sweep_udu(int dtype, int64_t D, const void* diag, const void* sub, void* ou, void* ocd,
+                  int32_t* info, int64_t B, int64_t T, cudaStream_t s);
+
 }  // namespace mf

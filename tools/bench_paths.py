@@ -88,6 +88,25 @@ def ssm(b=4096, t=10_000):
     report("ssm.kl_divergence B=4096 T=1e4 D=2", b * t, (4 * 4 + 2 * 2) * 8, timeit(lambda: m.kl_divergence(m)))
 
 
+def btd(b=4096, t=10_000):
+    """solve / inverse subset / U D U^T on config-2 shapes (D = 3), sweep vs direct-load kernels."""
+    diag, sub, rhs = bench_inputs.matern52_posterior_precision(b, t, DEV)
+    m = mf.SymmetricBlockTriDiagonal(diag, sub)
+    chol = m.cholesky
+    lib = _lib.lib()
+    for knob, label in ((0, "TMA sweep"), (1, "direct loads")):
+        lib.mf_set_tuning(4, knob)
+        report(f"btd.solve fwd B={b} T={t} D=3 [{label}]", b * t, (2 * 9 + 2 * 3) * 8,
+               timeit(lambda: chol.solve(rhs)))
+        report(f"btd.solve bwd B={b} T={t} D=3 [{label}]", b * t, (2 * 9 + 2 * 3) * 8,
+               timeit(lambda: chol.solve(rhs, transpose_left=True)))
+        report(f"btd.block_diagonal_of_inverse B={b} T={t} D=3 [{label}]", b * t, (3 * 9) * 8,
+               timeit(lambda: chol.block_diagonal_of_inverse()))
+        report(f"btd.upper_diagonal_lower B={b} T={t} D=3 [{label}]", b * t, (4 * 9) * 8,
+               timeit(lambda: m.upper_diagonal_lower()))
+    lib.mf_set_tuning(4, 0)
+
+
 def config4(b=256, t=10_000):
     """Config 4 at reduced T (the full T=1e5 needs 118 GB of inputs: in-place, 8 GPUs or B-chunks)."""
     diag, sub, rhs = bench_inputs.sum_kernel_posterior_precision(b, t, DEV)
