@@ -38,6 +38,20 @@ int run(const typename Core::Params& p, int64_t nchains, cudaStream_t s) {
 
 }  // namespace
 
+// Segments per chain for the parallel-in-time evaluation of an exact (affine) recurrence: enough
+// virtual chains to occupy the GPU, segments of at least 64 steps.
+static void plan_segments(int64_t B, int64_t T, int64_t* P, int64_t* L) {
+  const int64_t target = (int64_t)148 * 192;
+  int64_t p = B >= target / 2 ? 1 : (target + B - 1) / B;
+  if (p > T / 64) p = T / 64;
+  if (p < 1) p = 1;
+  if (tuning(3) > 0 && tuning(3) < T) p = (T + tuning(3) - 1) / tuning(3);
+  int64_t l = (T + p - 1) / p;
+  if (l < 2) l = 2;
+  *L = l;
+  *P = (T + l - 1) / l;
+}
+
 int ssm_sweep_moments(int dtype, int64_t D, int expectations, const void* mu0, const void* chol_p0,
                       const void* a, const void* b, const void* chol_q, void* o_vec, void* o_diag,
                       void* o_sub, int64_t B, int64_t T, cudaStream_t s) {
@@ -45,9 +59,18 @@ int ssm_sweep_moments(int dtype, int64_t D, int expectations, const void* mu0, c
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
     SsmMomentsParams<Tp> p{(const Tp*)mu0, (const Tp*)chol_p0, (const Tp*)a, (const Tp*)b,
-                           (const Tp*)chol_q, (Tp*)o_vec, (Tp*)o_diag, (Tp*)o_sub, B, T};
-    if (expectations) return run<SsmMomentsCore<Tp, kD, true>>(p, B, s);
-    return run<SsmMomentsCore<Tp, kD, false>>(p, B, s);
+                           (const Tp*)chol_q, (Tp*)o_vec, (Tp*)o_diag, (Tp*)o_sub, B, T, 1, T};
+    if (tuning(2) != 1 && o_diag && (o_vec || !expectations)) plan_segments(B, T, &p.P, &p.L);
+    if (p.P > 1) {
+      int rc = run<SsmMomSummaryCore<Tp, kD>>(p, B * p.P, s);
+      if (rc != MF_OK) return rc;
+      if (p.P > 64) ssm_moments_seed_kernel<Tp, kD, true><<<grid_for(B * 32, 128), 128, 0, s>>>(p);
+      else ssm_moments_seed_kernel<Tp, kD, false><<<grid_for(B, 128), 128, 0, s>>>(p);
+      rc = check_launch();
+      if (rc != MF_OK) return rc;
+    }
+    if (expectations) return run<SsmMomentsCore<Tp, kD, true>>(p, B * p.P, s);
+    return run<SsmMomentsCore<Tp, kD, false>>(p, B * p.P, s);
   });
 }
 

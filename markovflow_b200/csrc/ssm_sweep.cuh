@@ -59,12 +59,47 @@ __device__ __forceinline__ void st_s(T* __restrict__ s, const T* __restrict__ r)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Few long chains are cut into P segments of L steps ("virtual chains", as in kalman_sweep.cuh) and
+// evaluated parallel in time -- the moment recursion is affine, so this is exact:
+//   1. SsmMomSummaryCore : every segment composes its transitions into one element (Phi, c, Qt):
+//                          mu_end = Phi mu + c,  Sigma_end = Phi Sigma Phi^T + Qt
+//   2. ssm_moments_seed_kernel : per chain, fold the elements in order -> state before every segment
+//   3. SsmMomentsCore    : every segment runs the ordinary recursion from its seed.
+// No workspace: elements and seeds live in the output slots of each segment's LAST step, which the
+// owning virtual chain overwrites with the final values after it has read its seed
+// (Phi | seed Sigma -> o_diag[last], c | seed mu -> o_vec[last], Qt -> o_diag[last-1]; L >= 2).
 template <typename T>
 struct SsmMomentsParams {
   const T *mu0, *chol_p0, *a, *b, *chol_q;
   T *o_vec, *o_diag, *o_sub;  // means|eta_lin [B,T,D], covs|eta_diag [B,T,D,D], lag-one [B,T-1,D,D]
   int64_t B, Tn;
+  int64_t P, L;  // segments per chain, steps per segment (P == 1: L == Tn)
 };
+
+// entry of local step j of segment (c, k0): states / transitions leading into the step
+template <typename T>
+__device__ __forceinline__ StreamGeom vgeom_states(const T* base, int64_t c, int64_t Tn, int E,
+                                                   int64_t k0, int64_t steps) {
+  StreamGeom g;
+  g.step0 = base ? byte_ptr(base) + (c * Tn + k0) * (int64_t)(E * sizeof(T)) : nullptr;
+  g.first = 0;
+  g.end = steps;
+  return g;
+}
+template <typename T>
+__device__ __forceinline__ StreamGeom vgeom_incoming(const T* base, int64_t c, int64_t Tn, int E,
+                                                     int64_t k0, int64_t steps) {
+  StreamGeom g;
+  g.step0 = base ? byte_ptr(base) + (c * (Tn - 1) + k0 - 1) * (int64_t)(E * sizeof(T)) : nullptr;
+  g.first = k0 == 0 ? 1 : 0;
+  g.end = steps;
+  return g;
+}
+__device__ __forceinline__ int64_t seg_steps(int64_t Tn, int64_t k0, int64_t L) {
+  int64_t n = Tn - k0;
+  if (n > L) n = L;
+  return n < 0 ? 0 : n;
+}
 
 // EXPECT = false: (mu_k, Sigma_kk, A_k Sigma_kk);  EXPECT = true: (mu_k, Sigma_kk + mu mu^T,
 // A_k Sigma_kk + mu_{k+1} mu_k^T).  The lag-one block k is produced at step k+1 (incoming form).
@@ -77,26 +112,43 @@ struct SsmMomentsCore {
   static constexpr bool BACKWARD = false;
   static constexpr int ein(int i) { return i == 1 ? D : DD; }
   static constexpr int eout(int i) { return i == 0 ? D : DD; }
-  static __device__ __forceinline__ int64_t num_chains(const Params& p) { return p.B; }
-  static __device__ __forceinline__ int64_t max_steps(const Params& p) { return p.Tn; }
-  static __device__ __forceinline__ StreamGeom in_geom(const Params& p, int i, int64_t c) {
-    return geom_incoming<T>(i == 0 ? p.a : (i == 1 ? p.b : p.chol_q), c, p.Tn, ein(i));
+  static __device__ __forceinline__ int64_t num_chains(const Params& p) { return p.B * p.P; }
+  static __device__ __forceinline__ int64_t max_steps(const Params& p) { return p.L; }
+  static __device__ __forceinline__ StreamGeom in_geom(const Params& p, int i, int64_t v) {
+    const int64_t c = v / p.P, k0 = (v % p.P) * p.L;
+    return vgeom_incoming<T>(i == 0 ? p.a : (i == 1 ? p.b : p.chol_q), c, p.Tn, ein(i), k0,
+                             seg_steps(p.Tn, k0, p.L));
   }
-  static __device__ __forceinline__ StreamGeom out_geom(const Params& p, int i, int64_t c) {
-    if (i == 2) return geom_incoming<T>(p.o_sub, c, p.Tn, DD);
-    return geom_states<T>(i == 0 ? p.o_vec : p.o_diag, c, p.Tn, eout(i));
+  static __device__ __forceinline__ StreamGeom out_geom(const Params& p, int i, int64_t v) {
+    const int64_t c = v / p.P, k0 = (v % p.P) * p.L;
+    const int64_t n = seg_steps(p.Tn, k0, p.L);
+    if (i == 2) return vgeom_incoming<T>(p.o_sub, c, p.Tn, DD, k0, n);
+    return vgeom_states<T>(i == 0 ? p.o_vec : p.o_diag, c, p.Tn, eout(i), k0, n);
   }
   T mu[D], P[DD];
-  __device__ __forceinline__ void init(const Params& p, int64_t c) {
-    T L[DD];
-    load_vec<T, D>(mu, p.mu0 + c * D);
-    load_vec<T, DD>(L, p.chol_p0 + c * DD);
-    llt<T, D>(P, L);
+  int64_t k0_;
+  __device__ __forceinline__ void init(const Params& p, int64_t v) {
+    const int64_t c = v / p.P;
+    k0_ = (v % p.P) * p.L;
+    if (k0_ == 0) {
+      T L[DD];
+      load_vec<T, D>(mu, p.mu0 + c * D);
+      load_vec<T, DD>(L, p.chol_p0 + c * DD);
+      llt<T, D>(P, L);
+    } else {  // seed = state at step k0 - 1, parked in this segment's last output slots
+#pragma unroll
+      for (int i = 0; i < D; ++i) mu[i] = T(0);
+      const int64_t kl = k0_ + seg_steps(p.Tn, k0_, p.L) - 1;
+      if (kl >= k0_) {
+        if (p.o_vec) load_vec<T, D>(mu, p.o_vec + (c * p.Tn + kl) * D);
+        load_vec<T, DD>(P, p.o_diag + (c * p.Tn + kl) * DD);
+      }
+    }
   }
   __device__ __forceinline__ void tile(const Params& p, const T* const* in, T* const* out,
                                        int64_t j0, int ns) {
     for (int j = 0; j < ns; ++j) {
-      if (j0 + j > 0) {
+      if (k0_ + j0 + j > 0) {
         T A[DD], off[D], L[DD], AP[DD], E[DD];
         ld_s<T, DD>(A, in[0] + j * DD);
         ld_s<T, D>(off, in[1] + j * D);
@@ -141,6 +193,208 @@ struct SsmMomentsCore {
   }
   __device__ __forceinline__ void finish(const Params&, int64_t, bool) {}
 };
+
+// pass 1: the composed transition of every segment but the last of each chain
+template <typename T_, int D>
+struct SsmMomSummaryCore {
+  using T = T_;
+  using Params = SsmMomentsParams<T>;
+  static constexpr int DD = D * D;
+  static constexpr int NIN = 3, NOUT = 0;
+  static constexpr bool BACKWARD = false;
+  static constexpr int ein(int i) { return i == 1 ? D : DD; }
+  static constexpr int eout(int) { return 1; }
+  static __device__ __forceinline__ int64_t num_chains(const Params& p) { return p.B * p.P; }
+  static __device__ __forceinline__ int64_t max_steps(const Params& p) { return p.L; }
+  static __device__ __forceinline__ StreamGeom in_geom(const Params& p, int i, int64_t v) {
+    const int64_t c = v / p.P, seg = v % p.P, k0 = seg * p.L;
+    // the last segment has no successor: nothing to summarise
+    const int64_t n = seg + 1 < p.P ? seg_steps(p.Tn, k0, p.L) : 0;
+    return vgeom_incoming<T>(i == 0 ? p.a : (i == 1 ? p.b : p.chol_q), c, p.Tn, ein(i), k0, n);
+  }
+  static __device__ __forceinline__ StreamGeom out_geom(const Params&, int, int64_t) {
+    return StreamGeom{nullptr, 0, 0};
+  }
+  T Phi[DD], cv[D], Qt[DD];
+  int64_t k0_;
+  bool live_;
+  __device__ __forceinline__ void init(const Params& p, int64_t v) {
+    k0_ = (v % p.P) * p.L;
+    live_ = (v % p.P) + 1 < p.P;
+#pragma unroll
+    for (int i = 0; i < DD; ++i) {
+      Phi[i] = (i / D == i % D) ? T(1) : T(0);
+      Qt[i] = T(0);
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) cv[i] = T(0);
+  }
+  __device__ __forceinline__ void tile(const Params&, const T* const* in, T* const*, int64_t j0, int ns) {
+    if (!live_) return;
+    for (int j = 0; j < ns; ++j) {
+      if (k0_ + j0 + j == 0) continue;
+      T A[DD], off[D], L[DD], AP[DD];
+      ld_s<T, DD>(A, in[0] + j * DD);
+      ld_s<T, D>(off, in[1] + j * D);
+      ld_s<T, DD>(L, in[2] + j * DD);
+      gemv_add<T, D>(off, A, cv);
+#pragma unroll
+      for (int r = 0; r < D; ++r) cv[r] = off[r];
+      gemm<T, D>(AP, A, Phi);
+#pragma unroll
+      for (int i = 0; i < DD; ++i) Phi[i] = AP[i];
+      gemm<T, D>(AP, A, Qt);
+      llt<T, D>(Qt, L);
+#pragma unroll
+      for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int q = 0; q <= r; ++q) {
+          T v = Qt[r * D + q];
+#pragma unroll
+          for (int s = 0; s < D; ++s) v = Num<T>::fma(AP[r * D + s], A[q * D + s], v);
+          Qt[r * D + q] = v;
+          Qt[q * D + r] = v;
+        }
+    }
+  }
+  __device__ __forceinline__ void finish(const Params& p, int64_t v, bool valid) {
+    if (!valid || !live_) return;
+    const int64_t c = v / p.P;
+    const int64_t kl = k0_ + p.L - 1;  // a live segment is complete: L steps
+    store_vec<T, DD>(p.o_diag + (c * p.Tn + kl) * DD, Phi);
+    store_vec<T, DD>(p.o_diag + (c * p.Tn + kl - 1) * DD, Qt);
+    if (p.o_vec) store_vec<T, D>(p.o_vec + (c * p.Tn + kl) * D, cv);
+  }
+};
+
+// ---- pass 2: state before every segment -------------------------------------------------------
+// element of a range of steps: mu_end = Phi mu + c,  Sigma_end = Phi Sigma Phi^T + Qt
+template <typename T, int D>
+struct MomElem {
+  T Phi[D * D], c[D], Qt[D * D];
+  __device__ __forceinline__ void identity() {
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) {
+      Phi[i] = (i / D == i % D) ? T(1) : T(0);
+      Qt[i] = T(0);
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) c[i] = T(0);
+  }
+  // Sigma <- M Sigma M^T + Q (symmetric result)
+  static __device__ __forceinline__ void congruence(T* __restrict__ sig, const T* __restrict__ M,
+                                                    const T* __restrict__ Q) {
+    T MS[D * D];
+    gemm<T, D>(MS, M, sig);
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+      for (int q = 0; q <= r; ++q) {
+        T v = Q[r * D + q];
+#pragma unroll
+        for (int s = 0; s < D; ++s) v = Num<T>::fma(MS[r * D + s], M[q * D + s], v);
+        sig[r * D + q] = v;
+        sig[q * D + r] = v;
+      }
+  }
+  // this <- later o this  (apply `this` first, then `later`)
+  __device__ __forceinline__ void then(const MomElem& later) {
+    T t[D * D], v[D];
+    gemm<T, D>(t, later.Phi, Phi);
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) Phi[i] = t[i];
+#pragma unroll
+    for (int i = 0; i < D; ++i) v[i] = later.c[i];
+    gemv_add<T, D>(v, later.Phi, c);
+#pragma unroll
+    for (int i = 0; i < D; ++i) c[i] = v[i];
+    congruence(Qt, later.Phi, later.Qt);
+  }
+  __device__ __forceinline__ void apply(T* __restrict__ mu, T* __restrict__ sig) const {
+    T v[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) v[i] = c[i];
+    gemv_add<T, D>(v, Phi, mu);
+#pragma unroll
+    for (int i = 0; i < D; ++i) mu[i] = v[i];
+    congruence(sig, Phi, Qt);
+  }
+  __device__ __forceinline__ void load(const SsmMomentsParams<T>& p, int64_t c_, int64_t kl) {
+    load_vec<T, D * D>(Phi, p.o_diag + (c_ * p.Tn + kl) * D * D);
+    load_vec<T, D * D>(Qt, p.o_diag + (c_ * p.Tn + kl - 1) * D * D);
+    if (p.o_vec) load_vec<T, D>(c, p.o_vec + (c_ * p.Tn + kl) * D);
+    else {
+#pragma unroll
+      for (int i = 0; i < D; ++i) c[i] = T(0);
+    }
+  }
+  __device__ __forceinline__ void shfl_up_from(const MomElem& src, int delta) {
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) {
+      Phi[i] = __shfl_up_sync(0xffffffffu, src.Phi[i], delta);
+      Qt[i] = __shfl_up_sync(0xffffffffu, src.Qt[i], delta);
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) c[i] = __shfl_up_sync(0xffffffffu, src.c[i], delta);
+  }
+};
+
+// One WARP per chain: lane l owns segments [l*m, (l+1)*m); it composes their elements, the warp
+// scans the 32 composites, and every lane then walks its segments from its prefix state, parking
+// the state before every segment s >= 1 in that segment's last output slots (which held the
+// segment's own element: loaded before it is overwritten).  One thread per chain when P is small.
+template <typename T, int D, bool WARP>
+__global__ void __launch_bounds__(128)
+ssm_moments_seed_kernel(const SsmMomentsParams<T> p) {
+  constexpr int DD = D * D;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t c = WARP ? tid / 32 : tid;
+  const int lane = WARP ? (int)(tid & 31) : 0;
+  if (c >= p.B) return;
+  const int64_t nlive = p.P - 1;  // segments that have a successor
+  const int64_t m = WARP ? (nlive + 31) / 32 : p.P;
+  const int64_t s0 = lane * m;
+  int64_t s1 = s0 + m;
+  if (s1 > p.P) s1 = p.P;
+  T mu[D], sig[DD], L[DD];
+  load_vec<T, D>(mu, p.mu0 + c * D);
+  load_vec<T, DD>(L, p.chol_p0 + c * DD);
+  llt<T, D>(sig, L);
+  if (WARP) {
+    MomElem<T, D> mine, e, other;
+    mine.identity();
+    for (int64_t seg = s0; seg < s1 && seg < nlive; ++seg) {
+      e.load(p, c, seg * p.L + p.L - 1);
+      mine.then(e);
+    }
+#pragma unroll 1
+    for (int delta = 1; delta < 32; delta <<= 1) {
+      other.shfl_up_from(mine, delta);
+      if (lane >= delta) {
+        other.then(mine);
+        mine = other;
+      }
+    }
+    // exclusive prefix: the inclusive composite of the previous lane
+    other.shfl_up_from(mine, 1);
+    if (lane > 0) other.apply(mu, sig);
+    if (lane == 31) s1 = p.P;  // the last lane also parks the seed of the final segment
+  }
+  for (int64_t seg = s0; seg < s1; ++seg) {
+    const int64_t k0 = seg * p.L;
+    const int64_t n = seg_steps(p.Tn, k0, p.L);
+    if (n <= 0) break;
+    const int64_t kl = k0 + n - 1;
+    MomElem<T, D> e;
+    const bool live = seg < nlive;
+    if (live) e.load(p, c, kl);
+    if (seg > 0) {
+      if (p.o_vec) store_vec<T, D>(p.o_vec + (c * p.Tn + kl) * D, mu);
+      store_vec<T, DD>(p.o_diag + (c * p.Tn + kl) * DD, sig);
+    }
+    if (live) e.apply(mu, sig);
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 template <typename T>

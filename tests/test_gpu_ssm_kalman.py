@@ -364,3 +364,81 @@ def test_segment_element_matches_oracle_element():
         want = np.concatenate([np.reshape(x, -1) for x in want])
         assert max_rel_err(got, want) < 1e-9
         lo += n
+
+
+# ------------------------------------------------------------------------------------------------
+# few long chains: the moment recursion is evaluated parallel in time (segment elements -> seeds ->
+# seeded sweeps, ssm_sweep.cuh); results must equal the sequential sweep and the direct propagation
+# ------------------------------------------------------------------------------------------------
+
+def _propagate_moments(mu0, chol_p0, a_s, b_s, chol_q):
+    """Direct numpy propagation of (mu_k, Sigma_kk, A_k Sigma_kk) for batched arrays."""
+    t = a_s.shape[-3] + 1
+    mu = [mu0]
+    p = [chol_p0 @ np.swapaxes(chol_p0, -1, -2)]
+    sub = []
+    for k in range(t - 1):
+        a = a_s[..., k, :, :]
+        sub.append(a @ p[-1])
+        mu.append(np.einsum("...ij,...j->...i", a, mu[-1]) + b_s[..., k, :])
+        lq = chol_q[..., k, :, :]
+        p.append(a @ p[-1] @ np.swapaxes(a, -1, -2) + lq @ np.swapaxes(lq, -1, -2))
+    return np.stack(mu, -2), np.stack(p, -3), np.stack(sub, -3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("d", [1, 2, 3, 4])
+@pytest.mark.parametrize("b,t", [(1, 1000), (3, 301), (2, 129), (5, 640)])
+def test_marginals_parallel_in_time(b, t, d, dtype):
+    import markovflow_b200 as mf
+    from markovflow_b200 import _lib
+
+    rng = np.random.RandomState(b * 1000 + t + d)
+    state = np.random.get_state()
+    np.random.seed(rng.randint(1 << 30))
+    arrays = random_ssm_arrays((b,), t - 1, d, scale_a=0.6 / np.sqrt(d))
+    np.random.set_state(state)
+    ssm = make_ssm(arrays, dtype)
+    want_mu, want_p, want_sub = _propagate_moments(*arrays)
+    tol = TOL[dtype]
+    lib = _lib.lib()
+    results = {}
+    for knob in (0, 1):  # 0: parallel in time when it pays, 1: sequential sweep
+        lib.mf_set_tuning(2, knob)
+        try:
+            mean, cov = ssm.marginals
+            cov2, sub = ssm.covariance_blocks()
+            eta = mf.ssm_to_expectations(ssm)
+        finally:
+            lib.mf_set_tuning(2, 0)
+        results[knob] = (npy(mean), npy(cov), npy(sub), [npy(e) for e in eta])
+        assert max_rel_err(npy(mean), want_mu) < tol
+        assert max_rel_err(npy(cov), want_p) < tol
+        assert max_rel_err(npy(cov2), want_p) < tol
+        assert max_rel_err(npy(sub), want_sub) < tol
+        assert max_rel_err(npy(eta[0]), want_mu) < tol
+        assert max_rel_err(npy(eta[1]), want_p + want_mu[..., :, None] * want_mu[..., None, :]) < tol
+        assert max_rel_err(npy(eta[2]), want_sub + want_mu[..., 1:, :, None] * want_mu[..., :-1, None, :]) < tol
+    for x, y in zip(results[0][:3], results[1][:3]):
+        assert max_rel_err(x, y) < tol
+
+
+def test_marginals_parallel_in_time_segment_length_knob():
+    """Forced short segments (knob 3) with a ragged last segment of one step."""
+    from markovflow_b200 import _lib
+
+    lib = _lib.lib()
+    # more than 64 segments per chain: the seeds come from the warp-scan kernel
+    for t, d, segs in ((101, 2, (2, 3, 10, 50, 100)), (1001, 3, (4, 7, 13)), (2500, 1, (2, 39))):
+        arrays = random_ssm_arrays((2,), t - 1, d)
+        want_mu, want_p, want_sub = _propagate_moments(*arrays)
+        for seg in segs:
+            lib.mf_set_tuning(3, seg)
+            try:
+                ssm = make_ssm(arrays)
+                mean, cov = ssm.marginals
+                _, sub = ssm.covariance_blocks()
+            finally:
+                lib.mf_set_tuning(3, 0)
+            assert max_rel_err(npy(mean), want_mu) < 1e-10 and max_rel_err(npy(cov), want_p) < 1e-10
+            assert max_rel_err(npy(sub), want_sub) < 1e-10
