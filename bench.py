@@ -26,6 +26,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+_JSON_OUT = sys.stdout
 
 B_PER_GPU, T, D = 4096, 10000, 3
 ALGO_BYTES_PER_STEP = (4 * D * D + 2 * D) * 8  # read diag+sub+rhs, write Ld+Ls+x  
@@ -106,13 +107,14 @@ def cpu_reference_run(steps: int, warmup: int, sample_chains: int):
     diag = np.tile(np.stack(diags), (reps, 1, 1, 1))[:sample_chains]
     sub = np.tile(np.stack(subs), (reps, 1, 1, 1))[:sample_chains]
     rhs = rng.standard_normal((sample_chains, T, D))
-    cores = c_ref.max_threads()
+    # all host cores, whatever OMP_NUM_THREADS says (torchrun sets it to 1)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     for _ in range(max(1, warmup)):
-        c_ref.chol_solve_batch(diag, sub, rhs)
+        c_ref.chol_solve_batch(diag, sub, rhs, nthreads=cores)
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        _, _, _, info = c_ref.chol_solve_batch(diag, sub, rhs)
+        _, _, _, info = c_ref.chol_solve_batch(diag, sub, rhs, nthreads=cores)
         times.append(time.perf_counter() - t0)
     assert int(info.max()) == 0
     sec = sum(times) / len(times)
@@ -136,7 +138,7 @@ def run_reference(args):
                                    "Cholesky, band->block, re-band, banded solve), OpenMP over chains"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 def _timed(fn, warm=3, reps=10):
@@ -408,7 +410,7 @@ def run_gpu(args):
                      "algorithmic_bytes_per_state_step": ALGO_BYTES_PER_STEP},
         "cpu_baseline": cpu, "clocks": clocks.summary(), "extra": extras,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -424,6 +426,12 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the config 3/4/5 measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE JSON line: everything else that libraries write to file descriptor 1
+    # (e.g. NCCL's version banner) is sent to stderr; the JSON line goes to the saved descriptor.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

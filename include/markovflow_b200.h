@@ -48,7 +48,10 @@ const char* mf_last_cuda_error(void);
 /* Development/tuning knobs (kernel variant selection); knob 0: Cholesky sweep variant
  * (0 auto = TMA bulk-copy ring, 1 direct global-memory streaming, 2 cp.async element-staged ring),
  * knob 1: steps per stage of variant 2; knob 2: Kalman log-likelihood path (0 auto, 1 one thread
- * per chain, 2 parallel-in-time); knob 3: steps per parallel-in-time segment (0 auto). */
+ * per chain, 2 parallel-in-time; also: 1 = no parallel-in-time evaluation of the moment recursions);
+ * knob 3: steps per parallel-in-time segment (0 auto); knob 4: 1 = direct-load kernels instead of
+ * the TMA chain sweeps; knob 7: large-block Cholesky (0/1 one warp per chain, 2 experimental
+ * one-CTA-per-chain kernel). */
 int mf_set_tuning(int knob, int value);
 
 /* ---------------------------------------------------------------------------------------------

@@ -130,3 +130,48 @@ def test_config4_sum_kernel_d17_posterior_precision():
     assert max_rel_err(np.tril(rec_d), np.tril(diag)) < 1e-12
     assert max_rel_err(gs @ np.swapaxes(gd[:, :-1], -1, -2), sub) < 1e-12
     assert max_rel_err(O.btd_dense_mult(gd, gs, npy(x)), rhs) < 1e-8
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("t,offset", [(2, 0), (5, 1), (8, 0), (33, 1), (100, 0)])
+def test_team_kernel_variant_matches_oracle(t, offset, dtype):
+    """The experimental one-CTA-per-chain kernel (tuning knob 7 = 2; fraction-free elimination in
+    role-specialised warps, btd_team.cuh) must produce the same factor, solve, log-det and failure
+    report as the oracle, for aligned and misaligned (offset) arrays, out of place and in place."""
+    from markovflow_b200 import _lib
+    from markovflow_b200._lib import check, current_stream, i64, ptr
+
+    d, b = 17, 4
+    diag, sub, _, _ = random_well_conditioned_spd_btd((b,), t, d, rng=t)
+    rhs = np.random.default_rng(t).standard_normal((b, t, d))
+    o_ld, o_ls = O.btd_cholesky(diag, sub)
+    o_x = O.btd_solve(o_ld, o_ls, rhs)
+
+    def shifted(x):
+        flat = torch.empty(x.size + offset, dtype=dtype, device=dev())
+        v = flat[offset:].view(x.shape)
+        v.copy_(torch.as_tensor(x).to(dtype))
+        return v
+
+    lib = _lib.lib()
+    for inplace in (False, True):
+        gd, gs, gr = shifted(diag), shifted(sub), shifted(rhs)
+        od, os_, ox = (gd, gs, gr) if inplace else (torch.full_like(gd, float("nan")),
+                                                    torch.full_like(gs, float("nan")),
+                                                    torch.full_like(gr, float("nan")))
+        logdet = torch.empty(b, dtype=dtype, device=dev())
+        info = torch.empty(b, dtype=torch.int32, device=dev())
+        lib.mf_set_tuning(7, 2)
+        try:
+            check(lib.mf_btd_cholesky(_lib.MF_F64 if dtype == torch.float64 else _lib.MF_F32, ptr(gd), ptr(gs),
+                                      ptr(gr), ptr(od), ptr(os_), ptr(ox), ptr(logdet), ptr(info), i64(b),
+                                      i64(t), i64(d), current_stream()), "mf_btd_cholesky")
+            torch.cuda.synchronize()
+        finally:
+            lib.mf_set_tuning(7, 0)
+        tol = TOL[dtype]
+        assert int(info.abs().max()) == 0
+        assert max_rel_err(npy(od), o_ld) < tol and max_rel_err(npy(os_), o_ls) < tol
+        assert max_rel_err(npy(ox), o_x) < tol
+        assert max_rel_err(npy(logdet), O.btd_abs_log_det(o_ld)) < tol
+        assert np.all(np.triu(npy(od), 1) == 0.0)
