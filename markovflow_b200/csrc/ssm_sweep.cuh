@@ -577,50 +577,80 @@ struct NatToSsmCore {
 #pragma unroll
     for (int i = 0; i < D; ++i) z[i] = T(0);
   }
+  // Outputs of a step that are NOT on the recursion's dependent path (offsets, chol of the inverse):
+  // they only need the step's own factor S, so they are evaluated one iteration late, in the same
+  // basic block as the next step's dependent chain -- the two interleave instead of queueing up
+  // behind each other in the in-order pipeline.
+  __device__ __forceinline__ void emit(T* const* out, int j) {
+    T off[D], Qc[DD], r2[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) off[i] = z[i];
+    trsv_lower<T, D>(S, rinv, off);
+    trsv_lower_t<T, D>(S, rinv, off);
+    st_s<T, D>(out[1] + j * D, off);
+    chol_inverse<T, D>(Qc, S, rinv);
+    chol_lower<T, D>(Qc, r2);
+    zero_upper<T, D>(Qc);
+    st_s<T, DD>(out[2] + j * DD, Qc);
+  }
+  // dependent chain of step k: D_k, its factor and z_k from the factor of step k+1
+  __device__ __forceinline__ void advance(const T* const* in, T* const* out, int j, int64_t k) {
+    T Dk[DD], th[D], S2[DD], rinv2[D];
+    ld_s<T, D>(th, in[0] + j * D);
+    ld_s<T, DD>(Dk, in[1] + j * DD);
+#pragma unroll
+    for (int i = 0; i < DD; ++i) Dk[i] = T(-2) * Dk[i];
+    if (k + 1 < Tn_) {
+      T A[DD], Th[DD];
+      ld_s<T, DD>(A, in[2] + j * DD);
+#pragma unroll
+      for (int i = 0; i < DD; ++i) Th[i] = A[i];
+      trsm_left_lower<T, D>(S, rinv, A);
+      trsm_left_lower_t<T, D>(S, rinv, A);  // A_k = D_{k+1}^{-1} theta_sub_k
+      st_s<T, DD>(out[0] + j * DD, A);
+#pragma unroll
+      for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int q = 0; q <= r; ++q) {
+          T v = Dk[r * D + q];
+#pragma unroll
+          for (int s = 0; s < D; ++s) v = Num<T>::fma(-Th[s * D + r], A[s * D + q], v);
+          Dk[r * D + q] = v;
+        }
+      gemv_t_add<T, D>(th, A, z);
+    }
+#pragma unroll
+    for (int i = 0; i < DD; ++i) S2[i] = Dk[i];
+    const bool ok = chol_lower<T, D>(S2, rinv2);
+    if (!ok && fail == 0) fail = (int32_t)(k + 1);
+    // commit the new state only now: emit() of the previous step still reads the old one
+#pragma unroll
+    for (int i = 0; i < D; ++i) z2_[i] = th[i];
+#pragma unroll
+    for (int i = 0; i < DD; ++i) S2_[i] = S2[i];
+#pragma unroll
+    for (int i = 0; i < D; ++i) r2_[i] = rinv2[i];
+  }
+  T S2_[DD], r2_[D], z2_[D];
+  __device__ __forceinline__ void commit() {
+#pragma unroll
+    for (int i = 0; i < DD; ++i) S[i] = S2_[i];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      rinv[i] = r2_[i];
+      z[i] = z2_[i];
+    }
+  }
   __device__ __forceinline__ void tile(const Params&, const T* const* in, T* const* out, int64_t j0,
                                        int ns) {
-    for (int j = ns - 1; j >= 0; --j) {
-      const int64_t k = j0 + j;
-      T Dk[DD], th[D], off[D], Qc[DD], r2[D];
-      ld_s<T, D>(th, in[0] + j * D);
-      ld_s<T, DD>(Dk, in[1] + j * DD);
-#pragma unroll
-      for (int i = 0; i < DD; ++i) Dk[i] = T(-2) * Dk[i];
-      if (k + 1 < Tn_) {
-        T A[DD], Th[DD];
-        ld_s<T, DD>(A, in[2] + j * DD);
-#pragma unroll
-        for (int i = 0; i < DD; ++i) Th[i] = A[i];
-        trsm_left_lower<T, D>(S, rinv, A);
-        trsm_left_lower_t<T, D>(S, rinv, A);  // A_k = D_{k+1}^{-1} theta_sub_k
-        st_s<T, DD>(out[0] + j * DD, A);
-#pragma unroll
-        for (int r = 0; r < D; ++r)
-#pragma unroll
-          for (int q = 0; q <= r; ++q) {
-            T v = Dk[r * D + q];
-#pragma unroll
-            for (int s = 0; s < D; ++s) v = Num<T>::fma(-Th[s * D + r], A[s * D + q], v);
-            Dk[r * D + q] = v;
-          }
-        gemv_t_add<T, D>(th, A, z);
-      }
-#pragma unroll
-      for (int i = 0; i < D; ++i) z[i] = th[i];
-#pragma unroll
-      for (int i = 0; i < DD; ++i) S[i] = Dk[i];
-      const bool ok = chol_lower<T, D>(S, rinv);
-      if (!ok && fail == 0) fail = (int32_t)(k + 1);
-#pragma unroll
-      for (int i = 0; i < D; ++i) off[i] = z[i];
-      trsv_lower<T, D>(S, rinv, off);
-      trsv_lower_t<T, D>(S, rinv, off);
-      st_s<T, D>(out[1] + j * D, off);
-      chol_inverse<T, D>(Qc, S, rinv);
-      chol_lower<T, D>(Qc, r2);
-      zero_upper<T, D>(Qc);
-      st_s<T, DD>(out[2] + j * DD, Qc);
+    advance(in, out, ns - 1, j0 + ns - 1);
+    commit();
+    for (int j = ns - 2; j >= 0; --j) {
+      advance(in, out, j, j0 + j);  // reads the state of step j+1 ...
+      emit(out, j + 1);             // ... and so does this: independent, interleaved by ptxas
+      commit();
     }
+    emit(out, 0);  // the tile's output stage is handed over when tile() returns
   }
   __device__ __forceinline__ void finish(const Params& p, int64_t c, bool valid) {
     if (valid && p.info) p.info[c] = fail;
@@ -638,12 +668,12 @@ struct SweepAuto {
   static cudaError_t launch(const typename Core::Params& prm, int64_t nchains, cudaStream_t s) {
     if constexpr (choice == 0) {
       // few chains: one compute warp per CTA so that more SMs get a CTA
-      if (nchains <= (int64_t)148 * 48) return launch_chain_sweep<Core, 32, 8, 2, 2>(prm, nchains, s);
-      return launch_chain_sweep<Core, 64, 8, 2, 2>(prm, nchains, s);
+      if (nchains <= (int64_t)148 * 48) return launch_chain_sweep<Core, 32, 8, 2, 2>(prm, nchains, s, true);
+      return launch_chain_sweep<Core, 64, 8, 2, 2>(prm, nchains, s, true);
     } else if constexpr (choice == 1) {
-      return launch_chain_sweep<Core, 32, 8, 2, 2>(prm, nchains, s);
+      return launch_chain_sweep<Core, 32, 8, 2, 2>(prm, nchains, s, true);
     } else if constexpr (choice == 2) {
-      return launch_chain_sweep<Core, 32, 4, 2, 2>(prm, nchains, s);
+      return launch_chain_sweep<Core, 32, 4, 2, 2>(prm, nchains, s, true);
     } else {
       return cudaErrorInvalidConfiguration;
     }

@@ -120,7 +120,7 @@ __device__ __forceinline__ uint32_t sweep_ranges(const SweepSeg& sg, int E, int6
 
 template <class Core, int C, int K, int NSI, int NSO>
 __global__ void __launch_bounds__(SweepCfg<Core, C, K, NSI, NSO>::THREADS)
-chain_sweep_kernel(const typename Core::Params prm) {
+chain_sweep_kernel(const typename Core::Params prm, const int cpb) {
   using Cfg = SweepCfg<Core, C, K, NSI, NSO>;
   using T = typename Core::T;
   constexpr int ES = Cfg::ES, NIN = Cfg::NIN, NOUT = Cfg::NOUT, NSOE = Cfg::NSO_EFF;
@@ -136,7 +136,8 @@ chain_sweep_kernel(const typename Core::Params prm) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t nchains = Core::num_chains(prm);
-  const int64_t chain0 = (int64_t)blockIdx.x * C;
+  // cpb <= C chains per CTA: few chains are spread over all SMs (fewer bulk copies per CTA and tile)
+  const int64_t chain0 = (int64_t)blockIdx.x * cpb;
   const int64_t nsteps = Core::max_steps(prm);
   const int64_t ntiles = (nsteps + K - 1) / K;
 
@@ -167,7 +168,7 @@ chain_sweep_kernel(const typename Core::Params prm) {
 #pragma unroll
       for (int q = 0; q < NIN; ++q)
         if (q == stream) roff = Cfg::off_in(q) + c * Cfg::rs_in(q);
-      const bool valid = ch < nchains;
+      const bool valid = c < cpb && ch < nchains;
       const SweepSeg sg = make_seg(valid ? Core::in_geom(prm, stream, ch) : StreamGeom{nullptr, 0, 0}, valid);
       auto issue_load = [&](int64_t t) {
         const int si = (int)(t % NSI);
@@ -200,7 +201,7 @@ chain_sweep_kernel(const typename Core::Params prm) {
 #pragma unroll
       for (int q = 0; q < NOUT; ++q)
         if (q == stream) roff = Cfg::off_out(q) + c * Cfg::rs_out(q);
-      const bool valid = ch < nchains;
+      const bool valid = c < cpb && ch < nchains;
       const SweepSeg sg = make_seg(valid ? Core::out_geom(prm, stream, ch) : StreamGeom{nullptr, 0, 0}, valid);
       for (int64_t t = 0; t < ntiles; ++t) {
         const int so = (int)(t % NSO);
@@ -231,7 +232,7 @@ chain_sweep_kernel(const typename Core::Params prm) {
   // --------------------------------- compute threads ------------------------------------------
   const int c = warp * 32 + lane;
   const int64_t chain = chain0 + c;
-  const bool valid = chain < nchains;
+  const bool valid = c < cpb && chain < nchains;
   int in_off[NIN > 0 ? NIN : 1], out_off[NOUT > 0 ? NOUT : 1];
 #pragma unroll
   for (int i = 0; i < NIN; ++i) {
@@ -279,7 +280,7 @@ chain_sweep_kernel(const typename Core::Params prm) {
 // Host-side launcher: configures dynamic shared memory once per instantiation.
 template <class Core, int C, int K, int NSI, int NSO>
 inline cudaError_t launch_chain_sweep(const typename Core::Params& prm, int64_t nchains,
-                                      cudaStream_t s) {
+                                      cudaStream_t s, bool spread = false) {
   using Cfg = SweepCfg<Core, C, K, NSI, NSO>;
   auto kern = chain_sweep_kernel<Core, C, K, NSI, NSO>;
   static bool configured = false;
@@ -289,8 +290,14 @@ inline cudaError_t launch_chain_sweep(const typename Core::Params& prm, int64_t 
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const unsigned grid = (unsigned)((nchains + C - 1) / C);
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(prm);
+  // few chains: spread them over all 148 SMs (a CTA then serves fewer than C chains)
+  int64_t cpb = C;
+  if (spread && nchains < (int64_t)148 * C) {
+    cpb = (nchains + 147) / 148;
+    if (cpb < 1) cpb = 1;
+  }
+  const unsigned grid = (unsigned)((nchains + cpb - 1) / cpb);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(prm, (int)cpb);
   return cudaGetLastError();
 }
 
