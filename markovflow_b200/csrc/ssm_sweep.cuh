@@ -540,42 +540,92 @@ struct SsmKlCore {
 };
 
 // ---------------------------------------------------------------------------------------------
+// naturals -> SSM parameters: backward U D U^T sweep (nat_to_ssm_kernel in nat_kernels.cuh has the
+// algebra)
+//     D_k = Th_k - Ths_k^T D_{k+1}^{-1} Ths_k,   z_k = th_k + Ths_k^T D_{k+1}^{-1} z_{k+1}
+// (Th = -2 theta_diag, Ths = theta_sub).  The map (D_{k+1}, z_{k+1}) -> (D_k, z_k) is linear-
+// fractional and closed under composition in the form
+//     D_out = P - Q (D_in + R)^{-1} Q^T,      z_out = p + Q (D_in + R)^{-1} (z_in + r),
+// with the extension by one step  P' = Th - Ths^T P^{-1} Ths  (the recursion itself, started without
+// an incoming block),  Q' = Ths^T P^{-1} Q,  R' = R - Q^T P^{-1} Q,  p' = th + Ths^T P^{-1} p,
+// r' = r + Q^T P^{-1} p.  Few long chains are therefore evaluated parallel in time, exactly:
+//   1. NatSummaryCore : every segment (but the first) reduces its steps to one element (P,Q,R,p,r)
+//   2. nat_seed_kernel: per chain, fold the elements from the last segment down -> (D, z) entering
+//                       every segment
+//   3. NatToSsmCore   : every segment runs the ordinary sweep from its seed.
+// No workspace: elements and seeds are parked in the output slots of each segment's FIRST two steps
+// (the last ones a backward sweep writes):  P | seed D -> out_chol[k0], R -> out_chol[k0+1],
+// Q -> out_a[k0], p | seed z -> out_off[k0], r -> out_off[k0+1];  L >= 2.
 template <typename T>
 struct NatToSsmParams {
   const T *th_lin, *th_diag, *th_sub;
   T *out_a, *out_off, *out_chol;
   int32_t* info;
   int64_t B, Tn;
+  int64_t P, L;  // segments per chain, steps per segment (P == 1: L == Tn)
 };
 
-// Backward U D U^T sweep (see nat_to_ssm_kernel in nat_kernels.cuh for the algebra).
+// transition LEAVING local step j of segment (c, k0): entry k0 + j of a [B,T-1,...] stream
+template <typename T>
+__device__ __forceinline__ StreamGeom vgeom_outgoing(const T* base, int64_t c, int64_t Tn, int E,
+                                                     int64_t k0, int64_t steps) {
+  StreamGeom g;
+  g.step0 = base ? byte_ptr(base) + (c * (Tn - 1) + k0) * (int64_t)(E * sizeof(T)) : nullptr;
+  g.first = 0;
+  int64_t n = Tn - 1 - k0;
+  g.end = n < steps ? (n < 0 ? 0 : n) : steps;
+  return g;
+}
+
 template <typename T_, int D>
-struct NatToSsmCore {
+struct NatGeomBase {
+  using T = T_;
+  using Params = NatToSsmParams<T>;
+  static constexpr int DD = D * D;
+  static constexpr bool BACKWARD = true;
+  static __device__ __forceinline__ int64_t num_chains(const Params& p) { return p.B * p.P; }
+  static __device__ __forceinline__ int64_t max_steps(const Params& p) { return p.L; }
+  static constexpr int ein(int i) { return i == 0 ? D : DD; }
+  static __device__ __forceinline__ StreamGeom in_geom(const Params& p, int i, int64_t v) {
+    const int64_t c = v / p.P, k0 = (v % p.P) * p.L;
+    const int64_t n = seg_steps(p.Tn, k0, p.L);
+    if (i == 2) return vgeom_outgoing<T>(p.th_sub, c, p.Tn, DD, k0, n);
+    return vgeom_states<T>(i == 0 ? p.th_lin : p.th_diag, c, p.Tn, ein(i), k0, n);
+  }
+};
+
+// Backward U D U^T sweep of one segment, seeded with the state entering it.
+template <typename T_, int D>
+struct NatToSsmCore : NatGeomBase<T_, D> {
   using T = T_;
   using Params = NatToSsmParams<T>;
   static constexpr int DD = D * D;
   static constexpr int NIN = 3, NOUT = 3;
-  static constexpr bool BACKWARD = true;
-  static constexpr int ein(int i) { return i == 0 ? D : DD; }
   static constexpr int eout(int i) { return i == 1 ? D : DD; }
-  static __device__ __forceinline__ int64_t num_chains(const Params& p) { return p.B; }
-  static __device__ __forceinline__ int64_t max_steps(const Params& p) { return p.Tn; }
-  static __device__ __forceinline__ StreamGeom in_geom(const Params& p, int i, int64_t c) {
-    if (i == 2) return geom_outgoing<T>(p.th_sub, c, p.Tn, DD);
-    return geom_states<T>(i == 0 ? p.th_lin : p.th_diag, c, p.Tn, ein(i));
-  }
-  static __device__ __forceinline__ StreamGeom out_geom(const Params& p, int i, int64_t c) {
-    if (i == 0) return geom_outgoing<T>(p.out_a, c, p.Tn, DD);
-    return geom_states<T>(i == 1 ? p.out_off : p.out_chol, c, p.Tn, eout(i));
+  static __device__ __forceinline__ StreamGeom out_geom(const Params& p, int i, int64_t v) {
+    const int64_t c = v / p.P, k0 = (v % p.P) * p.L;
+    const int64_t n = seg_steps(p.Tn, k0, p.L);
+    if (i == 0) return vgeom_outgoing<T>(p.out_a, c, p.Tn, DD, k0, n);
+    return vgeom_states<T>(i == 1 ? p.out_off : p.out_chol, c, p.Tn, eout(i), k0, n);
   }
   T S[DD], rinv[D], z[D];
+  T S2_[DD], r2_[D], z2_[D];
   int32_t fail;
-  int64_t Tn_;
-  __device__ __forceinline__ void init(const Params& p, int64_t) {
+  int64_t Tn_, k0_, n_;
+  __device__ __forceinline__ void init(const Params& p, int64_t v) {
     fail = 0;
     Tn_ = p.Tn;
+    const int64_t c = v / p.P;
+    k0_ = (v % p.P) * p.L;
+    n_ = seg_steps(p.Tn, k0_, p.L);
 #pragma unroll
     for (int i = 0; i < D; ++i) z[i] = T(0);
+    if (n_ > 0 && k0_ + n_ < p.Tn) {  // not the last segment: factor the seed D entering it
+      load_vec<T, DD>(S, p.out_chol + (c * p.Tn + k0_) * DD);
+      load_vec<T, D>(z, p.out_off + (c * p.Tn + k0_) * D);
+      const bool ok = chol_lower<T, D>(S, rinv);
+      if (!ok) fail = (int32_t)(k0_ + n_ + 1);
+    }
   }
   // Outputs of a step that are NOT on the recursion's dependent path (offsets, chol of the inverse):
   // they only need the step's own factor S, so they are evaluated one iteration late, in the same
@@ -623,7 +673,7 @@ struct NatToSsmCore {
     for (int i = 0; i < DD; ++i) S2[i] = Dk[i];
     const bool ok = chol_lower<T, D>(S2, rinv2);
     if (!ok && fail == 0) fail = (int32_t)(k + 1);
-    // commit the new state only now: emit() of the previous step still reads the old one
+    // commit the new state only later: emit() of the previous step still reads the old one
 #pragma unroll
     for (int i = 0; i < D; ++i) z2_[i] = th[i];
 #pragma unroll
@@ -631,7 +681,6 @@ struct NatToSsmCore {
 #pragma unroll
     for (int i = 0; i < D; ++i) r2_[i] = rinv2[i];
   }
-  T S2_[DD], r2_[D], z2_[D];
   __device__ __forceinline__ void commit() {
 #pragma unroll
     for (int i = 0; i < DD; ++i) S[i] = S2_[i];
@@ -643,19 +692,216 @@ struct NatToSsmCore {
   }
   __device__ __forceinline__ void tile(const Params&, const T* const* in, T* const* out, int64_t j0,
                                        int ns) {
-    advance(in, out, ns - 1, j0 + ns - 1);
+    if (n_ - j0 < ns) ns = (int)(n_ - j0);  // ragged last segment
+    if (ns <= 0) return;
+    advance(in, out, ns - 1, k0_ + j0 + ns - 1);
     commit();
     for (int j = ns - 2; j >= 0; --j) {
-      advance(in, out, j, j0 + j);  // reads the state of step j+1 ...
-      emit(out, j + 1);             // ... and so does this: independent, interleaved by ptxas
+      advance(in, out, j, k0_ + j0 + j);  // reads the state of step j+1 ...
+      emit(out, j + 1);                   // ... and so does this: independent, interleaved by ptxas
       commit();
     }
     emit(out, 0);  // the tile's output stage is handed over when tile() returns
   }
-  __device__ __forceinline__ void finish(const Params& p, int64_t c, bool valid) {
-    if (valid && p.info) p.info[c] = fail;
+  __device__ __forceinline__ void finish(const Params& p, int64_t v, bool valid) {
+    if (!valid || !p.info) return;
+    if (p.P == 1) p.info[v] = fail;
+    else if (fail) atomicMax(p.info + v / p.P, fail);
   }
 };
+
+// pass 1: element (P, Q, R, p, r) of every segment but the first
+template <typename T_, int D>
+struct NatSummaryCore : NatGeomBase<T_, D> {
+  using T = T_;
+  using Params = NatToSsmParams<T>;
+  static constexpr int DD = D * D;
+  static constexpr int NIN = 3, NOUT = 0;
+  static constexpr int eout(int) { return 1; }
+  static __device__ __forceinline__ StreamGeom in_geom(const Params& p, int i, int64_t v) {
+    StreamGeom g = NatGeomBase<T_, D>::in_geom(p, i, v);
+    if (v % p.P == 0) g.end = 0;  // the first segment feeds nobody: nothing to load
+    return g;
+  }
+  static __device__ __forceinline__ StreamGeom out_geom(const Params&, int, int64_t) {
+    return StreamGeom{nullptr, 0, 0};
+  }
+  T S[DD], rinv[D], Pm[DD], Q[DD], R[DD], pv[D], rv[D];
+  int32_t fail;
+  int64_t Tn_, k0_, n_;
+  bool live_, started_;
+  __device__ __forceinline__ void init(const Params& p, int64_t v) {
+    Tn_ = p.Tn;
+    k0_ = (v % p.P) * p.L;
+    n_ = seg_steps(p.Tn, k0_, p.L);
+    live_ = (v % p.P) > 0 && n_ > 0;
+    started_ = false;
+    fail = 0;
+  }
+  __device__ __forceinline__ void tile(const Params&, const T* const* in, T* const*, int64_t j0, int ns) {
+    if (!live_) return;
+    if (n_ - j0 < ns) ns = (int)(n_ - j0);
+    for (int j = ns - 1; j >= 0; --j) {
+      const int64_t k = k0_ + j0 + j;
+      T Dk[DD], th[D], Ths[DD];
+      ld_s<T, D>(th, in[0] + j * D);
+      ld_s<T, DD>(Dk, in[1] + j * DD);
+#pragma unroll
+      for (int i = 0; i < DD; ++i) Dk[i] = T(-2) * Dk[i];
+      const bool coupled = k + 1 < Tn_;
+      if (coupled) ld_s<T, DD>(Ths, in[2] + j * DD);
+      if (!started_) {
+        // far end of the segment: P = Th, Q = Ths^T, R = 0, p = th, r = 0 (the last segment of a
+        // chain has no incoming block: only P and p matter)
+#pragma unroll
+        for (int a = 0; a < D; ++a)
+#pragma unroll
+          for (int b = 0; b < D; ++b) {
+            Q[a * D + b] = coupled ? Ths[b * D + a] : T(0);
+            R[a * D + b] = T(0);
+          }
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          pv[i] = th[i];
+          rv[i] = T(0);
+        }
+        started_ = true;
+      } else {
+        // S = chol(P) of the previous step: W = P^{-1} Q, A = P^{-1} Ths
+        T W[DD], A[DD], u[D];
+#pragma unroll
+        for (int i = 0; i < DD; ++i) {
+          W[i] = Q[i];
+          A[i] = Ths[i];
+        }
+        trsm_left_lower<T, D>(S, rinv, W);
+        trsm_left_lower_t<T, D>(S, rinv, W);
+        trsm_left_lower<T, D>(S, rinv, A);
+        trsm_left_lower_t<T, D>(S, rinv, A);
+        // r' = r + W^T p,  R' = R - Q^T W,  Q' = Ths^T W,  p' = th + A^T p,  P' = Th - Ths^T A
+        gemv_t_add<T, D>(rv, W, pv);
+        T Qn[DD];
+#pragma unroll
+        for (int a = 0; a < D; ++a)
+#pragma unroll
+          for (int b = 0; b < D; ++b) {
+            T vr = R[a * D + b], vq = T(0);
+#pragma unroll
+            for (int s = 0; s < D; ++s) {
+              vr = Num<T>::fma(-Q[s * D + a], W[s * D + b], vr);
+              vq = Num<T>::fma(Ths[s * D + a], W[s * D + b], vq);
+            }
+            R[a * D + b] = vr;
+            Qn[a * D + b] = vq;
+          }
+#pragma unroll
+        for (int i = 0; i < DD; ++i) Q[i] = Qn[i];
+#pragma unroll
+        for (int i = 0; i < D; ++i) u[i] = th[i];
+        gemv_t_add<T, D>(u, A, pv);
+#pragma unroll
+        for (int i = 0; i < D; ++i) pv[i] = u[i];
+#pragma unroll
+        for (int r = 0; r < D; ++r)
+#pragma unroll
+          for (int q = 0; q <= r; ++q) {
+            T v = Dk[r * D + q];
+#pragma unroll
+            for (int s = 0; s < D; ++s) v = Num<T>::fma(-Ths[s * D + r], A[s * D + q], v);
+            Dk[r * D + q] = v;
+          }
+      }
+#pragma unroll
+      for (int i = 0; i < DD; ++i) {
+        Pm[i] = Dk[i];
+        S[i] = Dk[i];
+      }
+      const bool ok = chol_lower<T, D>(S, rinv);
+      if (!ok && fail == 0) fail = (int32_t)(k + 1);
+    }
+  }
+  __device__ __forceinline__ void finish(const Params& p, int64_t v, bool valid) {
+    if (!valid || !live_) return;
+    const int64_t c = v / p.P;
+    mirror_lower<T, D>(Pm);
+    store_vec<T, DD>(p.out_chol + (c * p.Tn + k0_) * DD, Pm);
+    store_vec<T, D>(p.out_off + (c * p.Tn + k0_) * D, pv);
+    if (n_ >= 2) {
+      store_vec<T, DD>(p.out_chol + (c * p.Tn + k0_ + 1) * DD, R);
+      store_vec<T, D>(p.out_off + (c * p.Tn + k0_ + 1) * D, rv);
+    }
+    if (k0_ < p.Tn - 1) store_vec<T, DD>(p.out_a + (c * (p.Tn - 1) + k0_) * DD, Q);
+    if (fail && p.info) atomicMax(p.info + c, fail);
+  }
+};
+
+// pass 2: one thread per chain folds the elements from the last segment down and parks the state
+// (D, z) entering every segment s < P-1 in that segment's first output slots.
+template <typename T, int D>
+__global__ void __launch_bounds__(128)
+nat_seed_kernel(const NatToSsmParams<T> p) {
+  constexpr int DD = D * D;
+  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= p.B) return;
+  T Din[DD], zin[D];
+  int32_t fail = 0;
+  for (int64_t seg = p.P - 1; seg >= 0; --seg) {
+    const int64_t k0 = seg * p.L;
+    const int64_t n = seg_steps(p.Tn, k0, p.L);
+    if (n <= 0) continue;
+    const bool last = k0 + n >= p.Tn;
+    T Pm[DD], Q[DD], R[DD], pv[D], rv[D];
+    if (seg > 0) {  // element of this segment (loaded before its slots receive the seed)
+      load_vec<T, DD>(Pm, p.out_chol + (c * p.Tn + k0) * DD);
+      load_vec<T, D>(pv, p.out_off + (c * p.Tn + k0) * D);
+      if (!last) {
+        load_vec<T, DD>(R, p.out_chol + (c * p.Tn + k0 + 1) * DD);
+        load_vec<T, D>(rv, p.out_off + (c * p.Tn + k0 + 1) * D);
+        load_vec<T, DD>(Q, p.out_a + (c * (p.Tn - 1) + k0) * DD);
+      }
+    }
+    if (!last) {
+      store_vec<T, DD>(p.out_chol + (c * p.Tn + k0) * DD, Din);
+      store_vec<T, D>(p.out_off + (c * p.Tn + k0) * D, zin);
+    }
+    if (seg == 0) break;
+    if (last) {
+#pragma unroll
+      for (int i = 0; i < DD; ++i) Din[i] = Pm[i];
+#pragma unroll
+      for (int i = 0; i < D; ++i) zin[i] = pv[i];
+    } else {
+      // M = D_in + R = C C^T;  Y = M^{-1} Q^T;  D_out = P - Q Y;  z_out = p + Y^T (z_in + r)
+      T M[DD], rinv[D], Y[DD], u[D];
+#pragma unroll
+      for (int i = 0; i < DD; ++i) M[i] = Din[i] + R[i];
+      const bool ok = chol_lower<T, D>(M, rinv);
+      if (!ok && fail == 0) fail = (int32_t)(k0 + n + 1);
+#pragma unroll
+      for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int b = 0; b < D; ++b) Y[a * D + b] = Q[b * D + a];
+      trsm_left_lower<T, D>(M, rinv, Y);
+      trsm_left_lower_t<T, D>(M, rinv, Y);
+#pragma unroll
+      for (int i = 0; i < D; ++i) u[i] = zin[i] + rv[i];
+#pragma unroll
+      for (int i = 0; i < D; ++i) zin[i] = pv[i];
+      gemv_t_add<T, D>(zin, Y, u);
+#pragma unroll
+      for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int q = 0; q <= r; ++q) {
+          T v = Pm[r * D + q];
+#pragma unroll
+          for (int s = 0; s < D; ++s) v = Num<T>::fma(-Q[r * D + s], Y[s * D + q], v);
+          Din[r * D + q] = v;
+          Din[q * D + r] = v;
+        }
+    }
+  }
+  if (fail && p.info) atomicMax(p.info + c, fail);
+}
 
 // ---------------------------------------------------------------------------------------------
 // Compile-time choice of a ring geometry that fits (chains per CTA, steps per tile, stages).

@@ -125,3 +125,55 @@ def test_not_positive_definite_naturals_raise():
     th_diag[1, 2] *= -1.0
     with pytest.raises(mf.CholeskyError):
         mf.naturals_to_ssm_params(tt(th_lin), tt(th_diag), tt(th_sub))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 5e-4)])
+@pytest.mark.parametrize("d", [1, 2, 3, 4])
+@pytest.mark.parametrize("b,t", [(1, 1000), (3, 301), (2, 130), (5, 640)])
+def test_naturals_to_ssm_params_parallel_in_time(b, t, d, dtype, tol):
+    """Few long chains: the backward U D U^T recursion is evaluated parallel in time (segment
+    elements of the linear-fractional map -> seeds -> seeded sweeps, ssm_sweep.cuh).  Must agree
+    with the sequential sweep (tuning knob 2 = 1) and recover the SSM the naturals came from."""
+    import markovflow_b200 as mf
+    from markovflow_b200 import _lib
+
+    state = np.random.get_state()
+    np.random.seed(b * 7919 + t * 13 + d)
+    arrays = random_ssm_arrays((b,), t - 1, d, scale_a=0.6 / np.sqrt(d))
+    np.random.set_state(state)
+    mu0, l0, a, bb, lq = arrays
+    want = (a, bb, l0, lq, mu0)
+    th = mf.ssm_to_naturals(make_ssm(arrays))  # float64 naturals on the device
+    th = tuple(x.to(dtype) for x in th)
+    lib = _lib.lib()
+    res = {}
+    for knob in (0, 1):
+        lib.mf_set_tuning(2, knob)
+        try:
+            res[knob] = mf.naturals_to_ssm_params(*th)
+        finally:
+            lib.mf_set_tuning(2, 0)
+        _check_params(res[knob], want, tol)
+    for g, w in zip(res[0], res[1]):
+        assert max_rel_err(npy(g), npy(w)) < tol
+
+
+def test_naturals_to_ssm_params_parallel_in_time_short_segments_and_failure():
+    import markovflow_b200 as mf
+    from markovflow_b200 import _lib
+
+    arrays = random_ssm_arrays((2,), 200, 2)
+    mu0, l0, a, bb, lq = arrays
+    th = mf.ssm_to_naturals(make_ssm(arrays))
+    lib = _lib.lib()
+    for seg in (4, 7, 50, 100, 199):  # knob 3: steps per segment (ragged last segments included)
+        lib.mf_set_tuning(3, seg)
+        try:
+            got = mf.naturals_to_ssm_params(*th)
+        finally:
+            lib.mf_set_tuning(3, 0)
+        _check_params(got, (a, bb, l0, lq, mu0), 1e-9)
+    bad = th[1].clone()
+    bad[1, 120] *= -1.0
+    with pytest.raises(mf.CholeskyError):
+        mf.naturals_to_ssm_params(th[0], bad, th[2])
