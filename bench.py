@@ -303,6 +303,9 @@ def run_gpu(args):
         _lib.check(st, "mf_btd_cholesky")
 
     # ---- device-resident timing ----------------------------------------------------------------
+    # cudaProfilerStart/Stop bracket the warm-up + timed launches: `ncu --profile-from-start off`
+    # then lists exactly the launches of the timed region (no effect without a profiler)
+    torch.cuda.profiler.start()
     for _ in range(args.warmup):
         step()
     barrier()
@@ -316,6 +319,7 @@ def run_gpu(args):
             z.record()
         e1.record()
         barrier()
+        torch.cuda.profiler.stop()
         # keep the sampled window long enough (~1.5 s) for several nvidia-smi samples under load
         for _ in range(max(0, 450 - args.steps)):
             step()
