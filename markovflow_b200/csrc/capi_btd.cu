@@ -155,6 +155,12 @@ int mf_btd_cholesky(int dtype, const void* diag, const void* sub, const void* rh
     return exp_chol_d3(tuning(6) - 1, diag, sub, rhs, out_diag, out_sub, out_x, out_logdet, info, B, T, s);
   if (D > MF_SMALL_D_MAX)
     return big_cholesky(dtype, diag, sub, rhs, out_diag, out_sub, out_x, out_logdet, info, B, T, D, s);
+  if (D <= kSsmSweepMaxD && tuning(4) != 1) {
+    // few long chains: parallel in time (btd_pit.cuh); the log-determinant is read off the factor
+    const int rc = btd_sweep_cholesky_pit(dtype, D, diag, sub, rhs, out_diag, out_sub, out_x, info, B, T, s);
+    if (rc == MF_OK && out_logdet) return mf_btd_abs_log_det(dtype, out_diag, out_logdet, B, T, D, stream);
+    if (rc != MF_ERR_UNSUPPORTED) return rc;
+  }
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;

@@ -1,5 +1,6 @@
 // TMA-sweep implementations of LowerTriangularBlockTriDiagonal.solve, the sparse inverse subset and
 // the U D U^T factorisation (btd_sweep_cores.cuh); called from capi_btd.cu.
+#include "btd_pit.cuh"
 #include "btd_sweep_cores.cuh"
 #include "dispatch.cuh"
 #include "ssm_sweep_api.h"
@@ -76,6 +77,43 @@ int btd_sweep_udu(int dtype, int64_t D, const void* diag, const void* sub, void*
     constexpr int kD = decltype(dd)::value;
     BtdUduParams<Tp> p{(const Tp*)diag, (const Tp*)sub, (Tp*)ou, (Tp*)ocd, info, B, T};
     return run<BtdUduCore<Tp, kD>>(p, B, s);
+  });
+}
+
+// Few long chains: block Cholesky (+ solve) parallel in time (btd_pit.cuh).  MF_ERR_UNSUPPORTED when
+// it does not apply (many chains, short chains, aliased outputs, D > 4): the caller then runs the
+// sequential sweep.  out_logdet is filled from the factor afterwards by the caller.
+int btd_sweep_cholesky_pit(int dtype, int64_t D, const void* diag, const void* sub, const void* rhs,
+                           void* od, void* os, void* ox, int32_t* info, int64_t B, int64_t T,
+                           cudaStream_t s) {
+  if (!sub || !os || T < 128 || B > 1024 || tuning(2) == 1) return MF_ERR_UNSUPPORTED;
+  if (od == diag || os == sub || (rhs && ox == rhs)) return MF_ERR_UNSUPPORTED;  // slots are scratch
+  return dispatch_btd_sweep(dtype, D, [&](auto tt, auto dd) {
+    using Tp = typename decltype(tt)::type;
+    constexpr int kD = decltype(dd)::value;
+    CholPitParams<Tp> p{(const Tp*)diag, (const Tp*)sub, (const Tp*)rhs, (Tp*)od, (Tp*)os, (Tp*)ox,
+                        info, B, T, 1, T};
+    const int64_t target = (int64_t)148 * 192;
+    int64_t np = (target + B - 1) / B;
+    if (np > T / 64) np = T / 64;
+    if (np > 512) np = 512;  // the seeds are folded sequentially per chain
+    if (tuning(3) > 1 && tuning(3) < T) np = (T + tuning(3) - 1) / tuning(3);
+    if (np < 2) return (int)MF_ERR_UNSUPPORTED;
+    p.L = (T + np - 1) / np;
+    if (p.L < 2) p.L = 2;
+    p.P = (T + p.L - 1) / p.L;
+    if (p.P < 2) return (int)MF_ERR_UNSUPPORTED;
+    if (info && cudaMemsetAsync(info, 0, sizeof(int32_t) * B, s) != cudaSuccess) return check_launch();
+    int rc;
+    if (rhs) rc = run<CholPitSummaryCore<Tp, kD, true>>(p, B * p.P, s);
+    else rc = run<CholPitSummaryCore<Tp, kD, false>>(p, B * p.P, s);
+    if (rc != MF_OK) return rc;
+    if (rhs) chol_pit_seed_kernel<Tp, kD, true><<<grid_for(B, 128), 128, 0, s>>>(p);
+    else chol_pit_seed_kernel<Tp, kD, false><<<grid_for(B, 128), 128, 0, s>>>(p);
+    rc = check_launch();
+    if (rc != MF_OK) return rc;
+    if (rhs) return run<CholPitCore<Tp, kD, true>>(p, B * p.P, s);
+    return run<CholPitCore<Tp, kD, false>>(p, B * p.P, s);
   });
 }
 

@@ -29,6 +29,9 @@ int btd_sweep_solve(int dtype, int64_t D, const void* ld, const void* ls, const 
                     int64_t n, int64_t Bm, int64_t T, int transpose, cudaStream_t s);
 int btd_sweep_inverse_subset(int dtype, int64_t D, const void* ld, const void* ls, void* od, void* os,
                              int64_t B, int64_t T, cudaStream_t s);
+int btd_sweep_cholesky_pit(int dtype, int64_t D, const void* diag, const void* sub, const void* rhs,
+                           void* od, void* os, void* ox, int32_t* info, int64_t B, int64_t T,
+                           cudaStream_t s);
 int btd_sweep_udu(int dtype, int64_t D, const void* diag, const void* sub, void* ou, void* ocd,
                   int32_t* info, int64_t B, int64_t T, cudaStream_t s);
 

@@ -354,3 +354,78 @@ def test_config2_shape_slice_matern52_posterior_precision():
     assert max_rel_err(npy(chol.block_diagonal), o_ld) < 1e-10
     assert max_rel_err(npy(chol.block_sub_diagonal), o_ls) < 1e-10
     assert max_rel_err(npy(x), O.btd_solve(o_ld, o_ls, rhs)) < 1e-10
+
+
+# ------------------------------------------------------------------------------------------------
+# few long chains: the factorisation is evaluated parallel in time (btd_pit.cuh) -- segment elements
+# of the linear-fractional map (S, r) -> (S', r'), seeds, seeded sweeps.  Must equal the oracle and
+# the sequential sweep (tuning knob 2 = 1).
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("d", [1, 2, 3, 4])
+@pytest.mark.parametrize("b,t", [(1, 2000), (3, 301), (2, 130), (7, 640)])
+def test_cholesky_parallel_in_time(b, t, d, dtype):
+    from markovflow_b200 import _lib
+
+    _, S = _mods()
+    diag, sub, _, _ = random_well_conditioned_spd_btd((b,), t, d, rng=31 * d + t)
+    rhs = np.random.default_rng(t).standard_normal((b, t, d))
+    if dtype == torch.float32:
+        diag, sub, rhs = (a.astype(np.float32).astype(np.float64) for a in (diag, sub, rhs))
+    o_ld, o_ls = O.btd_cholesky(diag, sub)
+    o_x = O.btd_solve(o_ld, o_ls, rhs)
+    tol = TOL[dtype]
+    lib = _lib.lib()
+    out = {}
+    for knob in (0, 1):
+        lib.mf_set_tuning(2, knob)
+        try:
+            m = S(tt(diag, dtype), tt(sub, dtype))
+            chol, x, logdet = m.cholesky_and_solve(tt(rhs, dtype), want_log_det=True)
+            plain = m.cholesky
+        finally:
+            lib.mf_set_tuning(2, 0)
+        assert max_rel_err(npy(chol.block_diagonal), o_ld) < tol
+        assert max_rel_err(npy(chol.block_sub_diagonal), o_ls) < tol
+        assert max_rel_err(npy(x), o_x) < tol
+        assert max_rel_err(npy(logdet), O.btd_abs_log_det(o_ld)) < tol
+        assert float(torch.triu(chol.block_diagonal, 1).abs().max()) == 0.0
+        assert max_rel_err(npy(plain.block_diagonal), o_ld) < tol
+        out[knob] = (npy(chol.block_diagonal), npy(chol.block_sub_diagonal), npy(x))
+    for a, b_ in zip(out[0], out[1]):
+        assert max_rel_err(a, b_) < tol
+
+
+def test_cholesky_parallel_in_time_segments_alias_and_failure():
+    from markovflow_b200 import CholeskyError, _lib
+
+    _, S = _mods()
+    t, d, b = 400, 3, 2
+    diag, sub, _, _ = random_well_conditioned_spd_btd((b,), t, d, rng=9)
+    rhs = np.random.default_rng(1).standard_normal((b, t, d))
+    o_ld, o_ls = O.btd_cholesky(diag, sub)
+    o_x = O.btd_solve(o_ld, o_ls, rhs)
+    lib = _lib.lib()
+    for seg in (2, 3, 7, 64, 133, 399):  # knob 3: steps per segment, ragged last segments included
+        lib.mf_set_tuning(3, seg)
+        try:
+            chol, x, _ = S(tt(diag), tt(sub)).cholesky_and_solve(tt(rhs))
+        finally:
+            lib.mf_set_tuning(3, 0)
+        assert max_rel_err(npy(chol.block_diagonal), o_ld) < 1e-10
+        assert max_rel_err(npy(chol.block_sub_diagonal), o_ls) < 1e-10
+        assert max_rel_err(npy(x), o_x) < 1e-10
+    # in place (outputs alias inputs): the output slots cannot serve as scratch -> sequential sweep
+    dg, sb = tt(diag).clone(), tt(sub).clone()
+    info = torch.zeros(b, dtype=torch.int32, device=dev())
+    st = lib.mf_btd_cholesky(_lib.MF_F64, _lib.ptr(dg), _lib.ptr(sb), None, _lib.ptr(dg), _lib.ptr(sb), None,
+                             None, _lib.ptr(info), _lib.i64(b), _lib.i64(t), _lib.i64(d), _lib.current_stream())
+    assert st == 0
+    torch.cuda.synchronize()
+    assert max_rel_err(npy(dg), o_ld) < 1e-10 and max_rel_err(npy(sb), o_ls) < 1e-10
+    # a block that is not positive definite is reported for its chain
+    bad = diag.copy()
+    bad[1, 250] = -np.eye(d)
+    with pytest.raises(CholeskyError, match="chain 1"):
+        S(tt(bad), tt(sub)).cholesky

@@ -107,6 +107,21 @@ def btd(b=4096, t=10_000):
     lib.mf_set_tuning(4, 0)
 
 
+def fewchains():
+    """Cholesky + solve of FEW long chains: parallel in time (btd_pit.cuh) vs the sequential sweep."""
+    lib = _lib.lib()
+    for b, t in ((1, 1_000_000), (8, 100_000), (64, 10_000), (256, 10_000), (1024, 10_000)):
+        diag, sub, rhs = bench_inputs.matern52_posterior_precision(b, t, DEV, chunk=min(b, 64))
+        m = mf.SymmetricBlockTriDiagonal(diag, sub)
+        for knob, label in ((0, "parallel in time"), (1, "sequential sweep")):
+            lib.mf_set_tuning(2, knob)
+            ms = timeit(lambda: m.cholesky_and_solve(rhs), warm=2, reps=5)
+            report(f"cholesky+solve B={b} T={t} D=3 f64 [{label}]", b * t, 336, ms)
+        lib.mf_set_tuning(2, 0)
+        del diag, sub, rhs, m
+        torch.cuda.empty_cache()
+
+
 def config4(b=256, t=10_000):
     """Config 4 at reduced T (the full T=1e5 needs 118 GB of inputs: in-place, 8 GPUs or B-chunks)."""
     diag, sub, rhs = bench_inputs.sum_kernel_posterior_precision(b, t, DEV)
