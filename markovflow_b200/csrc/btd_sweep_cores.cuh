@@ -13,54 +13,86 @@
 namespace mf {
 
 // ---------------------------------------------------------------------------------------------
+// Triangular solve.  The recursion is affine in x, so few long chains are evaluated parallel in time
+// (exactly): every segment composes its steps into (Phi, c) with x_out = Phi x_in + c (SUMMARY pass:
+// the recursion is run on c and on the D columns of Phi), a per-chain fold gives the x entering every
+// segment, and the segments then run the ordinary sweep from their seeds.  No workspace: the D+1
+// vectors of an element and the seed are parked in the output slots the owning segment writes last.
 template <typename T>
 struct BtdSolveParams {
   const T *ld, *ls, *rhs;
   T* out;
   int64_t n, Bm, Tn;
+  int64_t P, L;  // segments per chain, steps per segment (P == 1: L == Tn)
 };
+
+// output step that holds parked vector i (0: c | seed, 1..D: columns of Phi) of segment [k0, k0+n)
+template <bool TRANSPOSE>
+__device__ __forceinline__ int64_t solve_slot(int64_t k0, int64_t n, int i) {
+  return TRANSPOSE ? k0 + i : k0 + n - 1 - i;
+}
 
 // forward : x_k = Ld_k^{-1} (b_k - Ls_{k-1} x_{k-1});  backward: x_k = Ld_k^{-T} (b_k - Ls_k^T x_{k+1}).
 // UNIT: identity diagonal blocks (ld == NULL);  SUB: a sub-diagonal exists.
-template <typename T_, int D, bool TRANSPOSE, bool UNIT, bool SUB>
+template <typename T_, int D, bool TRANSPOSE, bool UNIT, bool SUB, bool SUMMARY = false>
 struct BtdSolveCore {
   using T = T_;
   using Params = BtdSolveParams<T>;
   static constexpr int DD = D * D;
-  static constexpr int NIN = 1 + (UNIT ? 0 : 1) + (SUB ? 1 : 0), NOUT = 1;
+  static constexpr int NIN = 1 + (UNIT ? 0 : 1) + (SUB ? 1 : 0), NOUT = SUMMARY ? 0 : 1;
   static constexpr bool BACKWARD = TRANSPOSE;
   static constexpr int I_LD = UNIT ? -1 : 1, I_LS = SUB ? (UNIT ? 1 : 2) : -1;
   static constexpr int ein(int i) { return i == 0 ? D : DD; }
   static constexpr int eout(int) { return D; }
-  static __device__ __forceinline__ int64_t num_chains(const Params& p) { return p.n; }
-  static __device__ __forceinline__ int64_t max_steps(const Params& p) { return p.Tn; }
-  static __device__ __forceinline__ StreamGeom in_geom(const Params& p, int i, int64_t c) {
-    if (i == 0) return geom_states<T>(p.rhs, c, p.Tn, D);
-    if (i == I_LD) return geom_states<T>(p.ld, c % p.Bm, p.Tn, DD);
-    // forward needs Ls_{k-1} at step k (incoming), backward needs Ls_k at step k (outgoing)
-    return TRANSPOSE ? geom_outgoing<T>(p.ls, c % p.Bm, p.Tn, DD) : geom_incoming<T>(p.ls, c % p.Bm, p.Tn, DD);
+  static __device__ __forceinline__ int64_t num_chains(const Params& p) { return p.n * p.P; }
+  static __device__ __forceinline__ int64_t max_steps(const Params& p) { return p.L; }
+  // a segment is summarised iff another segment consumes its result
+  static __device__ __forceinline__ bool is_live(const Params& p, int64_t v) {
+    const int64_t seg = v % p.P, k0 = seg * p.L;
+    return TRANSPOSE ? (seg > 0 && k0 < p.Tn) : (k0 + p.L < p.Tn);
   }
-  static __device__ __forceinline__ StreamGeom out_geom(const Params& p, int, int64_t c) {
-    return geom_states<T>(p.out, c, p.Tn, D);
+  static __device__ __forceinline__ StreamGeom in_geom(const Params& p, int i, int64_t v) {
+    const int64_t c = v / p.P, k0 = (v % p.P) * p.L;
+    int64_t n = seg_steps(p.Tn, k0, p.L);
+    if (SUMMARY && !is_live(p, v)) n = 0;
+    if (i == 0) return vgeom_states<T>(p.rhs, c, p.Tn, D, k0, n);
+    if (i == I_LD) return vgeom_states<T>(p.ld, c % p.Bm, p.Tn, DD, k0, n);
+    // forward needs Ls_{k-1} at step k (incoming), backward needs Ls_k at step k (outgoing)
+    return TRANSPOSE ? vgeom_outgoing<T>(p.ls, c % p.Bm, p.Tn, DD, k0, n)
+                     : vgeom_incoming<T>(p.ls, c % p.Bm, p.Tn, DD, k0, n);
+  }
+  static __device__ __forceinline__ StreamGeom out_geom(const Params& p, int, int64_t v) {
+    if (SUMMARY) return StreamGeom{nullptr, 0, 0};
+    const int64_t c = v / p.P, k0 = (v % p.P) * p.L;
+    return vgeom_states<T>(p.out, c, p.Tn, D, k0, seg_steps(p.Tn, k0, p.L));
   }
   T x[D];
-  int64_t Tn_;
-  __device__ __forceinline__ void init(const Params& p, int64_t) {
+  T Phi[SUMMARY ? DD : 1];  // column q at Phi[q * D ..]
+  int64_t Tn_, k0_, n_;
+  bool live_;
+  __device__ __forceinline__ void init(const Params& p, int64_t v) {
+    const int64_t c = v / p.P;
     Tn_ = p.Tn;
+    k0_ = (v % p.P) * p.L;
+    n_ = seg_steps(p.Tn, k0_, p.L);
+    live_ = !SUMMARY || is_live(p, v);
 #pragma unroll
     for (int i = 0; i < D; ++i) x[i] = T(0);
+    if (SUMMARY) {
+#pragma unroll
+      for (int i = 0; i < DD; ++i) Phi[SUMMARY ? i : 0] = (i / D == i % D) ? T(1) : T(0);
+    } else if (n_ > 0 && (TRANSPOSE ? k0_ + n_ < p.Tn : k0_ > 0)) {
+      load_vec<T, D>(x, p.out + (c * p.Tn + solve_slot<TRANSPOSE>(k0_, n_, 0)) * D);  // seed
+    }
   }
-  __device__ __forceinline__ void step(const T* const* in, T* const* out, int j, int64_t k) {
-    T r[D];
-    ld_s<T, D>(r, in[0] + j * D);
-    if (SUB) {
-      const bool coupled = TRANSPOSE ? (k + 1 < Tn_) : (k > 0);
-      if (coupled) {
-        T A[DD];
-        ld_s<T, DD>(A, in[I_LS < 0 ? 0 : I_LS] + j * DD);
-        if (TRANSPOSE) gemv_t_sub<T, D>(r, A, x);
-        else gemv_sub<T, D>(r, A, x);
-      }
+  // r <- Ld^{-1} (r - Ls xin)  (or the transposed form); blocks of local step j
+  __device__ __forceinline__ void apply(T* __restrict__ r, const T* __restrict__ xin, const T* const* in,
+                                        int j, bool coupled) {
+    if (SUB && coupled) {
+      T A[DD];
+      ld_s<T, DD>(A, in[I_LS < 0 ? 0 : I_LS] + j * DD);
+      if (TRANSPOSE) gemv_t_sub<T, D>(r, A, xin);
+      else gemv_sub<T, D>(r, A, xin);
     }
     if (!UNIT) {
       T L[DD], rinv[D];
@@ -70,20 +102,85 @@ struct BtdSolveCore {
       if (TRANSPOSE) trsv_lower_t<T, D>(L, rinv, r);
       else trsv_lower<T, D>(L, rinv, r);
     }
+  }
+  __device__ __forceinline__ void step(const T* const* in, T* const* out, int j, int64_t k) {
+    const bool coupled = TRANSPOSE ? (k + 1 < Tn_) : (k > 0);
+    T r[D];
+    ld_s<T, D>(r, in[0] + j * D);
+    apply(r, x, in, j, coupled);
+    if (SUMMARY) {
+#pragma unroll
+      for (int q = 0; q < D; ++q) {
+        T h[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) h[i] = T(0);
+        apply(h, Phi + (SUMMARY ? q * D : 0), in, j, coupled);
+#pragma unroll
+        for (int i = 0; i < D; ++i) Phi[SUMMARY ? q * D + i : 0] = coupled ? h[i] : T(0);
+      }
+    }
 #pragma unroll
     for (int i = 0; i < D; ++i) x[i] = r[i];
-    st_s<T, D>(out[0] + j * D, x);
+    if (!SUMMARY) st_s<T, D>(out[0] + j * D, x);
   }
   __device__ __forceinline__ void tile(const Params&, const T* const* in, T* const* out, int64_t j0,
                                        int ns) {
+    if (!live_) return;
+    if (n_ - j0 < ns) ns = (int)(n_ - j0);
     if (TRANSPOSE) {
-      for (int j = ns - 1; j >= 0; --j) step(in, out, j, j0 + j);
+      for (int j = ns - 1; j >= 0; --j) step(in, out, j, k0_ + j0 + j);
     } else {
-      for (int j = 0; j < ns; ++j) step(in, out, j, j0 + j);
+      for (int j = 0; j < ns; ++j) step(in, out, j, k0_ + j0 + j);
     }
   }
-  __device__ __forceinline__ void finish(const Params&, int64_t, bool) {}
+  __device__ __forceinline__ void finish(const Params& p, int64_t v, bool valid) {
+    if (!SUMMARY || !valid || !live_) return;
+    const int64_t c = v / p.P;
+    store_vec<T, D>(p.out + (c * p.Tn + solve_slot<TRANSPOSE>(k0_, n_, 0)) * D, x);
+#pragma unroll
+    for (int q = 0; q < D; ++q)
+      store_vec<T, D>(p.out + (c * p.Tn + solve_slot<TRANSPOSE>(k0_, n_, q + 1)) * D,
+                      Phi + (SUMMARY ? q * D : 0));
+  }
 };
+
+// fold of the segment elements of one rhs chain (one thread per chain), in sweep order; parks the x
+// entering every segment in that segment's seed slot.
+template <typename T, int D, bool TRANSPOSE>
+__global__ void __launch_bounds__(128)
+btd_solve_seed_kernel(const BtdSolveParams<T> p) {
+  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= p.n) return;
+  T x[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) x[i] = T(0);
+  const int64_t nseg = (p.Tn + p.L - 1) / p.L;
+  for (int64_t it = 0; it < nseg; ++it) {
+    const int64_t seg = TRANSPOSE ? nseg - 1 - it : it;
+    const int64_t k0 = seg * p.L;
+    const int64_t n = seg_steps(p.Tn, k0, p.L);
+    const bool live = it + 1 < nseg;  // feeds a later segment of the sweep
+    T cv[D], Phi[D * D];
+    if (live) {
+      load_vec<T, D>(cv, p.out + (c * p.Tn + solve_slot<TRANSPOSE>(k0, n, 0)) * D);
+#pragma unroll
+      for (int q = 0; q < D; ++q)
+        load_vec<T, D>(Phi + q * D, p.out + (c * p.Tn + solve_slot<TRANSPOSE>(k0, n, q + 1)) * D);
+    }
+    if (it > 0) store_vec<T, D>(p.out + (c * p.Tn + solve_slot<TRANSPOSE>(k0, n, 0)) * D, x);
+    if (!live) break;
+    T y[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      T v = cv[i];
+#pragma unroll
+      for (int q = 0; q < D; ++q) v = Num<T>::fma(Phi[q * D + i], x[q], v);
+      y[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) x[i] = y[i];
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 template <typename T>

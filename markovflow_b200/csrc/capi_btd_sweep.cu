@@ -1,5 +1,7 @@
 // TMA-sweep implementations of LowerTriangularBlockTriDiagonal.solve, the sparse inverse subset and
 // the U D U^T factorisation (btd_sweep_cores.cuh); called from capi_btd.cu.
+#include <type_traits>
+
 #include "btd_pit.cuh"
 #include "btd_sweep_cores.cuh"
 #include "dispatch.cuh"
@@ -39,21 +41,53 @@ int run(const typename Core::Params& p, int64_t nchains, cudaStream_t s) {
 
 }  // namespace
 
+// segments per chain for a parallel-in-time sweep whose seeds are folded by one thread per chain
+static void plan_pit(int64_t chains, int64_t T, int min_len, int64_t* P, int64_t* L) {
+  const int64_t target = (int64_t)148 * 192;
+  int64_t np = chains >= target / 2 ? 1 : (target + chains - 1) / chains;
+  if (np > T / 64) np = T / 64;
+  if (np > 512) np = 512;
+  if (tuning(3) > 1 && tuning(3) < T) np = (T + tuning(3) - 1) / tuning(3);
+  if (np < 1) np = 1;
+  int64_t l = (T + np - 1) / np;
+  if (l < min_len) l = min_len;
+  // a ragged last segment must still hold the parked vectors (backward sweeps summarise it)
+  while (l < T && T % l != 0 && T % l < min_len) ++l;
+  *L = l;
+  *P = (T + l - 1) / l;
+}
+
 int btd_sweep_solve(int dtype, int64_t D, const void* ld, const void* ls, const void* rhs, void* out,
                     int64_t n, int64_t Bm, int64_t T, int transpose, cudaStream_t s) {
   return dispatch_btd_sweep(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
-    BtdSolveParams<Tp> p{(const Tp*)ld, (const Tp*)ls, (const Tp*)rhs, (Tp*)out, n, Bm, T};
+    BtdSolveParams<Tp> p{(const Tp*)ld, (const Tp*)ls, (const Tp*)rhs, (Tp*)out, n, Bm, T, 1, T};
+    // few long chains with a recursion (sub-diagonal): parallel in time; the output slots serve as
+    // scratch, so not when out aliases rhs
+    if (ls && tuning(2) != 1 && out != rhs && T >= 128) plan_pit(n, T, kD + 2, &p.P, &p.L);
     const int v = (transpose ? 4 : 0) | (ld ? 0 : 2) | (ls ? 1 : 0);
+    auto go = [&](auto tr, auto unit, auto sub) -> int {
+      constexpr bool kT = decltype(tr)::value, kU = decltype(unit)::value, kS = decltype(sub)::value;
+      if (p.P > 1) {
+        int rc = run<BtdSolveCore<Tp, kD, kT, kU, kS, true>>(p, n * p.P, s);
+        if (rc != MF_OK) return rc;
+        btd_solve_seed_kernel<Tp, kD, kT><<<grid_for(n, 128), 128, 0, s>>>(p);
+        rc = check_launch();
+        if (rc != MF_OK) return rc;
+      }
+      return run<BtdSolveCore<Tp, kD, kT, kU, kS, false>>(p, n * p.P, s);
+    };
+    using Y = std::true_type;
+    using N = std::false_type;
     switch (v) {
-      case 0: return run<BtdSolveCore<Tp, kD, false, false, false>>(p, n, s);
-      case 1: return run<BtdSolveCore<Tp, kD, false, false, true>>(p, n, s);
-      case 3: return run<BtdSolveCore<Tp, kD, false, true, true>>(p, n, s);
-      case 4: return run<BtdSolveCore<Tp, kD, true, false, false>>(p, n, s);
-      case 5: return run<BtdSolveCore<Tp, kD, true, false, true>>(p, n, s);
-      case 7: return run<BtdSolveCore<Tp, kD, true, true, true>>(p, n, s);
-      default: return MF_ERR_UNSUPPORTED;  // identity matrix: nothing to sweep
+      case 0: return go(N{}, N{}, N{});
+      case 1: return go(N{}, N{}, Y{});
+      case 3: return go(N{}, Y{}, Y{});
+      case 4: return go(Y{}, N{}, N{});
+      case 5: return go(Y{}, N{}, Y{});
+      case 7: return go(Y{}, Y{}, Y{});
+      default: return (int)MF_ERR_UNSUPPORTED;  // identity matrix: nothing to sweep
     }
   });
 }

@@ -429,3 +429,36 @@ def test_cholesky_parallel_in_time_segments_alias_and_failure():
     bad[1, 250] = -np.eye(d)
     with pytest.raises(CholeskyError, match="chain 1"):
         S(tt(bad), tt(sub)).cholesky
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("transpose_left", [False, True])
+@pytest.mark.parametrize("unit", [False, True])
+@pytest.mark.parametrize("d", [1, 2, 3, 4])
+def test_solve_parallel_in_time(d, unit, transpose_left, dtype):
+    """Few long chains: the triangular solve (an affine recursion) is evaluated parallel in time;
+    equal to the oracle and to the sequential sweep, with leading sample dimensions broadcasting."""
+    from markovflow_b200 import _lib
+
+    L, _ = _mods()
+    lib = _lib.lib()
+    for b, t, seg in ((1, 1500, 0), (2, 301, 0), (3, 400, 7), (2, 131, 65)):
+        _, _, ld, ls = random_well_conditioned_spd_btd((b,), t, d, rng=17 * d + t)
+        if unit:
+            ld = np.broadcast_to(np.eye(d), ld.shape).copy()
+        rhs = np.random.default_rng(t).standard_normal((2, b, t, d))
+        if dtype == torch.float32:
+            ld, ls, rhs = (a.astype(np.float32).astype(np.float64) for a in (ld, ls, rhs))
+        want = O.btd_solve(ld, ls, rhs, transpose_left=transpose_left)
+        got = {}
+        for knob in (0, 1):
+            lib.mf_set_tuning(2, knob)
+            lib.mf_set_tuning(3, seg)
+            try:
+                low = L(tt(ld, dtype), tt(ls, dtype), unit_diagonal=unit)
+                got[knob] = npy(low.solve(tt(rhs, dtype), transpose_left=transpose_left))
+            finally:
+                lib.mf_set_tuning(2, 0)
+                lib.mf_set_tuning(3, 0)
+            assert max_rel_err(got[knob], want) < TOL[dtype]
+        assert max_rel_err(got[0], got[1]) < TOL[dtype]
