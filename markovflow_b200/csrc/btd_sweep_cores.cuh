@@ -255,76 +255,212 @@ struct BtdInvSubsetCore {
 };
 
 // ---------------------------------------------------------------------------------------------
+// U D U^T.  D_k = K_kk - K_{k+1,k}^T D_{k+1}^{-1} K_{k+1,k} is the linear-fractional recursion of
+// ssm_sweep.cuh (naturals -> SSM) without the vector part: elements D_out = P - Q (D_in + R)^{-1} Q^T,
+// extension by a step  P' = K_kk - Ks^T P^{-1} Ks,  Q' = Ks^T P^{-1} Q,  R' = R - Q^T P^{-1} Q.
+// Few long chains: summary pass -> per-chain fold -> seeded sweeps; elements and seeds are parked in
+// the output slots of each segment's FIRST steps (P | seed D -> ocd[k0], R -> ocd[k0+1], Q -> ou[k0]).
 template <typename T>
 struct BtdUduParams {
   const T *diag, *sub;
   T *ou, *ocd;
   int32_t* info;
   int64_t B, Tn;
+  int64_t P, L;
 };
 
 // cholD_{T-1} = chol(K_{T-1,T-1});  U_k^T = D_{k+1}^{-1} K_{k+1,k};  D_k = K_kk - K_{k+1,k}^T U_k^T
-template <typename T_, int D>
+template <typename T_, int D, bool SUMMARY = false>
 struct BtdUduCore {
   using T = T_;
   using Params = BtdUduParams<T>;
   static constexpr int DD = D * D;
-  static constexpr int NIN = 2, NOUT = 2;
+  static constexpr int NIN = 2, NOUT = SUMMARY ? 0 : 2;
   static constexpr bool BACKWARD = true;
   static constexpr int ein(int) { return DD; }
   static constexpr int eout(int) { return DD; }
-  static __device__ __forceinline__ int64_t num_chains(const Params& p) { return p.B; }
-  static __device__ __forceinline__ int64_t max_steps(const Params& p) { return p.Tn; }
-  static __device__ __forceinline__ StreamGeom in_geom(const Params& p, int i, int64_t c) {
-    if (i == 0) return geom_states<T>(p.diag, c, p.Tn, DD);
-    return geom_outgoing<T>(p.sub, c, p.Tn, DD);
+  static __device__ __forceinline__ int64_t num_chains(const Params& p) { return p.B * p.P; }
+  static __device__ __forceinline__ int64_t max_steps(const Params& p) { return p.L; }
+  static __device__ __forceinline__ StreamGeom in_geom(const Params& p, int i, int64_t v) {
+    const int64_t c = v / p.P, seg = v % p.P, k0 = seg * p.L;
+    int64_t n = seg_steps(p.Tn, k0, p.L);
+    if (SUMMARY && seg == 0) n = 0;  // the first segment feeds nobody
+    if (i == 0) return vgeom_states<T>(p.diag, c, p.Tn, DD, k0, n);
+    return vgeom_outgoing<T>(p.sub, c, p.Tn, DD, k0, n);
   }
-  static __device__ __forceinline__ StreamGeom out_geom(const Params& p, int i, int64_t c) {
-    if (i == 0) return geom_outgoing<T>(p.ou, c, p.Tn, DD);
-    return geom_states<T>(p.ocd, c, p.Tn, DD);
+  static __device__ __forceinline__ StreamGeom out_geom(const Params& p, int i, int64_t v) {
+    if (SUMMARY) return StreamGeom{nullptr, 0, 0};
+    const int64_t c = v / p.P, k0 = (v % p.P) * p.L;
+    const int64_t n = seg_steps(p.Tn, k0, p.L);
+    if (i == 0) return vgeom_outgoing<T>(p.ou, c, p.Tn, DD, k0, n);
+    return vgeom_states<T>(p.ocd, c, p.Tn, DD, k0, n);
   }
   T C[DD], rinv[D];
+  T Pm[SUMMARY ? DD : 1], Q[SUMMARY ? DD : 1], R[SUMMARY ? DD : 1];
   int32_t fail;
-  int64_t Tn_;
-  __device__ __forceinline__ void init(const Params& p, int64_t) {
+  int64_t Tn_, k0_, n_;
+  bool live_, have_;  // have_: C holds the factor of the block after the current step
+  __device__ __forceinline__ void init(const Params& p, int64_t v) {
+    const int64_t c = v / p.P;
     Tn_ = p.Tn;
     fail = 0;
+    k0_ = (v % p.P) * p.L;
+    n_ = seg_steps(p.Tn, k0_, p.L);
+    live_ = n_ > 0 && (!SUMMARY || (v % p.P) > 0);
+    have_ = false;
+    if (!SUMMARY && n_ > 0 && k0_ + n_ < p.Tn) {  // seed: the D entering this segment
+      load_vec<T, DD>(C, p.ocd + (c * p.Tn + k0_) * DD);
+      const bool ok = chol_lower<T, D>(C, rinv);
+      if (!ok) fail = (int32_t)(k0_ + n_ + 1);
+      have_ = true;
+    }
   }
   __device__ __forceinline__ void tile(const Params&, const T* const* in, T* const* out, int64_t j0,
                                        int ns) {
+    if (!live_) return;
+    if (n_ - j0 < ns) ns = (int)(n_ - j0);
     for (int j = ns - 1; j >= 0; --j) {
-      const int64_t k = j0 + j;
+      const int64_t k = k0_ + j0 + j;
       T Dk[DD];
       ld_s<T, DD>(Dk, in[0] + j * DD);
       if (k + 1 < Tn_) {
-        T K[DD], X[DD];
+        T K[DD];
         ld_s<T, DD>(K, in[1] + j * DD);
+        if (have_) {
+          T X[DD];
 #pragma unroll
-        for (int i = 0; i < DD; ++i) X[i] = K[i];
-        trsm_left_lower<T, D>(C, rinv, X);
-        trsm_left_lower_t<T, D>(C, rinv, X);  // X = D_{k+1}^{-1} K_{k+1,k}
-        st_s<T, DD>(out[0] + j * DD, X);
+          for (int i = 0; i < DD; ++i) X[i] = K[i];
+          trsm_left_lower<T, D>(C, rinv, X);
+          trsm_left_lower_t<T, D>(C, rinv, X);  // X = D_{k+1}^{-1} K_{k+1,k}
+          if (!SUMMARY) st_s<T, DD>(out[0] + j * DD, X);
+          if (SUMMARY) {
+            // Q' = K^T W, R' = R - Q^T W with W = D_{k+1}^{-1} Q
+            T W[DD], Qn[DD];
 #pragma unroll
-        for (int i = 0; i < D; ++i)
+            for (int i = 0; i < DD; ++i) W[i] = Q[SUMMARY ? i : 0];
+            trsm_left_lower<T, D>(C, rinv, W);
+            trsm_left_lower_t<T, D>(C, rinv, W);
 #pragma unroll
-          for (int q = 0; q <= i; ++q) {
-            T v = Dk[i * D + q];
+            for (int a = 0; a < D; ++a)
 #pragma unroll
-            for (int s = 0; s < D; ++s) v = Num<T>::fma(-K[s * D + i], X[s * D + q], v);
-            Dk[i * D + q] = v;
+              for (int b = 0; b < D; ++b) {
+                T vr = R[SUMMARY ? a * D + b : 0], vq = T(0);
+#pragma unroll
+                for (int s = 0; s < D; ++s) {
+                  vr = Num<T>::fma(-Q[SUMMARY ? s * D + a : 0], W[s * D + b], vr);
+                  vq = Num<T>::fma(K[s * D + a], W[s * D + b], vq);
+                }
+                R[SUMMARY ? a * D + b : 0] = vr;
+                Qn[a * D + b] = vq;
+              }
+#pragma unroll
+            for (int i = 0; i < DD; ++i) Q[SUMMARY ? i : 0] = Qn[i];
           }
+#pragma unroll
+          for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int q = 0; q <= i; ++q) {
+              T v = Dk[i * D + q];
+#pragma unroll
+              for (int s = 0; s < D; ++s) v = Num<T>::fma(-K[s * D + i], X[s * D + q], v);
+              Dk[i * D + q] = v;
+            }
+        } else if (SUMMARY) {
+          // far end of the segment: P = K_kk, Q = K_{k+1,k}^T, R = 0
+#pragma unroll
+          for (int a = 0; a < D; ++a)
+#pragma unroll
+            for (int b = 0; b < D; ++b) {
+              Q[SUMMARY ? a * D + b : 0] = K[b * D + a];
+              R[SUMMARY ? a * D + b : 0] = T(0);
+            }
+        }
+      }
+      if (SUMMARY) {
+#pragma unroll
+        for (int i = 0; i < DD; ++i) Pm[SUMMARY ? i : 0] = Dk[i];
       }
 #pragma unroll
       for (int i = 0; i < DD; ++i) C[i] = Dk[i];
       const bool ok = chol_lower<T, D>(C, rinv);
       if (!ok && fail == 0) fail = (int32_t)(k + 1);
-      zero_upper<T, D>(C);
-      st_s<T, DD>(out[1] + j * DD, C);
+      have_ = true;
+      if (!SUMMARY) {
+        zero_upper<T, D>(C);
+        st_s<T, DD>(out[1] + j * DD, C);
+      }
     }
   }
-  __device__ __forceinline__ void finish(const Params& p, int64_t c, bool valid) {
-    if (valid && p.info) p.info[c] = fail;
+  __device__ __forceinline__ void finish(const Params& p, int64_t v, bool valid) {
+    if (!valid) return;
+    const int64_t c = v / p.P;
+    if (SUMMARY) {
+      if (!live_) return;
+      mirror_lower<T, D>(Pm);
+      store_vec<T, DD>(p.ocd + (c * p.Tn + k0_) * DD, Pm);
+      if (n_ >= 2) store_vec<T, DD>(p.ocd + (c * p.Tn + k0_ + 1) * DD, R);
+      if (k0_ < p.Tn - 1) store_vec<T, DD>(p.ou + (c * (p.Tn - 1) + k0_) * DD, Q);
+      if (fail && p.info) atomicMax(p.info + c, fail);
+      return;
+    }
+    if (!p.info) return;
+    if (p.P == 1) p.info[v] = fail;
+    else if (fail) atomicMax(p.info + c, fail);
   }
 };
+
+// fold of the elements from the last segment down; parks the D entering every segment s < P-1
+template <typename T, int D>
+__global__ void __launch_bounds__(128)
+btd_udu_seed_kernel(const BtdUduParams<T> p) {
+  constexpr int DD = D * D;
+  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= p.B) return;
+  T Din[DD];
+  int32_t fail = 0;
+  for (int64_t seg = p.P - 1; seg >= 0; --seg) {
+    const int64_t k0 = seg * p.L;
+    const int64_t n = seg_steps(p.Tn, k0, p.L);
+    if (n <= 0) continue;
+    const bool last = k0 + n >= p.Tn;
+    T Pm[DD], Q[DD], R[DD];
+    if (seg > 0) {
+      load_vec<T, DD>(Pm, p.ocd + (c * p.Tn + k0) * DD);
+      if (!last) {
+        load_vec<T, DD>(R, p.ocd + (c * p.Tn + k0 + 1) * DD);
+        load_vec<T, DD>(Q, p.ou + (c * (p.Tn - 1) + k0) * DD);
+      }
+    }
+    if (!last) store_vec<T, DD>(p.ocd + (c * p.Tn + k0) * DD, Din);
+    if (seg == 0) break;
+    if (last) {
+#pragma unroll
+      for (int i = 0; i < DD; ++i) Din[i] = Pm[i];
+    } else {
+      T M[DD], rinv[D], Y[DD];
+#pragma unroll
+      for (int i = 0; i < DD; ++i) M[i] = Din[i] + R[i];
+      const bool ok = chol_lower<T, D>(M, rinv);
+      if (!ok && fail == 0) fail = (int32_t)(k0 + n + 1);
+#pragma unroll
+      for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int b = 0; b < D; ++b) Y[a * D + b] = Q[b * D + a];
+      trsm_left_lower<T, D>(M, rinv, Y);
+      trsm_left_lower_t<T, D>(M, rinv, Y);
+#pragma unroll
+      for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int q = 0; q <= r; ++q) {
+          T v = Pm[r * D + q];
+#pragma unroll
+          for (int s = 0; s < D; ++s) v = Num<T>::fma(-Q[r * D + s], Y[s * D + q], v);
+          Din[r * D + q] = v;
+          Din[q * D + r] = v;
+        }
+    }
+  }
+  if (fail && p.info) atomicMax(p.info + c, fail);
+}
 
 }  // namespace mf

@@ -109,8 +109,17 @@ int btd_sweep_udu(int dtype, int64_t D, const void* diag, const void* sub, void*
   return dispatch_btd_sweep(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
-    BtdUduParams<Tp> p{(const Tp*)diag, (const Tp*)sub, (Tp*)ou, (Tp*)ocd, info, B, T};
-    return run<BtdUduCore<Tp, kD>>(p, B, s);
+    BtdUduParams<Tp> p{(const Tp*)diag, (const Tp*)sub, (Tp*)ou, (Tp*)ocd, info, B, T, 1, T};
+    if (tuning(2) != 1 && T >= 128 && ocd != diag && ou != sub) plan_pit(B, T, 2, &p.P, &p.L);
+    if (p.P > 1) {
+      if (info && cudaMemsetAsync(info, 0, sizeof(int32_t) * B, s) != cudaSuccess) return check_launch();
+      int rc = run<BtdUduCore<Tp, kD, true>>(p, B * p.P, s);
+      if (rc != MF_OK) return rc;
+      btd_udu_seed_kernel<Tp, kD><<<grid_for(B, 128), 128, 0, s>>>(p);
+      rc = check_launch();
+      if (rc != MF_OK) return rc;
+    }
+    return run<BtdUduCore<Tp, kD, false>>(p, B * p.P, s);
   });
 }
 

@@ -462,3 +462,37 @@ def test_solve_parallel_in_time(d, unit, transpose_left, dtype):
                 lib.mf_set_tuning(3, 0)
             assert max_rel_err(got[knob], want) < TOL[dtype]
         assert max_rel_err(got[0], got[1]) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("d", [1, 2, 3, 4])
+def test_upper_diagonal_lower_parallel_in_time(d, dtype):
+    """Few long chains: U D U^T through the linear-fractional segment elements; equal to the oracle
+    and to the sequential sweep; a non-positive-definite block still raises."""
+    from markovflow_b200 import CholeskyError, _lib
+
+    _, S = _mods()
+    lib = _lib.lib()
+    for b, t, seg in ((1, 1500, 0), (2, 301, 0), (3, 400, 7), (2, 131, 65), (2, 129, 2)):
+        diag, sub, _, _ = random_well_conditioned_spd_btd((b,), t, d, rng=23 * d + t)
+        if dtype == torch.float32:
+            diag, sub = (a.astype(np.float32).astype(np.float64) for a in (diag, sub))
+        o_u, o_cd = O.btd_upper_diagonal_lower(diag, sub)
+        got = {}
+        for knob in (0, 1):
+            lib.mf_set_tuning(2, knob)
+            lib.mf_set_tuning(3, seg)
+            try:
+                lower_m, diag_m = S(tt(diag, dtype), tt(sub, dtype)).upper_diagonal_lower()
+            finally:
+                lib.mf_set_tuning(2, 0)
+                lib.mf_set_tuning(3, 0)
+            got[knob] = (npy(lower_m.block_sub_diagonal), npy(diag_m.block_diagonal))
+            assert max_rel_err(got[knob][0], o_u) < TOL[dtype]
+            assert max_rel_err(got[knob][1], o_cd) < TOL[dtype]
+            assert float(torch.triu(diag_m.block_diagonal, 1).abs().max()) == 0.0
+        assert max_rel_err(got[0][0], got[1][0]) < TOL[dtype]
+    diag, sub, _, _ = random_well_conditioned_spd_btd((2,), 500, d, rng=3)
+    diag[1, 333] = -np.eye(d)
+    with pytest.raises(CholeskyError, match="chain 1"):
+        S(tt(diag), tt(sub)).upper_diagonal_lower()
