@@ -1,5 +1,7 @@
 // TMA-sweep implementations of the sequential StateSpaceModel / natural-parameter recurrences
 // (ssm_sweep.cuh); called from capi_ssm.cu and capi_nat.cu through ssm_sweep_api.h.
+#include <type_traits>
+
 #include "dispatch.cuh"
 #include "ssm_sweep.cuh"
 #include "ssm_sweep_api.h"
@@ -81,9 +83,28 @@ int ssm_sweep_affine(int dtype, int64_t D, const void* mu0, const void* chol_p0,
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
     SsmAffineParams<Tp> p{(const Tp*)mu0, (const Tp*)chol_p0, (const Tp*)a, (const Tp*)b,
-                          (const Tp*)chol_q, (const Tp*)eps, (Tp*)out, n, Bm, T};
-    if (eps) return run<SsmAffineCore<Tp, kD, true>>(p, n, s);
-    return run<SsmAffineCore<Tp, kD, false>>(p, n, s);
+                          (const Tp*)chol_q, (const Tp*)eps, (Tp*)out, n, Bm, T, 1, T};
+    if (tuning(2) != 1 && T >= 128 && out != eps) {
+      plan_segments(n, T, &p.P, &p.L);
+      if (p.P > 512) {  // the seeds are folded sequentially per chain
+        p.L = (T + 511) / 512;
+        p.P = (T + p.L - 1) / p.L;
+      }
+      if (p.L < kD + 2) { p.P = 1; p.L = T; }
+    }
+    auto go = [&](auto noise) -> int {
+      constexpr bool kN = decltype(noise)::value;
+      if (p.P > 1) {
+        int rc = run<SsmAffineCore<Tp, kD, kN, true>>(p, n * p.P, s);
+        if (rc != MF_OK) return rc;
+        ssm_affine_seed_kernel<Tp, kD><<<grid_for(n, 128), 128, 0, s>>>(p);
+        rc = check_launch();
+        if (rc != MF_OK) return rc;
+      }
+      return run<SsmAffineCore<Tp, kD, kN, false>>(p, n * p.P, s);
+    };
+    if (eps) return go(std::true_type{});
+    return go(std::false_type{});
   });
 }
 

@@ -397,41 +397,73 @@ ssm_moments_seed_kernel(const SsmMomentsParams<T> p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// x_k = A_k x_{k-1} + b_k (+ chol_q eps): affine in x, so few long chains run parallel in time: the
+// SUMMARY pass composes every segment into (Phi, c) by running the recursion on c and on the columns
+// of Phi, ssm_affine_seed_kernel folds them per chain, and the segments restart from their seeds.
+// The D+1 vectors of an element / the seed are parked in the segment's LAST output steps.
 template <typename T>
 struct SsmAffineParams {
   const T *mu0, *chol_p0, *a, *b, *chol_q, *eps;
   T* out;
   int64_t n, Bm, Tn;
+  int64_t P, L;
 };
 
-template <typename T_, int D, bool NOISE>
+template <typename T_, int D, bool NOISE, bool SUMMARY = false>
 struct SsmAffineCore {
   using T = T_;
   using Params = SsmAffineParams<T>;
   static constexpr int DD = D * D;
-  static constexpr int NIN = NOISE ? 4 : 2, NOUT = 1;
+  static constexpr int NIN = NOISE ? 4 : 2, NOUT = SUMMARY ? 0 : 1;
   static constexpr bool BACKWARD = false;
   static constexpr int ein(int i) { return (i == 0 || i == 2) ? DD : D; }
   static constexpr int eout(int) { return D; }
-  static __device__ __forceinline__ int64_t num_chains(const Params& p) { return p.n; }
-  static __device__ __forceinline__ int64_t max_steps(const Params& p) { return p.Tn; }
-  static __device__ __forceinline__ StreamGeom in_geom(const Params& p, int i, int64_t c) {
-    if (i == 3) return geom_states<T>(p.eps, c, p.Tn, D);
-    return geom_incoming<T>(i == 0 ? p.a : (i == 1 ? p.b : p.chol_q), c % p.Bm, p.Tn, ein(i));
+  static __device__ __forceinline__ int64_t num_chains(const Params& p) { return p.n * p.P; }
+  static __device__ __forceinline__ int64_t max_steps(const Params& p) { return p.L; }
+  static __device__ __forceinline__ bool is_live(const Params& p, int64_t v) {
+    return ((v % p.P) + 1) * p.L < p.Tn;  // complete segment with a successor
   }
-  static __device__ __forceinline__ StreamGeom out_geom(const Params& p, int, int64_t c) {
-    return geom_states<T>(p.out, c, p.Tn, D);
+  static __device__ __forceinline__ StreamGeom in_geom(const Params& p, int i, int64_t v) {
+    const int64_t c = v / p.P, k0 = (v % p.P) * p.L;
+    int64_t n = seg_steps(p.Tn, k0, p.L);
+    if (SUMMARY && !is_live(p, v)) n = 0;
+    if (i == 3) return vgeom_states<T>(p.eps, c, p.Tn, D, k0, n);
+    return vgeom_incoming<T>(i == 0 ? p.a : (i == 1 ? p.b : p.chol_q), c % p.Bm, p.Tn, ein(i), k0, n);
+  }
+  static __device__ __forceinline__ StreamGeom out_geom(const Params& p, int, int64_t v) {
+    if (SUMMARY) return StreamGeom{nullptr, 0, 0};
+    const int64_t c = v / p.P, k0 = (v % p.P) * p.L;
+    return vgeom_states<T>(p.out, c, p.Tn, D, k0, seg_steps(p.Tn, k0, p.L));
   }
   T x[D];
-  int64_t cm;
-  __device__ __forceinline__ void init(const Params& p, int64_t c) {
+  T Phi[SUMMARY ? DD : 1];  // column q at Phi[q * D ..]
+  int64_t cm, k0_, n_;
+  bool live_;
+  __device__ __forceinline__ void init(const Params& p, int64_t v) {
+    const int64_t c = v / p.P;
     cm = c % p.Bm;
-    load_vec<T, D>(x, p.mu0 + cm * D);
+    k0_ = (v % p.P) * p.L;
+    n_ = seg_steps(p.Tn, k0_, p.L);
+    live_ = !SUMMARY || is_live(p, v);
+    if (SUMMARY) {
+#pragma unroll
+      for (int i = 0; i < DD; ++i) Phi[SUMMARY ? i : 0] = (i / D == i % D) ? T(1) : T(0);
+    }
+    if (k0_ == 0) {
+      load_vec<T, D>(x, p.mu0 + cm * D);
+    } else if (SUMMARY) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) x[i] = T(0);
+    } else if (n_ > 0) {
+      load_vec<T, D>(x, p.out + (c * p.Tn + k0_ + n_ - 1) * D);  // seed: x_{k0-1}
+    }
   }
   __device__ __forceinline__ void tile(const Params& p, const T* const* in, T* const* out,
                                        int64_t j0, int ns) {
+    if (!live_) return;
+    if (n_ - j0 < ns) ns = (int)(n_ - j0);
     for (int j = 0; j < ns; ++j) {
-      if (j0 + j > 0) {
+      if (k0_ + j0 + j > 0) {
         T A[DD], off[D];
         ld_s<T, DD>(A, in[0] + j * DD);
         ld_s<T, D>(off, in[1] + j * D);
@@ -445,18 +477,82 @@ struct SsmAffineCore {
         gemv_add<T, D>(off, A, x);
 #pragma unroll
         for (int r = 0; r < D; ++r) x[r] = off[r];
-      } else if (NOISE) {
-        T L[DD], e[D];
-        load_vec<T, DD>(L, p.chol_p0 + cm * DD);
-        zero_upper<T, D>(L);
-        ld_s<T, D>(e, in[3] + j * D);
-        gemv_add<T, D>(x, L, e);
+        if (SUMMARY) {
+          T t[DD];
+          // columns of Phi <- A (columns of Phi): Phi is stored column by column, i.e. as Phi^T
+#pragma unroll
+          for (int q = 0; q < D; ++q)
+#pragma unroll
+            for (int r = 0; r < D; ++r) {
+              T v = T(0);
+#pragma unroll
+              for (int s2 = 0; s2 < D; ++s2) v = Num<T>::fma(A[r * D + s2], Phi[SUMMARY ? q * D + s2 : 0], v);
+              t[q * D + r] = v;
+            }
+#pragma unroll
+          for (int i = 0; i < DD; ++i) Phi[SUMMARY ? i : 0] = t[i];
+        }
+      } else {
+        if (NOISE) {
+          T L[DD], e[D];
+          load_vec<T, DD>(L, p.chol_p0 + cm * DD);
+          zero_upper<T, D>(L);
+          ld_s<T, D>(e, in[3] + j * D);
+          gemv_add<T, D>(x, L, e);
+        }
       }
-      st_s<T, D>(out[0] + j * D, x);
+      if (!SUMMARY) st_s<T, D>(out[0] + j * D, x);
     }
   }
-  __device__ __forceinline__ void finish(const Params&, int64_t, bool) {}
+  __device__ __forceinline__ void finish(const Params& p, int64_t v, bool valid) {
+    if (!SUMMARY || !valid || !live_) return;
+    const int64_t c = v / p.P;
+    const int64_t kl = k0_ + n_ - 1;
+    store_vec<T, D>(p.out + (c * p.Tn + kl) * D, x);
+#pragma unroll
+    for (int q = 0; q < D; ++q)
+      store_vec<T, D>(p.out + (c * p.Tn + kl - 1 - q) * D, Phi + (SUMMARY ? q * D : 0));
+  }
 };
+
+// fold of the segment elements of one chain; parks x_{k0-1} in the seed slot of every segment s >= 1.
+// Segment 0 starts from mu0 (+ noise), so its element already is the state at its end: Phi unused.
+template <typename T, int D>
+__global__ void __launch_bounds__(128)
+ssm_affine_seed_kernel(const SsmAffineParams<T> p) {
+  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= p.n) return;
+  T x[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) x[i] = T(0);
+  for (int64_t seg = 0; seg < p.P; ++seg) {
+    const int64_t k0 = seg * p.L;
+    const int64_t n = seg_steps(p.Tn, k0, p.L);
+    if (n <= 0) break;
+    const int64_t kl = k0 + n - 1;
+    const bool live = (seg + 1) * p.L < p.Tn;
+    T cv[D], Phi[D * D];
+    if (live) {
+      load_vec<T, D>(cv, p.out + (c * p.Tn + kl) * D);
+#pragma unroll
+      for (int q = 0; q < D; ++q) load_vec<T, D>(Phi + q * D, p.out + (c * p.Tn + kl - 1 - q) * D);
+    }
+    if (seg > 0) store_vec<T, D>(p.out + (c * p.Tn + kl) * D, x);
+    if (!live) break;
+    T y[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      T v = cv[i];
+      if (seg > 0) {
+#pragma unroll
+        for (int q = 0; q < D; ++q) v = Num<T>::fma(Phi[q * D + i], x[q], v);
+      }
+      y[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) x[i] = y[i];
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 template <typename T>

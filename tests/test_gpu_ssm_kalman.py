@@ -442,3 +442,39 @@ def test_marginals_parallel_in_time_segment_length_knob():
                 lib.mf_set_tuning(3, 0)
             assert max_rel_err(npy(mean), want_mu) < 1e-10 and max_rel_err(npy(cov), want_p) < 1e-10
             assert max_rel_err(npy(sub), want_sub) < 1e-10
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("d", [1, 2, 3, 4])
+def test_means_and_samples_parallel_in_time(d, dtype):
+    """Few long chains: x_k = A_k x_{k-1} + b_k (+ chol_q eps) is evaluated parallel in time
+    (marginal_means, sample_from_epsilons with leading sample dimensions); equal to the oracle and to
+    the sequential sweep."""
+    from markovflow_b200 import _lib
+
+    lib = _lib.lib()
+    for b, t, seg in ((1, 1500, 0), (2, 301, 0), (3, 400, 9), (2, 131, 65)):
+        state = np.random.get_state()
+        np.random.seed(t * 10 + d)
+        arrays = random_ssm_arrays((b,), t - 1, d, scale_a=0.6 / np.sqrt(d))
+        eps = np.random.normal(size=(2, b, t, d))
+        np.random.set_state(state)
+        if dtype == torch.float32:
+            arrays = tuple(a.astype(np.float32).astype(np.float64) for a in arrays)
+            eps = eps.astype(np.float32).astype(np.float64)
+        ref = O.SSM(*arrays)
+        want_mean = O.ssm_marginal_means(ref)
+        want_s = O.ssm_sample_from_epsilons(ref, eps)
+        got = {}
+        for knob in (0, 1):
+            lib.mf_set_tuning(2, knob)
+            lib.mf_set_tuning(3, seg)
+            try:
+                ssm = make_ssm(arrays, dtype)
+                got[knob] = (npy(ssm.marginal_means), npy(ssm.sample_from_epsilons(tt(eps, dtype))))
+            finally:
+                lib.mf_set_tuning(2, 0)
+                lib.mf_set_tuning(3, 0)
+            assert max_rel_err(got[knob][0], want_mean) < TOL[dtype]
+            assert max_rel_err(got[knob][1], want_s) < TOL[dtype]
+        assert max_rel_err(got[0][1], got[1][1]) < TOL[dtype]
