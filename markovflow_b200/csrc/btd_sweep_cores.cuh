@@ -183,45 +183,71 @@ btd_solve_seed_kernel(const BtdSolveParams<T> p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Sparse inverse subset.  Sigma_kk = G_k + J_k^T Sigma_{k+1,k+1} J_k is affine in Sigma, so few long
+// chains run parallel in time: elements (Phi, Gt) with Sigma_out = Phi^T Sigma_in Phi + Gt
+// (Phi <- Phi J_k, Gt <- J_k^T Gt J_k + G_k going down), per-chain fold, seeded sweeps.  Elements and
+// seeds are parked in the output slots of each segment's FIRST steps (Gt | seed -> od[k0],
+// Phi -> od[k0+1]).
 template <typename T>
 struct BtdInvSubsetParams {
   const T *ld, *ls;
   T *od, *os;
   int64_t B, Tn;
+  int64_t P, L;
 };
 
 // Sigma_{T-1,T-1} = (Ld Ld^T)^{-1};  J_k = Ls_k Ld_k^{-1};  Sigma_{k+1,k} = -Sigma_{k+1,k+1} J_k;
 // Sigma_kk = (Ld_k Ld_k^T)^{-1} - J_k^T Sigma_{k+1,k}
-template <typename T_, int D, bool WANT_SUB>
+template <typename T_, int D, bool WANT_SUB, bool SUMMARY = false>
 struct BtdInvSubsetCore {
   using T = T_;
   using Params = BtdInvSubsetParams<T>;
   static constexpr int DD = D * D;
-  static constexpr int NIN = 2, NOUT = WANT_SUB ? 2 : 1;
+  static constexpr int NIN = 2, NOUT = SUMMARY ? 0 : (WANT_SUB ? 2 : 1);
   static constexpr bool BACKWARD = true;
   static constexpr int ein(int) { return DD; }
   static constexpr int eout(int) { return DD; }
-  static __device__ __forceinline__ int64_t num_chains(const Params& p) { return p.B; }
-  static __device__ __forceinline__ int64_t max_steps(const Params& p) { return p.Tn; }
-  static __device__ __forceinline__ StreamGeom in_geom(const Params& p, int i, int64_t c) {
-    if (i == 0) return geom_states<T>(p.ld, c, p.Tn, DD);
-    return geom_outgoing<T>(p.ls, c, p.Tn, DD);
+  static __device__ __forceinline__ int64_t num_chains(const Params& p) { return p.B * p.P; }
+  static __device__ __forceinline__ int64_t max_steps(const Params& p) { return p.L; }
+  static __device__ __forceinline__ StreamGeom in_geom(const Params& p, int i, int64_t v) {
+    const int64_t c = v / p.P, seg = v % p.P, k0 = seg * p.L;
+    int64_t n = seg_steps(p.Tn, k0, p.L);
+    if (SUMMARY && seg == 0) n = 0;  // the first segment feeds nobody
+    if (i == 0) return vgeom_states<T>(p.ld, c, p.Tn, DD, k0, n);
+    return vgeom_outgoing<T>(p.ls, c, p.Tn, DD, k0, n);
   }
-  static __device__ __forceinline__ StreamGeom out_geom(const Params& p, int i, int64_t c) {
-    if (i == 0) return geom_states<T>(p.od, c, p.Tn, DD);
-    return geom_outgoing<T>(p.os, c, p.Tn, DD);
+  static __device__ __forceinline__ StreamGeom out_geom(const Params& p, int i, int64_t v) {
+    if (SUMMARY) return StreamGeom{nullptr, 0, 0};
+    const int64_t c = v / p.P, k0 = (v % p.P) * p.L;
+    const int64_t n = seg_steps(p.Tn, k0, p.L);
+    if (i == 0) return vgeom_states<T>(p.od, c, p.Tn, DD, k0, n);
+    return vgeom_outgoing<T>(p.os, c, p.Tn, DD, k0, n);
   }
-  T sig[DD];
-  int64_t Tn_;
-  __device__ __forceinline__ void init(const Params& p, int64_t) {
+  T sig[DD];                 // Sigma of the step after the current one | Gt in the summary pass
+  T Phi[SUMMARY ? DD : 1];
+  int64_t Tn_, k0_, n_;
+  bool live_;
+  __device__ __forceinline__ void init(const Params& p, int64_t v) {
+    const int64_t c = v / p.P;
     Tn_ = p.Tn;
+    k0_ = (v % p.P) * p.L;
+    n_ = seg_steps(p.Tn, k0_, p.L);
+    live_ = n_ > 0 && (!SUMMARY || (v % p.P) > 0);
 #pragma unroll
     for (int i = 0; i < DD; ++i) sig[i] = T(0);
+    if (SUMMARY) {
+#pragma unroll
+      for (int i = 0; i < DD; ++i) Phi[SUMMARY ? i : 0] = (i / D == i % D) ? T(1) : T(0);
+    } else if (n_ > 0 && k0_ + n_ < p.Tn) {
+      load_vec<T, DD>(sig, p.od + (c * p.Tn + k0_) * DD);  // seed: Sigma entering the segment
+    }
   }
   __device__ __forceinline__ void tile(const Params&, const T* const* in, T* const* out, int64_t j0,
                                        int ns) {
+    if (!live_) return;
+    if (n_ - j0 < ns) ns = (int)(n_ - j0);
     for (int j = ns - 1; j >= 0; --j) {
-      const int64_t k = j0 + j;
+      const int64_t k = k0_ + j0 + j;
       T L[DD], loc[DD], rinv[D];
       ld_s<T, DD>(L, in[0] + j * DD);
 #pragma unroll
@@ -231,10 +257,10 @@ struct BtdInvSubsetCore {
         T J[DD], ssub[DD];
         ld_s<T, DD>(J, in[1] + j * DD);
         trsm_right_lower<T, D>(J, L, rinv);  // J = Ls Ld^{-1}
-        gemm<T, D>(ssub, sig, J);            // Sigma_{k+1,k+1} J
+        gemm<T, D>(ssub, sig, J);            // Sigma_{k+1,k+1} J   (summary: Gt J)
 #pragma unroll
         for (int i = 0; i < DD; ++i) ssub[i] = -ssub[i];
-        if (WANT_SUB) st_s<T, DD>(out[WANT_SUB ? 1 : 0] + j * DD, ssub);
+        if (!SUMMARY && WANT_SUB) st_s<T, DD>(out[WANT_SUB ? 1 : 0] + j * DD, ssub);
 #pragma unroll
         for (int i = 0; i < D; ++i)
 #pragma unroll
@@ -245,14 +271,71 @@ struct BtdInvSubsetCore {
             loc[i * D + q] = v;
           }
         mirror_lower<T, D>(loc);
+        if (SUMMARY) {
+          T t[DD];
+          gemm<T, D>(t, Phi, J);
+#pragma unroll
+          for (int i = 0; i < DD; ++i) Phi[SUMMARY ? i : 0] = t[i];
+        }
+      } else if (SUMMARY) {
+        // k = T-1: Sigma = G, nothing enters: the element is (0, G)
+#pragma unroll
+        for (int i = 0; i < DD; ++i) Phi[SUMMARY ? i : 0] = T(0);
       }
-      st_s<T, DD>(out[0] + j * DD, loc);
+      if (!SUMMARY) st_s<T, DD>(out[0] + j * DD, loc);
 #pragma unroll
       for (int i = 0; i < DD; ++i) sig[i] = loc[i];
     }
   }
-  __device__ __forceinline__ void finish(const Params&, int64_t, bool) {}
+  __device__ __forceinline__ void finish(const Params& p, int64_t v, bool valid) {
+    if (!SUMMARY || !valid || !live_) return;
+    const int64_t c = v / p.P;
+    store_vec<T, DD>(p.od + (c * p.Tn + k0_) * DD, sig);
+    if (n_ >= 2) store_vec<T, DD>(p.od + (c * p.Tn + k0_ + 1) * DD, Phi);
+  }
 };
+
+// fold from the last segment down; parks the Sigma entering every segment s < P-1 in od[k0]
+template <typename T, int D>
+__global__ void __launch_bounds__(128)
+btd_inv_subset_seed_kernel(const BtdInvSubsetParams<T> p) {
+  constexpr int DD = D * D;
+  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= p.B) return;
+  T sig[DD];
+#pragma unroll
+  for (int i = 0; i < DD; ++i) sig[i] = T(0);
+  for (int64_t seg = p.P - 1; seg >= 0; --seg) {
+    const int64_t k0 = seg * p.L;
+    const int64_t n = seg_steps(p.Tn, k0, p.L);
+    if (n <= 0) continue;
+    const bool last = k0 + n >= p.Tn;
+    T Gt[DD], Phi[DD];
+    if (seg > 0) {
+      load_vec<T, DD>(Gt, p.od + (c * p.Tn + k0) * DD);
+      if (!last) load_vec<T, DD>(Phi, p.od + (c * p.Tn + k0 + 1) * DD);
+    }
+    if (!last) store_vec<T, DD>(p.od + (c * p.Tn + k0) * DD, sig);
+    if (seg == 0) break;
+    if (last) {
+#pragma unroll
+      for (int i = 0; i < DD; ++i) sig[i] = Gt[i];
+    } else {
+      T SP[DD];
+      gemm<T, D>(SP, sig, Phi);  // Sigma Phi
+#pragma unroll
+      for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int q = 0; q <= r; ++q) {
+          T v = Gt[r * D + q];
+#pragma unroll
+          for (int s = 0; s < D; ++s) v = Num<T>::fma(Phi[s * D + r], SP[s * D + q], v);
+          sig[r * D + q] = v;
+          sig[q * D + r] = v;
+        }
+    }
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // U D U^T.  D_k = K_kk - K_{k+1,k}^T D_{k+1}^{-1} K_{k+1,k} is the linear-fractional recursion of

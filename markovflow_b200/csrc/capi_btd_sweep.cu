@@ -98,9 +98,17 @@ int btd_sweep_inverse_subset(int dtype, int64_t D, const void* ld, const void* l
   return dispatch_btd_sweep(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
-    BtdInvSubsetParams<Tp> p{(const Tp*)ld, (const Tp*)ls, (Tp*)od, (Tp*)os, B, T};
-    if (os) return run<BtdInvSubsetCore<Tp, kD, true>>(p, B, s);
-    return run<BtdInvSubsetCore<Tp, kD, false>>(p, B, s);
+    BtdInvSubsetParams<Tp> p{(const Tp*)ld, (const Tp*)ls, (Tp*)od, (Tp*)os, B, T, 1, T};
+    if (tuning(2) != 1 && T >= 128 && od != ld) plan_pit(B, T, 2, &p.P, &p.L);
+    if (p.P > 1) {
+      int rc = run<BtdInvSubsetCore<Tp, kD, false, true>>(p, B * p.P, s);
+      if (rc != MF_OK) return rc;
+      btd_inv_subset_seed_kernel<Tp, kD><<<grid_for(B, 128), 128, 0, s>>>(p);
+      rc = check_launch();
+      if (rc != MF_OK) return rc;
+    }
+    if (os) return run<BtdInvSubsetCore<Tp, kD, true, false>>(p, B * p.P, s);
+    return run<BtdInvSubsetCore<Tp, kD, false, false>>(p, B * p.P, s);
   });
 }
 

@@ -496,3 +496,35 @@ def test_upper_diagonal_lower_parallel_in_time(d, dtype):
     diag[1, 333] = -np.eye(d)
     with pytest.raises(CholeskyError, match="chain 1"):
         S(tt(diag), tt(sub)).upper_diagonal_lower()
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("d", [1, 2, 3, 4])
+def test_inverse_subset_parallel_in_time(d, dtype):
+    """Few long chains: the sparse inverse subset (affine in Sigma) evaluated parallel in time; equal
+    to the oracle and to the sequential sweep, with and without the sub-diagonal blocks."""
+    from markovflow_b200 import _lib
+
+    L, _ = _mods()
+    lib = _lib.lib()
+    for b, t, seg in ((1, 1500, 0), (2, 301, 0), (3, 400, 7), (2, 131, 65), (2, 129, 2)):
+        _, _, ld, ls = random_well_conditioned_spd_btd((b,), t, d, rng=29 * d + t)
+        if dtype == torch.float32:
+            ld, ls = (a.astype(np.float32).astype(np.float64) for a in (ld, ls))
+        o_d, o_s = O.btd_inverse_subset(ld, ls, want_sub=True)
+        got = {}
+        for knob in (0, 1):
+            lib.mf_set_tuning(2, knob)
+            lib.mf_set_tuning(3, seg)
+            try:
+                low = L(tt(ld, dtype), tt(ls, dtype))
+                gd, gs = low._inverse_subset(True)
+                only_d = low.block_diagonal_of_inverse()
+            finally:
+                lib.mf_set_tuning(2, 0)
+                lib.mf_set_tuning(3, 0)
+            got[knob] = (npy(gd), npy(gs))
+            assert max_rel_err(got[knob][0], o_d) < TOL[dtype]
+            assert max_rel_err(got[knob][1], o_s) < TOL[dtype]
+            assert max_rel_err(npy(only_d), o_d) < TOL[dtype]
+        assert max_rel_err(got[0][0], got[1][0]) < TOL[dtype]
