@@ -81,7 +81,7 @@ struct BtdSolveCore {
     if (SUMMARY) {
 #pragma unroll
       for (int i = 0; i < DD; ++i) Phi[SUMMARY ? i : 0] = (i / D == i % D) ? T(1) : T(0);
-    } else if (n_ > 0 && (TRANSPOSE ? k0_ + n_ < p.Tn : k0_ > 0)) {
+    } else if (SUB && n_ > 0 && (TRANSPOSE ? k0_ + n_ < p.Tn : k0_ > 0)) {
       load_vec<T, D>(x, p.out + (c * p.Tn + solve_slot<TRANSPOSE>(k0_, n_, 0)) * D);  // seed
     }
   }

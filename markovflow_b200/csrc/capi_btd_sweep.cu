@@ -65,11 +65,12 @@ int btd_sweep_solve(int dtype, int64_t D, const void* ld, const void* ls, const 
     BtdSolveParams<Tp> p{(const Tp*)ld, (const Tp*)ls, (const Tp*)rhs, (Tp*)out, n, Bm, T, 1, T};
     // few long chains with a recursion (sub-diagonal): parallel in time; the output slots serve as
     // scratch, so not when out aliases rhs
-    if (ls && tuning(2) != 1 && out != rhs && T >= 128) plan_pit(n, T, kD + 2, &p.P, &p.L);
+    // (block-diagonal matrices have no recursion at all: their segments are simply independent)
+    if (tuning(2) != 1 && T >= 128 && (!ls || out != rhs)) plan_pit(n, T, kD + 2, &p.P, &p.L);
     const int v = (transpose ? 4 : 0) | (ld ? 0 : 2) | (ls ? 1 : 0);
     auto go = [&](auto tr, auto unit, auto sub) -> int {
       constexpr bool kT = decltype(tr)::value, kU = decltype(unit)::value, kS = decltype(sub)::value;
-      if (p.P > 1) {
+      if (p.P > 1 && kS) {
         int rc = run<BtdSolveCore<Tp, kD, kT, kU, kS, true>>(p, n * p.P, s);
         if (rc != MF_OK) return rc;
         btd_solve_seed_kernel<Tp, kD, kT><<<grid_for(n, 128), 128, 0, s>>>(p);

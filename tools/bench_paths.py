@@ -122,6 +122,29 @@ def fewchains():
         torch.cuda.empty_cache()
 
 
+def gpr1():
+    """BASELINE config 1 scaled up: ONE Matern32 series, KalmanFilter log-likelihood + posterior SSM +
+    posterior marginals (kalman_filter.py:109-255); parallel in time vs sequential sweeps."""
+    lib = _lib.lib()
+    for t in (1_000, 100_000, 1_000_000):
+        ssm, h, y, lr = bench_inputs.kalman_inputs_config3(t, DEV)
+        kf = mf.KalmanFilter(ssm, mf.EmissionModel(h), y, lr)
+
+        def job():
+            ll = kf.log_likelihood()
+            post = kf.posterior_state_space_model()
+            return ll, post.marginals
+
+        for knob, label in ((0, "parallel in time"), (1, "sequential sweeps")):
+            lib.mf_set_tuning(2, knob)
+            ms = timeit(job, warm=2, reps=5)
+            report(f"GPR single series T={t} D=2 f64: log-lik + posterior SSM + marginals [{label}]", t,
+                   (2 * 4 + 2 + 2 + 1 + 3 * 4 + 2 * 2) * 8, ms)
+        lib.mf_set_tuning(2, 0)
+        del ssm, h, y, kf
+        torch.cuda.empty_cache()
+
+
 def config4(b=256, t=10_000):
     """Config 4 at reduced T (the full T=1e5 needs 118 GB of inputs: in-place, 8 GPUs or B-chunks)."""
     diag, sub, rhs = bench_inputs.sum_kernel_posterior_precision(b, t, DEV)
