@@ -214,6 +214,23 @@ def extra_measurements(dev, rank, world, dist, peak):
     if rank != 0:
         return out
 
+    # ---- config 1: ONE Matern32 series, log-likelihood + posterior SSM + posterior marginals --------
+    for t1 in (1_000, 1_000_000):
+        ssm1, h1, y1, lr1 = bench_inputs.kalman_inputs_config3(t1, dev)
+        kf = mf.KalmanFilter(ssm1, mf.EmissionModel(h1), y1, lr1)
+
+        def gpr_job():
+            post = kf.posterior_state_space_model()
+            return kf.log_likelihood(), post.marginals
+
+        ms = _timed(gpr_job, warm=2, reps=5)
+        out[f"config1_gpr_single_series_T{t1}"] = {
+            "ms": ms, "state_steps_per_s": t1 / (ms * 1e-3),
+            "workload": f"Matern32 D=2, ONE series T={t1}, f64: KalmanFilter.log_likelihood + "
+                        "posterior_state_space_model + posterior marginals; every sweep parallel in time"}
+        del ssm1, h1, y1, kf
+    torch.cuda.empty_cache()
+
     # ---- config 5: CVI site update, B = 1024 chains x M = 1e4 inducing states, D = 2 ---------------
     b5, t5 = 1024, 10_000
     th64 = bench_inputs.cvi_naturals_config5(b5, t5, dev, dtype=torch.float64)
