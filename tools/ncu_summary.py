@@ -61,7 +61,11 @@ def launches(path, title):
 def stalls(rep, title):
     rows = ncu_csv(rep, "source")
     hdr = next(r for r in rows if "Source" in r and "# Samples" in r)
-    data = rows[rows.index(hdr) + 1:]
+    data = []  # first kernel of the report only
+    for r in rows[rows.index(hdr) + 1:]:
+        if len(r) != len(hdr) or r == hdr:
+            break
+        data.append(r)
     ci = {h: i for i, h in enumerate(hdr)}
     cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
     tot = sum(int(r[ci["# Samples"]]) for r in data)
