@@ -38,7 +38,10 @@ struct CholTmaCfg {
   static constexpr int NJ = NSTREAM * C;          // (stream, chain) jobs per direction
   static constexpr int LPW = 32;                  // producer lanes used per warp
   static constexpr int NPW = (2 * NJ + LPW - 1) / LPW;  // producer warps: NJ loaders + NJ storers
-  static constexpr int THREADS = 32 * (1 + NPW);
+  // warp w runs on SM sub-partition w % 4: warp 4 would share sub-partition 0 with the compute warp
+  // (warp 0) and steal its issue slots with the UBLKCP loops, so it is left idle when NPW > 3
+  static constexpr int SKIP = NPW > 3 ? 1 : 0;
+  static constexpr int THREADS = 32 * (1 + NPW + SKIP);
   static constexpr size_t SMEM_BYTES =
       (size_t)STAGE_BYTES * (NSI + NSO) + sizeof(uint64_t) * (NSI + 2 * NSO) + 16;
   static constexpr bool ALIGN_OK = (SEG_M % 16 == 0) && (SEG_V % 16 == 0);
@@ -145,7 +148,8 @@ btd_chol_tma_kernel(const T* __restrict__ diag, const T* __restrict__ sub,
   if (warp >= 1) {
     // ---- producer threads: one per (direction, stream, chain) job; each issues ONE bulk copy
     //      per tile, so the per-lane UBLKCP issue cost is spread over NPW warps ----------------
-    const int p = (warp - 1) * Cfg::LPW + lane;
+    if (Cfg::SKIP && warp == 4) return;
+    const int p = (warp - 1 - ((Cfg::SKIP && warp > 4) ? 1 : 0)) * Cfg::LPW + lane;
     if (lane >= Cfg::LPW || p >= 2 * Cfg::NJ) return;
     const bool storer = p >= Cfg::NJ;
     const int job = storer ? p - Cfg::NJ : p;
