@@ -9,6 +9,7 @@
 //   SsmKlCore        forward : KL(q || p), chain-rule form                    (mf_ssm_kl_divergence)
 //   NatToSsmCore     backward: naturals -> SSM parameters, U D U^T sweep      (mf_nat_to_ssm)
 #pragma once
+#include "dispatch.cuh"
 #include "nat_kernels.cuh"
 #include "sweep.cuh"
 
@@ -1011,6 +1012,8 @@ struct SweepAuto {
     if constexpr (choice == 0) {
       // few chains: one compute warp per CTA so that more SMs get a CTA
       if (nchains <= (int64_t)148 * 48) return launch_chain_sweep<Core, 32, 8, 2, 2>(prm, nchains, s, true);
+      // (measured: <32, 16, 2, 2> -- half the bulk copies per step but one compute warp per CTA --
+      // is 0-45 % slower on the config-5 transforms: resident compute warps matter more)
       return launch_chain_sweep<Core, 64, 8, 2, 2>(prm, nchains, s, true);
     } else if constexpr (choice == 1) {
       return launch_chain_sweep<Core, 32, 8, 2, 2>(prm, nchains, s, true);
