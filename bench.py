@@ -389,7 +389,7 @@ def run_gpu(args):
         h2d_b, d2h_b = cholesky_solve_host.last_bytes
         e2e = {"value": world * b * T / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_b,
                "d2h_bytes_per_step": d2h_b, "ms_per_step": e2e_s * 1e3, "steps": n_e2e,
-               "api": "markovflow_b200.host.cholesky_solve_host (pinned host tensors, 512-chain chunks, 3 streams)"}
+               "api": "markovflow_b200.host.cholesky_solve_host (pinned host tensors, 128-chain chunks, 3 streams)"}
         if rank == 0:
             assert torch.equal(out[0][::512], od[::512].cpu()), "e2e result differs from device-resident result"
 

@@ -41,7 +41,7 @@ def cholesky_solve_host(
     sub: torch.Tensor,
     rhs: Optional[torch.Tensor] = None,
     out: Optional[Tuple[torch.Tensor, ...]] = None,
-    chunk: int = 512,
+    chunk: int = 128,
     device: Optional[torch.device] = None,
 ):
     """``SymmetricBlockTriDiagonal(diag, sub).cholesky`` (+ ``.solve(rhs)``) on host tensors.
