@@ -391,7 +391,10 @@ def run_gpu(args):
                "d2h_bytes_per_step": d2h_b, "ms_per_step": e2e_s * 1e3, "steps": n_e2e,
                "api": "markovflow_b200.host.cholesky_solve_host (pinned host tensors, 128-chain chunks, 3 streams)"}
         if rank == 0:
-            assert torch.equal(out[0][::512], od[::512].cpu()), "e2e result differs from device-resident result"
+            # chunks of <= 1024 chains take the parallel-in-time path: same factor to rounding
+            ref_ld = od[::512].cpu()
+            e2e_err = float((out[0][::512] - ref_ld).abs().max() / ref_ld.abs().max())
+            assert e2e_err < 1e-11, f"e2e result differs from device-resident result: {e2e_err:.2e}"
 
     peak, peak_src = measured_peak()
     extras = None
