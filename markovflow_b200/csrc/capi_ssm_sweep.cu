@@ -61,7 +61,8 @@ int ssm_sweep_moments(int dtype, int64_t D, int expectations, const void* mu0, c
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
     SsmMomentsParams<Tp> p{(const Tp*)mu0, (const Tp*)chol_p0, (const Tp*)a, (const Tp*)b,
-                           (const Tp*)chol_q, (Tp*)o_vec, (Tp*)o_diag, (Tp*)o_sub, B, T, 1, T};
+                           (const Tp*)chol_q, (Tp*)o_vec, (Tp*)o_diag, (Tp*)o_sub, B, T, 1, T,
+                           (Tp*)o_vec, (Tp*)o_diag, 0};
     if (tuning(2) != 1 && o_diag && (o_vec || !expectations)) plan_segments(B, T, &p.P, &p.L);
     if (p.P > 1) {
       int rc = run<SsmMomSummaryCore<Tp, kD>>(p, B * p.P, s);
@@ -117,8 +118,34 @@ int ssm_sweep_kl(int dtype, int64_t D, const void* q_mu0, const void* q_chol_p0,
     constexpr int kD = decltype(dd)::value;
     SsmKlParams<Tp> p{(const Tp*)q_mu0, (const Tp*)q_chol_p0, (const Tp*)q_a, (const Tp*)q_b,
                       (const Tp*)q_chol_q, (const Tp*)p_mu0, (const Tp*)p_chol_p0, (const Tp*)p_a,
-                      (const Tp*)p_b, (const Tp*)p_chol_q, (Tp*)out, B, T};
-    return run<SsmKlCore<Tp, kD>>(p, B, s);
+                      (const Tp*)p_b, (const Tp*)p_chol_q, (Tp*)out, B, T, 1, T, nullptr, nullptr, nullptr};
+    if (tuning(2) != 1 && T >= 128) plan_segments(B, T, &p.P, &p.L);
+    if (p.P == 1) return run<SsmKlCore<Tp, kD>>(p, B, s);
+    // few long chains: parallel in time.  Stream-ordered scratch for the elements / seeds / partials.
+    const size_t n_el = (size_t)B * p.P * 2;
+    const size_t bytes = sizeof(Tp) * (n_el * (kD + kD * kD) + (size_t)B * p.P);
+    Tp* ws = nullptr;
+    if (cudaMallocAsync((void**)&ws, bytes, s) != cudaSuccess) return check_launch();
+    Tp* ws_vec = ws;
+    Tp* ws_diag = ws + n_el * kD;
+    p.seed_vec = ws_vec;
+    p.seed_diag = ws_diag;
+    p.partial = ws_diag + n_el * kD * kD;
+    SsmMomentsParams<Tp> m{(const Tp*)q_mu0, (const Tp*)q_chol_p0, (const Tp*)q_a, (const Tp*)q_b,
+                           (const Tp*)q_chol_q, nullptr, nullptr, nullptr, B, T, p.P, p.L, ws_vec, ws_diag, 1};
+    int rc = run<SsmMomSummaryCore<Tp, kD>>(m, B * p.P, s);
+    if (rc == MF_OK) {
+      if (p.P > 64) ssm_moments_seed_kernel<Tp, kD, true><<<grid_for(B * 32, 128), 128, 0, s>>>(m);
+      else ssm_moments_seed_kernel<Tp, kD, false><<<grid_for(B, 128), 128, 0, s>>>(m);
+      rc = check_launch();
+    }
+    if (rc == MF_OK) rc = run<SsmKlCore<Tp, kD>>(p, B * p.P, s);
+    if (rc == MF_OK) {
+      ssm_kl_reduce_kernel<Tp><<<grid_for(B, 128), 128, 0, s>>>(p.partial, (Tp*)out, B, p.P);
+      rc = check_launch();
+    }
+    cudaFreeAsync(ws, s);
+    return rc;
   });
 }
 

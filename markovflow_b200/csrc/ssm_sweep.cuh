@@ -75,7 +75,17 @@ struct SsmMomentsParams {
   T *o_vec, *o_diag, *o_sub;  // means|eta_lin [B,T,D], covs|eta_diag [B,T,D,D], lag-one [B,T-1,D,D]
   int64_t B, Tn;
   int64_t P, L;  // segments per chain, steps per segment (P == 1: L == Tn)
+  // where elements / seeds are parked: the outputs themselves (compact == 0: entry c*Tn + kl - which)
+  // or a compact workspace (compact == 1: entry (c*P + seg)*2 + which) when there are no outputs
+  T *pk_vec, *pk_diag;
+  int compact;
 };
+
+template <typename T>
+__device__ __forceinline__ int64_t mom_park(const SsmMomentsParams<T>& p, int64_t c, int64_t seg,
+                                            int64_t kl, int which) {
+  return p.compact ? (c * p.P + seg) * 2 + which : c * p.Tn + kl - which;
+}
 
 // entry of local step j of segment (c, k0): states / transitions leading into the step
 template <typename T>
@@ -141,8 +151,9 @@ struct SsmMomentsCore {
       for (int i = 0; i < D; ++i) mu[i] = T(0);
       const int64_t kl = k0_ + seg_steps(p.Tn, k0_, p.L) - 1;
       if (kl >= k0_) {
-        if (p.o_vec) load_vec<T, D>(mu, p.o_vec + (c * p.Tn + kl) * D);
-        load_vec<T, DD>(P, p.o_diag + (c * p.Tn + kl) * DD);
+        const int64_t e = mom_park(p, c, v % p.P, kl, 0);
+        if (p.pk_vec) load_vec<T, D>(mu, p.pk_vec + e * D);
+        load_vec<T, DD>(P, p.pk_diag + e * DD);
       }
     }
   }
@@ -262,9 +273,10 @@ struct SsmMomSummaryCore {
     if (!valid || !live_) return;
     const int64_t c = v / p.P;
     const int64_t kl = k0_ + p.L - 1;  // a live segment is complete: L steps
-    store_vec<T, DD>(p.o_diag + (c * p.Tn + kl) * DD, Phi);
-    store_vec<T, DD>(p.o_diag + (c * p.Tn + kl - 1) * DD, Qt);
-    if (p.o_vec) store_vec<T, D>(p.o_vec + (c * p.Tn + kl) * D, cv);
+    const int64_t e0 = mom_park(p, c, v % p.P, kl, 0), e1 = mom_park(p, c, v % p.P, kl, 1);
+    store_vec<T, DD>(p.pk_diag + e0 * DD, Phi);
+    store_vec<T, DD>(p.pk_diag + e1 * DD, Qt);
+    if (p.pk_vec) store_vec<T, D>(p.pk_vec + e0 * D, cv);
   }
 };
 
@@ -320,10 +332,11 @@ struct MomElem {
     for (int i = 0; i < D; ++i) mu[i] = v[i];
     congruence(sig, Phi, Qt);
   }
-  __device__ __forceinline__ void load(const SsmMomentsParams<T>& p, int64_t c_, int64_t kl) {
-    load_vec<T, D * D>(Phi, p.o_diag + (c_ * p.Tn + kl) * D * D);
-    load_vec<T, D * D>(Qt, p.o_diag + (c_ * p.Tn + kl - 1) * D * D);
-    if (p.o_vec) load_vec<T, D>(c, p.o_vec + (c_ * p.Tn + kl) * D);
+  __device__ __forceinline__ void load(const SsmMomentsParams<T>& p, int64_t c_, int64_t seg, int64_t kl) {
+    const int64_t e0 = mom_park(p, c_, seg, kl, 0), e1 = mom_park(p, c_, seg, kl, 1);
+    load_vec<T, D * D>(Phi, p.pk_diag + e0 * D * D);
+    load_vec<T, D * D>(Qt, p.pk_diag + e1 * D * D);
+    if (p.pk_vec) load_vec<T, D>(c, p.pk_vec + e0 * D);
     else {
 #pragma unroll
       for (int i = 0; i < D; ++i) c[i] = T(0);
@@ -365,7 +378,7 @@ ssm_moments_seed_kernel(const SsmMomentsParams<T> p) {
     MomElem<T, D> mine, e, other;
     mine.identity();
     for (int64_t seg = s0; seg < s1 && seg < nlive; ++seg) {
-      e.load(p, c, seg * p.L + p.L - 1);
+      e.load(p, c, seg, seg * p.L + p.L - 1);
       mine.then(e);
     }
 #pragma unroll 1
@@ -388,10 +401,11 @@ ssm_moments_seed_kernel(const SsmMomentsParams<T> p) {
     const int64_t kl = k0 + n - 1;
     MomElem<T, D> e;
     const bool live = seg < nlive;
-    if (live) e.load(p, c, kl);
+    if (live) e.load(p, c, seg, kl);
     if (seg > 0) {
-      if (p.o_vec) store_vec<T, D>(p.o_vec + (c * p.Tn + kl) * D, mu);
-      store_vec<T, DD>(p.o_diag + (c * p.Tn + kl) * DD, sig);
+      const int64_t e0 = mom_park(p, c, seg, kl, 0);
+      if (p.pk_vec) store_vec<T, D>(p.pk_vec + e0 * D, mu);
+      store_vec<T, DD>(p.pk_diag + e0 * DD, sig);
     }
     if (live) e.apply(mu, sig);
   }
@@ -556,12 +570,20 @@ ssm_affine_seed_kernel(const SsmAffineParams<T> p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// KL(q || p), chain-rule form.  q's marginal (mu_k, Sigma_k) is the only state carried along the
+// chain, so few long chains are evaluated parallel in time with the moment elements above: summary
+// pass over q's transitions -> seeds -> every segment accumulates its share of the sum
+// (SsmKlParams::partial), added in segment order by ssm_kl_reduce_kernel.  KL has no large outputs
+// to park elements in: they live in a compact workspace (seed_vec / seed_diag).
 template <typename T>
 struct SsmKlParams {
   const T *q_mu0, *q_chol_p0, *q_a, *q_b, *q_chol_q;
   const T *p_mu0, *p_chol_p0, *p_a, *p_b, *p_chol_q;
   T* out;
   int64_t B, Tn;
+  int64_t P, L;
+  const T *seed_vec, *seed_diag;  // [B*P*2, D], [B*P*2, D*D]: entry (c*P + seg)*2 = state before seg
+  T* partial;                     // [B*P]
 };
 
 template <typename T_, int D>
@@ -573,34 +595,46 @@ struct SsmKlCore {
   static constexpr bool BACKWARD = false;
   static constexpr int ein(int i) { return (i % 3 == 1) ? D : DD; }
   static constexpr int eout(int) { return 1; }
-  static __device__ __forceinline__ int64_t num_chains(const Params& p) { return p.B; }
-  static __device__ __forceinline__ int64_t max_steps(const Params& p) { return p.Tn; }
-  static __device__ __forceinline__ StreamGeom in_geom(const Params& p, int i, int64_t c) {
+  static __device__ __forceinline__ int64_t num_chains(const Params& p) { return p.B * p.P; }
+  static __device__ __forceinline__ int64_t max_steps(const Params& p) { return p.L; }
+  static __device__ __forceinline__ StreamGeom in_geom(const Params& p, int i, int64_t v) {
     const T* base = i == 0 ? p.q_a : i == 1 ? p.q_b : i == 2 ? p.q_chol_q
                   : i == 3 ? p.p_a : i == 4 ? p.p_b : p.p_chol_q;
-    return geom_incoming<T>(base, c, p.Tn, ein(i));
+    const int64_t c = v / p.P, k0 = (v % p.P) * p.L;
+    return vgeom_incoming<T>(base, c, p.Tn, ein(i), k0, seg_steps(p.Tn, k0, p.L));
   }
   static __device__ __forceinline__ StreamGeom out_geom(const Params&, int, int64_t) {
     return StreamGeom{nullptr, 0, 0};
   }
   T mu[D], P[DD], kl;
   LogProd<T> ratio;
-  __device__ __forceinline__ void init(const Params& p, int64_t c) {
-    T Lq[DD], Lp[DD], dm[D];
+  int64_t k0_, n_;
+  __device__ __forceinline__ void init(const Params& p, int64_t v) {
+    const int64_t c = v / p.P;
+    k0_ = (v % p.P) * p.L;
+    n_ = seg_steps(p.Tn, k0_, p.L);
     ratio.init();
-    load_vec<T, D>(mu, p.q_mu0 + c * D);
-    load_vec<T, DD>(Lq, p.q_chol_p0 + c * DD);
-    load_vec<T, DD>(Lp, p.p_chol_p0 + c * DD);
-    load_vec<T, D>(dm, p.p_mu0 + c * D);
+    kl = T(0);
+    if (k0_ == 0) {
+      T Lq[DD], Lp[DD], dm[D];
+      load_vec<T, D>(mu, p.q_mu0 + c * D);
+      load_vec<T, DD>(Lq, p.q_chol_p0 + c * DD);
+      load_vec<T, DD>(Lp, p.p_chol_p0 + c * DD);
+      load_vec<T, D>(dm, p.p_mu0 + c * D);
 #pragma unroll
-    for (int i = 0; i < D; ++i) dm[i] = mu[i] - dm[i];
-    kl = kl_gauss_term<T, D>(Lp, Lq, nullptr, dm, nullptr, ratio);
-    llt<T, D>(P, Lq);
+      for (int i = 0; i < D; ++i) dm[i] = mu[i] - dm[i];
+      kl = kl_gauss_term<T, D>(Lp, Lq, nullptr, dm, nullptr, ratio);
+      llt<T, D>(P, Lq);
+    } else {
+      load_vec<T, D>(mu, p.seed_vec + v * 2 * D);
+      load_vec<T, DD>(P, p.seed_diag + v * 2 * DD);
+    }
   }
   __device__ __forceinline__ void tile(const Params&, const T* const* in, T* const*, int64_t j0,
                                        int ns) {
+    if (n_ - j0 < ns) ns = (int)(n_ - j0);
     for (int j = 0; j < ns; ++j) {
-      if (j0 + j == 0) continue;
+      if (k0_ + j0 + j == 0) continue;
       T Aq[DD], Ap[DD], bq[D], dm[D], Lq[DD], Lp[DD], AP[DD];
       ld_s<T, DD>(Aq, in[0] + j * DD);
       ld_s<T, D>(bq, in[1] + j * D);
@@ -631,10 +665,23 @@ struct SsmKlCore {
       for (int i = 0; i < D; ++i) mu[i] = bq[i];
     }
   }
-  __device__ __forceinline__ void finish(const Params& p, int64_t c, bool valid) {
-    if (valid) p.out[c] = kl + ratio.log_abs();
+  __device__ __forceinline__ void finish(const Params& p, int64_t v, bool valid) {
+    if (!valid) return;
+    const T val = kl + ratio.log_abs();
+    if (p.P == 1) p.out[v] = val;
+    else p.partial[v] = val;
   }
 };
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+ssm_kl_reduce_kernel(const T* __restrict__ partial, T* __restrict__ out, int64_t B, int64_t P) {
+  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= B) return;
+  T s = T(0);
+  for (int64_t seg = 0; seg < P; ++seg) s += partial[c * P + seg];
+  out[c] = s;
+}
 
 // ---------------------------------------------------------------------------------------------
 // naturals -> SSM parameters: backward U D U^T sweep (nat_to_ssm_kernel in nat_kernels.cuh has the

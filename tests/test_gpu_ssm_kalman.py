@@ -478,3 +478,35 @@ def test_means_and_samples_parallel_in_time(d, dtype):
             assert max_rel_err(got[knob][0], want_mean) < TOL[dtype]
             assert max_rel_err(got[knob][1], want_s) < TOL[dtype]
         assert max_rel_err(got[0][1], got[1][1]) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("d", [1, 2, 3, 4])
+def test_kl_divergence_parallel_in_time(d, dtype):
+    """Few long chains: KL(q || p) with q's marginals seeded per segment (moment elements in a
+    stream-ordered workspace) and the per-segment shares added in order; equal to the oracle and to
+    the sequential sweep."""
+    from markovflow_b200 import _lib
+
+    lib = _lib.lib()
+    for b, t, seg in ((1, 1500, 0), (2, 301, 0), (3, 400, 9), (2, 131, 65), (1, 3000, 4)):
+        state = np.random.get_state()
+        np.random.seed(t * 10 + d)
+        qa = random_ssm_arrays((b,), t - 1, d, scale_a=0.6 / np.sqrt(d))
+        pa = random_ssm_arrays((b,), t - 1, d, scale_a=0.6 / np.sqrt(d))
+        np.random.set_state(state)
+        if dtype == torch.float32:
+            qa = tuple(a.astype(np.float32).astype(np.float64) for a in qa)
+            pa = tuple(a.astype(np.float32).astype(np.float64) for a in pa)
+        want = O.ssm_kl_divergence(O.SSM(*qa), O.SSM(*pa))
+        got = {}
+        for knob in (0, 1):
+            lib.mf_set_tuning(2, knob)
+            lib.mf_set_tuning(3, seg)
+            try:
+                got[knob] = npy(make_ssm(qa, dtype).kl_divergence(make_ssm(pa, dtype)))
+            finally:
+                lib.mf_set_tuning(2, 0)
+                lib.mf_set_tuning(3, 0)
+            assert max_rel_err(got[knob], want) < (1e-9 if dtype == torch.float64 else 2e-4)
+        assert max_rel_err(got[0], got[1]) < (1e-10 if dtype == torch.float64 else 2e-4)
