@@ -236,6 +236,36 @@ int mf_expectations_to_ssm(int dtype, const void* eta_lin, const void* eta_diag,
                            const void* eta_sub, void* out_a, void* out_offsets, void* out_chols,
                            int32_t* info, int64_t B, int64_t T, int64_t D, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Conditionals on top of the marginals (markovflow/conditionals.py) -- SURVEY.md 8f-1
+ * ------------------------------------------------------------------------------------------- */
+
+/* pairwise_marginals (conditionals.py:423-485): joint mean / covariance of every pair of subsequent
+ * states (x_{k-1}, x_k), k = 0..T, with the initial (prior) state at both ends.
+ *   mean [B,T,D], cov [B,T,D,D], sub [B,T-1,D,D] = A_k Sigma_kk (as written by mf_ssm_marginals),
+ *   init_mean [init_batch,D], init_cov [init_batch,D,D] (init_batch = 1 or B),
+ *   out_mean [B,T+1,2D], out_cov [B,T+1,2D,2D]. */
+int mf_pairwise_marginals(int dtype, const void* mean, const void* cov, const void* sub,
+                          const void* init_mean, const void* init_cov, int64_t init_batch,
+                          void* out_mean, void* out_cov, int64_t B, int64_t T, int64_t D, void* stream);
+
+/* _conditional_statistics_from_transitions (conditionals.py:128-205): p(x_t | x_-, x_+) =
+ * N(D_t x_- + E_t x_+, T_t) from the transitions into t (a_mt, q_mt) and out of t (a_tp, q_tp),
+ * all [N,D,D].  out_p [N,D,2D] = [D_t | E_t], out_t [N,D,D] = T_t (the precision T_t^-1 when
+ * return_precision != 0), info [N] or NULL (1 where a Cholesky pivot was not positive). */
+int mf_conditional_statistics(int dtype, const void* a_mt, const void* q_mt, const void* a_tp,
+                              const void* q_tp, void* out_p, void* out_t, int32_t* info,
+                              int return_precision, int64_t N, int64_t D, void* stream);
+
+/* conditional_predict / base_conditional_predict (conditionals.py:29-83, 380-420):
+ *   mean = P m[idx], cov = T (+ P S[idx] P^T when pair_covs != NULL), the gather of the pairwise
+ *   marginals by insertion index fused in.  proj [B,N,D,2D], tcov [B,N,D,D], pair_means [B,M,2D],
+ *   pair_covs [B,M,2D,2D] or NULL, indices [B,N] (int64; NULL = identity, needs N == M),
+ *   out_mean [B,N,D], out_cov [B,N,D,D]. */
+int mf_conditional_predict(int dtype, const void* proj, const void* tcov, const void* pair_means,
+                           const void* pair_covs, const int64_t* indices, void* out_mean,
+                           void* out_cov, int64_t B, int64_t N, int64_t M, int64_t D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,13 @@ from .block_tri_diag import (
     LowerTriangularBlockTriDiagonal,
     SymmetricBlockTriDiagonal,
 )
+from .conditionals import (
+    base_conditional_predict,
+    conditional_predict_from_transitions,
+    conditional_statistics_from_transitions,
+    insertion_indices,
+    pairwise_marginals,
+)
 from .config import set_check_numerics
 from .emission_model import EmissionModel
 from .gauss_markov import GaussMarkovDistribution, check_compatible
@@ -33,6 +40,11 @@ from .state_space_model import (
 )
 
 __all__ = [
+    "base_conditional_predict",
+    "conditional_predict_from_transitions",
+    "conditional_statistics_from_transitions",
+    "insertion_indices",
+    "pairwise_marginals",
     "BlockTriDiagonal",
     "LowerTriangularBlockTriDiagonal",
     "SymmetricBlockTriDiagonal",

@@ -1034,3 +1034,51 @@ class Sum(_Stationary):
 
     def emission_row(self):
         return np.concatenate([k.emission_row() for k in self.kernels])
+
+
+# ------------------------------------------------------------------------------------------------
+# conditionals.py
+# ------------------------------------------------------------------------------------------------
+
+def pairwise_marginals(ssm: SSM, initial_mean: Array, initial_covariance: Array) -> Tuple[Array, Array]:
+    """``conditionals.pairwise_marginals`` (``conditionals.py:423-485``): joint of every pair of
+    subsequent states, with the initial state prepended and appended."""
+    means = ssm_marginal_means(ssm)
+    covs = ssm_marginal_covariances(ssm)
+    subs = ssm_subsequent_covariances(ssm, covs)
+    im = np.broadcast_to(initial_mean, means.shape[:-2] + means.shape[-1:])[..., None, :]
+    ic = np.broadcast_to(initial_covariance, covs.shape[:-3] + covs.shape[-2:])[..., None, :, :]
+    ext_m = np.concatenate([im, means, im], axis=-2)
+    joint_mean = np.concatenate([ext_m[..., :-1, :], ext_m[..., 1:, :]], axis=-1)
+    ext_c = np.concatenate([ic, covs, ic], axis=-3)
+    zero = np.zeros_like(ic)
+    ext_s = np.concatenate([zero, subs, zero], axis=-3)
+    top = np.concatenate([ext_c[..., :-1, :, :], np.swapaxes(ext_s, -1, -2)], axis=-1)
+    bottom = np.concatenate([ext_s, ext_c[..., 1:, :, :]], axis=-1)
+    return joint_mean, np.concatenate([top, bottom], axis=-2)
+
+
+def conditional_statistics_from_transitions(a_mt: Array, q_mt: Array, a_tp: Array, q_tp: Array,
+                                            return_precision: bool = False):
+    """``conditionals._conditional_statistics_from_transitions`` (``conditionals.py:128-205``)."""
+    a_tp_q_mt = a_tp @ q_mt
+    q_mp = q_tp + a_tp @ np.swapaxes(a_tp_q_mt, -1, -2)
+    chol = np.linalg.cholesky(q_mp)
+    v = np.linalg.solve(chol, a_tp_q_mt)
+    e = np.swapaxes(np.linalg.solve(np.swapaxes(chol, -1, -2), v), -1, -2)
+    d = a_mt - e @ a_tp @ a_mt
+    if return_precision:
+        t = np.linalg.inv(q_mt) + np.swapaxes(a_tp, -1, -2) @ np.linalg.solve(q_tp, a_tp)
+    else:
+        t = q_mt - np.swapaxes(v, -1, -2) @ v
+    return d, e, t
+
+
+def base_conditional_predict(proj: Array, tcov: Array, adjacent_states: Array,
+                             pairwise_state_covariances: Optional[Array] = None):
+    """``conditionals.base_conditional_predict`` (``conditionals.py:380-420``)."""
+    means = (proj @ adjacent_states[..., None])[..., 0]
+    covs = tcov
+    if pairwise_state_covariances is not None:
+        covs = covs + proj @ pairwise_state_covariances @ np.swapaxes(proj, -1, -2)
+    return means, covs
