@@ -90,8 +90,8 @@ struct CholPitCore : CholPitGeom<T_, D, RHS> {
     for (int i = 0; i < D; ++i) x[i] = T(0);
     if (k0_ > 0 && n_ > 0) {  // seed (Ls_{k0-1}, x_{k0-1}) parked in this segment's last slots
       const int64_t kl = k0_ + n_ - 1;
-      load_vec<T, DD>(Ls, p.od + (c * p.Tn + kl) * DD);
-      if (RHS) load_vec<T, D>(x, p.ox + (c * p.Tn + kl) * D);
+      load_vec_rw<T, DD>(Ls, p.od + (c * p.Tn + kl) * DD);
+      if (RHS) load_vec_rw<T, D>(x, p.ox + (c * p.Tn + kl) * D);
       coupled_ = true;
     }
   }
@@ -243,87 +243,93 @@ struct CholPitSummaryCore : CholPitGeom<T_, D, RHS> {
   }
 };
 
-// ---- pass 2: one thread per chain folds the elements in order ----------------------------------
+// ---- pass 2: fold of the elements -------------------------------------------------------------
+// element of segment [k0, k0 + L) parked by CholPitSummaryCore (kl = its last step)
 template <typename T, int D, bool RHS>
+__device__ __forceinline__ void chol_elem_load(LftElem<T, D, RHS>& e, const CholPitParams<T>& prm,
+                                               int64_t c, int64_t kl) {
+  constexpr int DD = D * D;
+  e.empty = 0;
+  load_vec_rw<T, DD>(e.P, prm.od + (c * prm.Tn + kl) * DD);
+  load_vec_rw<T, DD>(e.R, prm.od + (c * prm.Tn + kl - 1) * DD);
+  load_vec_rw<T, DD>(e.Q, prm.os + (c * (prm.Tn - 1) + kl) * DD);
+#pragma unroll
+  for (int i = 0; i < D; ++i) e.p[i] = e.r[i] = T(0);
+  if (RHS) {
+    load_vec_rw<T, D>(e.p, prm.ox + (c * prm.Tn + kl) * D);
+    load_vec_rw<T, D>(e.r, prm.ox + (c * prm.Tn + kl - 1) * D);
+  }
+}
+
+// WARP = false: one thread per chain walks the segments in order.  WARP = true (many segments): one
+// warp per chain -- lane l owns segments [l*m, (l+1)*m), combines their elements, the warp scans the
+// 32 composites, and every lane then walks its segments from its exclusive prefix.  For every
+// segment s >= 1 the pair (Ls_{k0-1}, x_{k0-1}) that its first step needs is parked in its last
+// output slots (which held the segment's own element: loaded before it is overwritten).
+template <typename T, int D, bool RHS, bool WARP>
 __global__ void __launch_bounds__(128)
 chol_pit_seed_kernel(const CholPitParams<T> p) {
   constexpr int DD = D * D;
-  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  using Elem = LftElem<T, D, RHS>;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t c = WARP ? tid / 32 : tid;
+  const int lane = WARP ? (int)(tid & 31) : 0;
   if (c >= p.B) return;
-  T S[DD], rr[D];
+  // live segments (complete, with a successor): 0 .. nlive-1
+  const int64_t nlive = (p.Tn - 1) / p.L;  // k0 + L < Tn  <=>  seg < (Tn - 1) / L  (integer division)
+  const int64_t m = WARP ? (p.P + 31) / 32 : p.P;
+  const int64_t s0 = lane * m;
+  int64_t s1 = s0 + m;
+  if (s1 > p.P) s1 = p.P;
   int32_t fail = 0;
-#pragma unroll
-  for (int i = 0; i < D; ++i) rr[i] = T(0);
-  for (int64_t seg = 0; seg < p.P; ++seg) {
+  Elem X;
+  X.clear();
+  if (WARP) {
+    Elem e, other;
+    for (int64_t seg = s0; seg < s1 && seg < nlive; ++seg) {
+      chol_elem_load<T, D, RHS>(e, p, c, seg * p.L + p.L - 1);
+      if (!X.then(e) && fail == 0) fail = (int32_t)(seg * p.L + 1);
+    }
+#pragma unroll 1
+    for (int delta = 1; delta < 32; delta <<= 1) {
+      other.shfl_up_from(X, delta);
+      if (lane >= delta) {
+        if (!other.then(X) && fail == 0) fail = (int32_t)(s0 * p.L + 1);
+        X = other;
+      }
+    }
+    other.shfl_up_from(X, 1);  // exclusive prefix: the inclusive composite of the previous lane
+    X = other;
+    if (lane == 0) X.clear();
+  }
+  for (int64_t seg = s0; seg < s1; ++seg) {
     const int64_t k0 = seg * p.L;
     const int64_t n = seg_steps(p.Tn, k0, p.L);
     if (n <= 0) break;
     const int64_t kl = k0 + n - 1;
-    const bool live = k0 + p.L < p.Tn;
-    T Pm[DD], Q[DD], R[DD], pv[D], rv[D];
-    if (live) {  // element of this segment (loaded before its slots receive the seed)
-      load_vec<T, DD>(Pm, p.od + (c * p.Tn + kl) * DD);
-      load_vec<T, DD>(R, p.od + (c * p.Tn + kl - 1) * DD);
-      load_vec<T, DD>(Q, p.os + (c * (p.Tn - 1) + kl) * DD);
-      if (RHS) {
-        load_vec<T, D>(pv, p.ox + (c * p.Tn + kl) * D);
-        load_vec<T, D>(rv, p.ox + (c * p.Tn + kl - 1) * D);
-      }
-    }
+    const bool live = seg < nlive;
+    Elem e;
+    e.clear();
+    if (live) chol_elem_load<T, D, RHS>(e, p, c, kl);  // before its slots receive the seed
     if (seg > 0) {
-      // what the first step of this segment needs: Ls_{k0-1} = A_{k0-1} Ld^{-T}, x_{k0-1} = Ld^{-1} r
+      // state after segments 0..seg-1 = (P, p) of their combined element
       T Lf[DD], rinv[D], A[DD], xs[D];
 #pragma unroll
-      for (int i = 0; i < DD; ++i) Lf[i] = S[i];
+      for (int i = 0; i < DD; ++i) Lf[i] = X.P[i];
       const bool ok = chol_lower<T, D>(Lf, rinv);
       if (!ok && fail == 0) fail = (int32_t)k0;
       load_vec<T, DD>(A, p.sub + (c * (p.Tn - 1) + k0 - 1) * DD);
-      trsm_right_lower_t<T, D>(A, Lf, rinv);
+      trsm_right_lower_t<T, D>(A, Lf, rinv);  // Ls_{k0-1} = A_{k0-1} Ld^{-T}
       store_vec<T, DD>(p.od + (c * p.Tn + kl) * DD, A);
       if (RHS) {
 #pragma unroll
-        for (int i = 0; i < D; ++i) xs[i] = rr[i];
-        trsv_lower<T, D>(Lf, rinv, xs);
+        for (int i = 0; i < D; ++i) xs[i] = X.p[i];
+        trsv_lower<T, D>(Lf, rinv, xs);  // x_{k0-1} = Ld^{-1} r
         store_vec<T, D>(p.ox + (c * p.Tn + kl) * D, xs);
       }
     }
     if (!live) break;
-    if (seg == 0) {
-#pragma unroll
-      for (int i = 0; i < DD; ++i) S[i] = Pm[i];
-#pragma unroll
-      for (int i = 0; i < D; ++i) rr[i] = RHS ? pv[i] : T(0);
-    } else {
-      // M = S + R = C C^T;  Y = M^{-1} Q^T;  S' = P - Q Y;  r' = p + Y^T (r_in + r)
-      T M[DD], rinv[D], Y[DD], u[D];
-#pragma unroll
-      for (int i = 0; i < DD; ++i) M[i] = S[i] + R[i];
-      const bool ok = chol_lower<T, D>(M, rinv);
-      if (!ok && fail == 0) fail = (int32_t)(k0 + 1);
-#pragma unroll
-      for (int a = 0; a < D; ++a)
-#pragma unroll
-        for (int b = 0; b < D; ++b) Y[a * D + b] = Q[b * D + a];
-      trsm_left_lower<T, D>(M, rinv, Y);
-      trsm_left_lower_t<T, D>(M, rinv, Y);
-      if (RHS) {
-#pragma unroll
-        for (int i = 0; i < D; ++i) u[i] = rr[i] + rv[i];
-#pragma unroll
-        for (int i = 0; i < D; ++i) rr[i] = pv[i];
-        gemv_t_add<T, D>(rr, Y, u);
-      }
-#pragma unroll
-      for (int a = 0; a < D; ++a)
-#pragma unroll
-        for (int b = 0; b <= a; ++b) {
-          T v = Pm[a * D + b];
-#pragma unroll
-          for (int s = 0; s < D; ++s) v = Num<T>::fma(-Q[a * D + s], Y[s * D + b], v);
-          S[a * D + b] = v;
-          S[b * D + a] = v;
-        }
-    }
+    if (!X.then(e) && fail == 0) fail = (int32_t)(k0 + 1);
   }
   if (fail && p.info) atomic_min_nonzero(p.info + c, fail);
 }

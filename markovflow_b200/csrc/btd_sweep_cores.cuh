@@ -82,7 +82,7 @@ struct BtdSolveCore {
 #pragma unroll
       for (int i = 0; i < DD; ++i) Phi[SUMMARY ? i : 0] = (i / D == i % D) ? T(1) : T(0);
     } else if (SUB && n_ > 0 && (TRANSPOSE ? k0_ + n_ < p.Tn : k0_ > 0)) {
-      load_vec<T, D>(x, p.out + (c * p.Tn + solve_slot<TRANSPOSE>(k0_, n_, 0)) * D);  // seed
+      load_vec_rw<T, D>(x, p.out + (c * p.Tn + solve_slot<TRANSPOSE>(k0_, n_, 0)) * D);  // seed
     }
   }
   // r <- Ld^{-1} (r - Ls xin)  (or the transposed form); blocks of local step j
@@ -162,10 +162,10 @@ btd_solve_seed_kernel(const BtdSolveParams<T> p) {
     const bool live = it + 1 < nseg;  // feeds a later segment of the sweep
     T cv[D], Phi[D * D];
     if (live) {
-      load_vec<T, D>(cv, p.out + (c * p.Tn + solve_slot<TRANSPOSE>(k0, n, 0)) * D);
+      load_vec_rw<T, D>(cv, p.out + (c * p.Tn + solve_slot<TRANSPOSE>(k0, n, 0)) * D);
 #pragma unroll
       for (int q = 0; q < D; ++q)
-        load_vec<T, D>(Phi + q * D, p.out + (c * p.Tn + solve_slot<TRANSPOSE>(k0, n, q + 1)) * D);
+        load_vec_rw<T, D>(Phi + q * D, p.out + (c * p.Tn + solve_slot<TRANSPOSE>(k0, n, q + 1)) * D);
     }
     if (it > 0) store_vec<T, D>(p.out + (c * p.Tn + solve_slot<TRANSPOSE>(k0, n, 0)) * D, x);
     if (!live) break;
@@ -239,7 +239,7 @@ struct BtdInvSubsetCore {
 #pragma unroll
       for (int i = 0; i < DD; ++i) Phi[SUMMARY ? i : 0] = (i / D == i % D) ? T(1) : T(0);
     } else if (n_ > 0 && k0_ + n_ < p.Tn) {
-      load_vec<T, DD>(sig, p.od + (c * p.Tn + k0_) * DD);  // seed: Sigma entering the segment
+      load_vec_rw<T, DD>(sig, p.od + (c * p.Tn + k0_) * DD);  // seed: Sigma entering the segment
     }
   }
   __device__ __forceinline__ void tile(const Params&, const T* const* in, T* const* out, int64_t j0,
@@ -312,8 +312,8 @@ btd_inv_subset_seed_kernel(const BtdInvSubsetParams<T> p) {
     const bool last = k0 + n >= p.Tn;
     T Gt[DD], Phi[DD];
     if (seg > 0) {
-      load_vec<T, DD>(Gt, p.od + (c * p.Tn + k0) * DD);
-      if (!last) load_vec<T, DD>(Phi, p.od + (c * p.Tn + k0 + 1) * DD);
+      load_vec_rw<T, DD>(Gt, p.od + (c * p.Tn + k0) * DD);
+      if (!last) load_vec_rw<T, DD>(Phi, p.od + (c * p.Tn + k0 + 1) * DD);
     }
     if (!last) store_vec<T, DD>(p.od + (c * p.Tn + k0) * DD, sig);
     if (seg == 0) break;
@@ -392,7 +392,7 @@ struct BtdUduCore {
     live_ = n_ > 0 && (!SUMMARY || (v % p.P) > 0);
     have_ = false;
     if (!SUMMARY && n_ > 0 && k0_ + n_ < p.Tn) {  // seed: the D entering this segment
-      load_vec<T, DD>(C, p.ocd + (c * p.Tn + k0_) * DD);
+      load_vec_rw<T, DD>(C, p.ocd + (c * p.Tn + k0_) * DD);
       const bool ok = chol_lower<T, D>(C, rinv);
       if (!ok) fail = (int32_t)(k0_ + n_ + 1);
       have_ = true;
@@ -492,58 +492,32 @@ struct BtdUduCore {
   }
 };
 
-// fold of the elements from the last segment down; parks the D entering every segment s < P-1
-template <typename T, int D>
-__global__ void __launch_bounds__(128)
-btd_udu_seed_kernel(const BtdUduParams<T> p) {
-  constexpr int DD = D * D;
-  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (c >= p.B) return;
-  T Din[DD];
-  int32_t fail = 0;
-  for (int64_t seg = p.P - 1; seg >= 0; --seg) {
-    const int64_t k0 = seg * p.L;
-    const int64_t n = seg_steps(p.Tn, k0, p.L);
-    if (n <= 0) continue;
-    const bool last = k0 + n >= p.Tn;
-    T Pm[DD], Q[DD], R[DD];
-    if (seg > 0) {
-      load_vec<T, DD>(Pm, p.ocd + (c * p.Tn + k0) * DD);
-      if (!last) {
-        load_vec<T, DD>(R, p.ocd + (c * p.Tn + k0 + 1) * DD);
-        load_vec<T, DD>(Q, p.ou + (c * (p.Tn - 1) + k0) * DD);
-      }
-    }
-    if (!last) store_vec<T, DD>(p.ocd + (c * p.Tn + k0) * DD, Din);
-    if (seg == 0) break;
-    if (last) {
-#pragma unroll
-      for (int i = 0; i < DD; ++i) Din[i] = Pm[i];
-    } else {
-      T M[DD], rinv[D], Y[DD];
-#pragma unroll
-      for (int i = 0; i < DD; ++i) M[i] = Din[i] + R[i];
-      const bool ok = chol_lower<T, D>(M, rinv);
-      if (!ok && fail == 0) fail = (int32_t)(k0 + n + 1);
-#pragma unroll
-      for (int a = 0; a < D; ++a)
-#pragma unroll
-        for (int b = 0; b < D; ++b) Y[a * D + b] = Q[b * D + a];
-      trsm_left_lower<T, D>(M, rinv, Y);
-      trsm_left_lower_t<T, D>(M, rinv, Y);
-#pragma unroll
-      for (int r = 0; r < D; ++r)
-#pragma unroll
-        for (int q = 0; q <= r; ++q) {
-          T v = Pm[r * D + q];
-#pragma unroll
-          for (int s = 0; s < D; ++s) v = Num<T>::fma(-Q[r * D + s], Y[s * D + q], v);
-          Din[r * D + q] = v;
-          Din[q * D + r] = v;
-        }
+// fold of the elements from the last segment down (lft_backward_fold in ssm_sweep.cuh); parks the D
+// entering every segment s < P-1 in ocd[k0]
+struct UduFoldPolicy {
+  template <typename T, int D>
+  static __device__ __forceinline__ void load(LftElem<T, D, false>& e, const BtdUduParams<T>& p,
+                                              int64_t c, int64_t k0, int64_t n, bool last) {
+    constexpr int DD = D * D;
+    e.clear();
+    e.empty = 0;
+    load_vec_rw<T, DD>(e.P, p.ocd + (c * p.Tn + k0) * DD);
+    if (!last) {
+      load_vec_rw<T, DD>(e.R, p.ocd + (c * p.Tn + k0 + 1) * DD);
+      load_vec_rw<T, DD>(e.Q, p.ou + (c * (p.Tn - 1) + k0) * DD);
     }
   }
-  if (fail && p.info) atomicMax(p.info + c, fail);
+  template <typename T, int D>
+  static __device__ __forceinline__ void seed(const BtdUduParams<T>& p, int64_t c, int64_t k0,
+                                              const LftElem<T, D, false>& X) {
+    store_vec<T, D * D>(p.ocd + (c * p.Tn + k0) * D * D, X.P);
+  }
+};
+
+template <typename T, int D, bool WARP>
+__global__ void __launch_bounds__(128)
+btd_udu_seed_kernel(const BtdUduParams<T> p) {
+  lft_backward_fold<T, D, false, UduFoldPolicy, BtdUduParams<T>, WARP>(p, p.info);
 }
 
 }  // namespace mf

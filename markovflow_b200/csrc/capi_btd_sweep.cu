@@ -42,11 +42,12 @@ int run(const typename Core::Params& p, int64_t nchains, cudaStream_t s) {
 }  // namespace
 
 // segments per chain for a parallel-in-time sweep whose seeds are folded by one thread per chain
-static void plan_pit(int64_t chains, int64_t T, int min_len, int64_t* P, int64_t* L) {
+static void plan_pit(int64_t chains, int64_t T, int min_len, int64_t* P, int64_t* L,
+                     bool sequential_fold = true) {
   const int64_t target = (int64_t)148 * 192;
   int64_t np = chains >= target / 2 ? 1 : (target + chains - 1) / chains;
   if (np > T / 64) np = T / 64;
-  if (np > 512) np = 512;
+  if (sequential_fold && np > 512) np = 512;
   if (tuning(3) > 1 && tuning(3) < T) np = (T + tuning(3) - 1) / tuning(3);
   if (np < 1) np = 1;
   int64_t l = (T + np - 1) / np;
@@ -119,12 +120,13 @@ int btd_sweep_udu(int dtype, int64_t D, const void* diag, const void* sub, void*
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
     BtdUduParams<Tp> p{(const Tp*)diag, (const Tp*)sub, (Tp*)ou, (Tp*)ocd, info, B, T, 1, T};
-    if (tuning(2) != 1 && T >= 128 && ocd != diag && ou != sub) plan_pit(B, T, 2, &p.P, &p.L);
+    if (tuning(2) != 1 && T >= 128 && ocd != diag && ou != sub) plan_pit(B, T, 2, &p.P, &p.L, false);
     if (p.P > 1) {
       if (info && cudaMemsetAsync(info, 0, sizeof(int32_t) * B, s) != cudaSuccess) return check_launch();
       int rc = run<BtdUduCore<Tp, kD, true>>(p, B * p.P, s);
       if (rc != MF_OK) return rc;
-      btd_udu_seed_kernel<Tp, kD><<<grid_for(B, 128), 128, 0, s>>>(p);
+      if (p.P > 64) btd_udu_seed_kernel<Tp, kD, true><<<grid_for(B * 32, 128), 128, 0, s>>>(p);
+      else btd_udu_seed_kernel<Tp, kD, false><<<grid_for(B, 128), 128, 0, s>>>(p);
       rc = check_launch();
       if (rc != MF_OK) return rc;
     }
@@ -148,7 +150,6 @@ int btd_sweep_cholesky_pit(int dtype, int64_t D, const void* diag, const void* s
     const int64_t target = (int64_t)148 * 192;
     int64_t np = (target + B - 1) / B;
     if (np > T / 64) np = T / 64;
-    if (np > 512) np = 512;  // the seeds are folded sequentially per chain
     if (tuning(3) > 1 && tuning(3) < T) np = (T + tuning(3) - 1) / tuning(3);
     if (np < 2) return (int)MF_ERR_UNSUPPORTED;
     p.L = (T + np - 1) / np;
@@ -160,8 +161,14 @@ int btd_sweep_cholesky_pit(int dtype, int64_t D, const void* diag, const void* s
     if (rhs) rc = run<CholPitSummaryCore<Tp, kD, true>>(p, B * p.P, s);
     else rc = run<CholPitSummaryCore<Tp, kD, false>>(p, B * p.P, s);
     if (rc != MF_OK) return rc;
-    if (rhs) chol_pit_seed_kernel<Tp, kD, true><<<grid_for(B, 128), 128, 0, s>>>(p);
-    else chol_pit_seed_kernel<Tp, kD, false><<<grid_for(B, 128), 128, 0, s>>>(p);
+    // many segments per chain: the fold is a warp scan over the elements
+    if (p.P > 64) {
+      if (rhs) chol_pit_seed_kernel<Tp, kD, true, true><<<grid_for(B * 32, 128), 128, 0, s>>>(p);
+      else chol_pit_seed_kernel<Tp, kD, false, true><<<grid_for(B * 32, 128), 128, 0, s>>>(p);
+    } else {
+      if (rhs) chol_pit_seed_kernel<Tp, kD, true, false><<<grid_for(B, 128), 128, 0, s>>>(p);
+      else chol_pit_seed_kernel<Tp, kD, false, false><<<grid_for(B, 128), 128, 0, s>>>(p);
+    }
     rc = check_launch();
     if (rc != MF_OK) return rc;
     if (rhs) return run<CholPitCore<Tp, kD, true>>(p, B * p.P, s);

@@ -159,16 +159,14 @@ int nat_sweep_to_ssm(int dtype, int64_t D, const void* th_lin, const void* th_di
                          (Tp*)out_off, (Tp*)out_chol, info, B, T, 1, T};
     if (tuning(2) != 1 && out_a) {
       plan_segments(B, T, &p.P, &p.L);
-      if (p.P > 64) {  // the seeds are folded sequentially per chain
-        p.L = (T + 63) / 64;
-        p.P = (T + p.L - 1) / p.L;
-      }
     }
     if (p.P > 1) {
       if (info && cudaMemsetAsync(info, 0, sizeof(int32_t) * B, s) != cudaSuccess) return check_launch();
       int rc = run<NatSummaryCore<Tp, kD>>(p, B * p.P, s);
       if (rc != MF_OK) return rc;
-      nat_seed_kernel<Tp, kD><<<grid_for(B, 128), 128, 0, s>>>(p);
+      // many segments per chain: the fold is a warp scan over the elements
+      if (p.P > 64) nat_seed_kernel<Tp, kD, true><<<grid_for(B * 32, 128), 128, 0, s>>>(p);
+      else nat_seed_kernel<Tp, kD, false><<<grid_for(B, 128), 128, 0, s>>>(p);
       rc = check_launch();
       if (rc != MF_OK) return rc;
     }

@@ -354,6 +354,15 @@ __device__ __forceinline__ void load_vec(T* __restrict__ r, const T* __restrict_
   for (int i = 0; i < N; ++i) r[i] = __ldg(g + i);
 }
 
+// plain (coherent, ordered) loads: for memory that the same kernel also writes -- the parked
+// elements / seeds of the parallel-in-time passes live in OUTPUT arrays.  load_vec's __ldg
+// (ld.global.nc) assumes read-only data and may be reordered past a later store to the same address.
+template <typename T, int N>
+__device__ __forceinline__ void load_vec_rw(T* r, const T* g) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) r[i] = g[i];
+}
+
 template <typename T, int N>
 __device__ __forceinline__ void store_vec(T* __restrict__ g, const T* __restrict__ r) {
 #pragma unroll

@@ -152,8 +152,8 @@ struct SsmMomentsCore {
       const int64_t kl = k0_ + seg_steps(p.Tn, k0_, p.L) - 1;
       if (kl >= k0_) {
         const int64_t e = mom_park(p, c, v % p.P, kl, 0);
-        if (p.pk_vec) load_vec<T, D>(mu, p.pk_vec + e * D);
-        load_vec<T, DD>(P, p.pk_diag + e * DD);
+        if (p.pk_vec) load_vec_rw<T, D>(mu, p.pk_vec + e * D);
+        load_vec_rw<T, DD>(P, p.pk_diag + e * DD);
       }
     }
   }
@@ -334,9 +334,9 @@ struct MomElem {
   }
   __device__ __forceinline__ void load(const SsmMomentsParams<T>& p, int64_t c_, int64_t seg, int64_t kl) {
     const int64_t e0 = mom_park(p, c_, seg, kl, 0), e1 = mom_park(p, c_, seg, kl, 1);
-    load_vec<T, D * D>(Phi, p.pk_diag + e0 * D * D);
-    load_vec<T, D * D>(Qt, p.pk_diag + e1 * D * D);
-    if (p.pk_vec) load_vec<T, D>(c, p.pk_vec + e0 * D);
+    load_vec_rw<T, D * D>(Phi, p.pk_diag + e0 * D * D);
+    load_vec_rw<T, D * D>(Qt, p.pk_diag + e1 * D * D);
+    if (p.pk_vec) load_vec_rw<T, D>(c, p.pk_vec + e0 * D);
     else {
 #pragma unroll
       for (int i = 0; i < D; ++i) c[i] = T(0);
@@ -470,7 +470,7 @@ struct SsmAffineCore {
 #pragma unroll
       for (int i = 0; i < D; ++i) x[i] = T(0);
     } else if (n_ > 0) {
-      load_vec<T, D>(x, p.out + (c * p.Tn + k0_ + n_ - 1) * D);  // seed: x_{k0-1}
+      load_vec_rw<T, D>(x, p.out + (c * p.Tn + k0_ + n_ - 1) * D);  // seed: x_{k0-1}
     }
   }
   __device__ __forceinline__ void tile(const Params& p, const T* const* in, T* const* out,
@@ -548,9 +548,9 @@ ssm_affine_seed_kernel(const SsmAffineParams<T> p) {
     const bool live = (seg + 1) * p.L < p.Tn;
     T cv[D], Phi[D * D];
     if (live) {
-      load_vec<T, D>(cv, p.out + (c * p.Tn + kl) * D);
+      load_vec_rw<T, D>(cv, p.out + (c * p.Tn + kl) * D);
 #pragma unroll
-      for (int q = 0; q < D; ++q) load_vec<T, D>(Phi + q * D, p.out + (c * p.Tn + kl - 1 - q) * D);
+      for (int q = 0; q < D; ++q) load_vec_rw<T, D>(Phi + q * D, p.out + (c * p.Tn + kl - 1 - q) * D);
     }
     if (seg > 0) store_vec<T, D>(p.out + (c * p.Tn + kl) * D, x);
     if (!live) break;
@@ -626,8 +626,8 @@ struct SsmKlCore {
       kl = kl_gauss_term<T, D>(Lp, Lq, nullptr, dm, nullptr, ratio);
       llt<T, D>(P, Lq);
     } else {
-      load_vec<T, D>(mu, p.seed_vec + v * 2 * D);
-      load_vec<T, DD>(P, p.seed_diag + v * 2 * DD);
+      load_vec_rw<T, D>(mu, p.seed_vec + v * 2 * D);
+      load_vec_rw<T, DD>(P, p.seed_diag + v * 2 * DD);
     }
   }
   __device__ __forceinline__ void tile(const Params&, const T* const* in, T* const*, int64_t j0,
@@ -682,6 +682,110 @@ ssm_kl_reduce_kernel(const T* __restrict__ partial, T* __restrict__ out, int64_t
   for (int64_t seg = 0; seg < P; ++seg) s += partial[c * P + seg];
   out[c] = s;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Element of a range of steps of a linear-fractional recursion (block Cholesky forward, U D U^T /
+// naturals -> SSM backward):  S_out = P - Q (S_in + R)^{-1} Q^T,  r_out = p + Q (S_in + R)^{-1} (r_in + r).
+// A chain's first range (in sweep order) has no incoming block, which behaves like
+// S_in = infinity: (S_in + R)^{-1} = 0, so the state after ranges 0..s-1 is simply (P, p) of their
+// COMBINED element -- the fold needs the combination only, never an application to a state:
+//   (e1 then e2):  S = P1 + R2 = C C^T,  Y = S^{-1} Q1,  u = S^{-1} (p1 + r2)
+//                  P = P2 - Q2 S^{-1} Q2^T,  Q = Q2 Y,  R = R1 - Q1^T Y,  p = p2 + Q2 u,  r = r1 + Q1^T u
+template <typename T, int D, bool RHS>
+struct LftElem {
+  static constexpr int DD = D * D;
+  T P[DD], Q[DD], R[DD], p[D], r[D];
+  int empty;  // 1: identity (nothing combined yet)
+  __device__ __forceinline__ void clear() {
+    empty = 1;
+#pragma unroll
+    for (int i = 0; i < DD; ++i) P[i] = Q[i] = R[i] = T(0);
+#pragma unroll
+    for (int i = 0; i < D; ++i) p[i] = r[i] = T(0);
+  }
+  // this <- (this then later); returns false if S = P1 + R2 is not positive definite
+  __device__ __forceinline__ bool then(const LftElem& e2) {
+    if (e2.empty) return true;
+    if (empty) {
+      *this = e2;
+      return true;
+    }
+    T S[DD], rinv[D], Y[DD], Z[DD], u[D];
+#pragma unroll
+    for (int i = 0; i < DD; ++i) S[i] = P[i] + e2.R[i];
+    const bool ok = chol_lower<T, D>(S, rinv);
+#pragma unroll
+    for (int i = 0; i < DD; ++i) Y[i] = Q[i];
+    trsm_left_lower<T, D>(S, rinv, Y);
+    trsm_left_lower_t<T, D>(S, rinv, Y);  // Y = S^{-1} Q1
+#pragma unroll
+    for (int a = 0; a < D; ++a)
+#pragma unroll
+      for (int b = 0; b < D; ++b) Z[a * D + b] = e2.Q[b * D + a];
+    trsm_left_lower<T, D>(S, rinv, Z);
+    trsm_left_lower_t<T, D>(S, rinv, Z);  // Z = S^{-1} Q2^T
+#pragma unroll
+    for (int i = 0; i < D; ++i) u[i] = p[i] + e2.r[i];
+    trsv_lower<T, D>(S, rinv, u);
+    trsv_lower_t<T, D>(S, rinv, u);  // u = S^{-1} (p1 + r2)
+    T Pn[DD], Qn[DD], Rn[DD], pn[D], rn[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a)
+#pragma unroll
+      for (int b = 0; b < D; ++b) {
+        T vp = e2.P[a * D + b], vq = T(0), vr = R[a * D + b];
+#pragma unroll
+        for (int s = 0; s < D; ++s) {
+          vp = Num<T>::fma(-e2.Q[a * D + s], Z[s * D + b], vp);
+          vq = Num<T>::fma(e2.Q[a * D + s], Y[s * D + b], vq);
+          vr = Num<T>::fma(-Q[s * D + a], Y[s * D + b], vr);
+        }
+        Pn[a * D + b] = vp;
+        Qn[a * D + b] = vq;
+        Rn[a * D + b] = vr;
+      }
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      T vp = e2.p[a], vr = r[a];
+#pragma unroll
+      for (int s = 0; s < D; ++s) {
+        vp = Num<T>::fma(e2.Q[a * D + s], u[s], vp);
+        vr = Num<T>::fma(Q[s * D + a], u[s], vr);
+      }
+      pn[a] = vp;
+      rn[a] = vr;
+    }
+#pragma unroll
+    for (int a = 0; a < D; ++a)
+#pragma unroll
+      for (int b = 0; b <= a; ++b) {  // P and R are symmetric: keep them exactly so
+        P[a * D + b] = P[b * D + a] = Pn[a * D + b];
+        R[a * D + b] = R[b * D + a] = Rn[a * D + b];
+      }
+#pragma unroll
+    for (int i = 0; i < DD; ++i) Q[i] = Qn[i];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      p[i] = pn[i];
+      r[i] = rn[i];
+    }
+    return ok;
+  }
+  __device__ __forceinline__ void shfl_up_from(const LftElem& src, int delta) {
+#pragma unroll
+    for (int i = 0; i < DD; ++i) {
+      P[i] = __shfl_up_sync(0xffffffffu, src.P[i], delta);
+      Q[i] = __shfl_up_sync(0xffffffffu, src.Q[i], delta);
+      R[i] = __shfl_up_sync(0xffffffffu, src.R[i], delta);
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      p[i] = RHS ? __shfl_up_sync(0xffffffffu, src.p[i], delta) : T(0);
+      r[i] = RHS ? __shfl_up_sync(0xffffffffu, src.r[i], delta) : T(0);
+    }
+    empty = __shfl_up_sync(0xffffffffu, src.empty, delta);
+  }
+};
 
 // ---------------------------------------------------------------------------------------------
 // naturals -> SSM parameters: backward U D U^T sweep (nat_to_ssm_kernel in nat_kernels.cuh has the
@@ -765,8 +869,8 @@ struct NatToSsmCore : NatGeomBase<T_, D> {
 #pragma unroll
     for (int i = 0; i < D; ++i) z[i] = T(0);
     if (n_ > 0 && k0_ + n_ < p.Tn) {  // not the last segment: factor the seed D entering it
-      load_vec<T, DD>(S, p.out_chol + (c * p.Tn + k0_) * DD);
-      load_vec<T, D>(z, p.out_off + (c * p.Tn + k0_) * D);
+      load_vec_rw<T, DD>(S, p.out_chol + (c * p.Tn + k0_) * DD);
+      load_vec_rw<T, D>(z, p.out_off + (c * p.Tn + k0_) * D);
       const bool ok = chol_lower<T, D>(S, rinv);
       if (!ok) fail = (int32_t)(k0_ + n_ + 1);
     }
@@ -979,72 +1083,96 @@ struct NatSummaryCore : NatGeomBase<T_, D> {
   }
 };
 
-// pass 2: one thread per chain folds the elements from the last segment down and parks the state
-// (D, z) entering every segment s < P-1 in that segment's first output slots.
-template <typename T, int D>
-__global__ void __launch_bounds__(128)
-nat_seed_kernel(const NatToSsmParams<T> p) {
-  constexpr int DD = D * D;
-  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+// Fold of the elements of a BACKWARD linear-fractional sweep (naturals -> SSM, U D U^T), in sweep
+// order it = 0..P-1 <-> segment P-1-it.  The state entering segment s < P-1 is (P, p) of the
+// combined element of the segments above it (LftElem).  WARP = false: one thread per chain;
+// WARP = true (many segments): one warp per chain, lane l owns sweep positions [l*m, (l+1)*m),
+// combines them, the warp scans the composites, every lane walks its positions from its prefix.
+// Policy: static void load(Elem&, params, c, k0, n, last)  -- element parked by the summary pass
+//         static void seed(params, c, k0, const Elem&)      -- park the state entering the segment
+template <typename T, int D, bool VEC, class Policy, class Params, bool WARP>
+__device__ __forceinline__ void lft_backward_fold(const Params& p, int32_t* info) {
+  using Elem = LftElem<T, D, VEC>;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t c = WARP ? tid / 32 : tid;
+  const int lane = WARP ? (int)(tid & 31) : 0;
   if (c >= p.B) return;
-  T Din[DD], zin[D];
+  const int64_t m = WARP ? (p.P + 31) / 32 : p.P;
+  const int64_t i0 = lane * m;
+  int64_t i1 = i0 + m;
+  if (i1 > p.P) i1 = p.P;
   int32_t fail = 0;
-  for (int64_t seg = p.P - 1; seg >= 0; --seg) {
-    const int64_t k0 = seg * p.L;
-    const int64_t n = seg_steps(p.Tn, k0, p.L);
-    if (n <= 0) continue;
-    const bool last = k0 + n >= p.Tn;
-    T Pm[DD], Q[DD], R[DD], pv[D], rv[D];
-    if (seg > 0) {  // element of this segment (loaded before its slots receive the seed)
-      load_vec<T, DD>(Pm, p.out_chol + (c * p.Tn + k0) * DD);
-      load_vec<T, D>(pv, p.out_off + (c * p.Tn + k0) * D);
-      if (!last) {
-        load_vec<T, DD>(R, p.out_chol + (c * p.Tn + k0 + 1) * DD);
-        load_vec<T, D>(rv, p.out_off + (c * p.Tn + k0 + 1) * D);
-        load_vec<T, DD>(Q, p.out_a + (c * (p.Tn - 1) + k0) * DD);
+  Elem X;
+  X.clear();
+  auto geom = [&](int64_t it, int64_t& k0, int64_t& n, bool& last) {
+    const int64_t seg = p.P - 1 - it;
+    k0 = seg * p.L;
+    n = seg_steps(p.Tn, k0, p.L);
+    last = k0 + n >= p.Tn;
+    return seg;
+  };
+  if (WARP) {
+    Elem e, other;
+    for (int64_t it = i0; it < i1 && it < p.P - 1; ++it) {  // the first segment feeds nobody
+      int64_t k0, n;
+      bool last;
+      geom(it, k0, n, last);
+      Policy::load(e, p, c, k0, n, last);
+      if (!X.then(e) && fail == 0) fail = (int32_t)(k0 + n + 1);
+    }
+#pragma unroll 1
+    for (int delta = 1; delta < 32; delta <<= 1) {
+      other.shfl_up_from(X, delta);
+      if (lane >= delta) {
+        if (!other.then(X) && fail == 0) fail = (int32_t)(p.Tn - i0 * p.L);
+        X = other;
       }
     }
-    if (!last) {
-      store_vec<T, DD>(p.out_chol + (c * p.Tn + k0) * DD, Din);
-      store_vec<T, D>(p.out_off + (c * p.Tn + k0) * D, zin);
-    }
+    other.shfl_up_from(X, 1);
+    X = other;
+    if (lane == 0) X.clear();
+  }
+  for (int64_t it = i0; it < i1; ++it) {
+    int64_t k0, n;
+    bool last;
+    const int64_t seg = geom(it, k0, n, last);
+    Elem e;
+    e.clear();
+    if (seg > 0) Policy::load(e, p, c, k0, n, last);  // before its slots receive the seed
+    if (it > 0) Policy::seed(p, c, k0, X);
     if (seg == 0) break;
-    if (last) {
-#pragma unroll
-      for (int i = 0; i < DD; ++i) Din[i] = Pm[i];
-#pragma unroll
-      for (int i = 0; i < D; ++i) zin[i] = pv[i];
-    } else {
-      // M = D_in + R = C C^T;  Y = M^{-1} Q^T;  D_out = P - Q Y;  z_out = p + Y^T (z_in + r)
-      T M[DD], rinv[D], Y[DD], u[D];
-#pragma unroll
-      for (int i = 0; i < DD; ++i) M[i] = Din[i] + R[i];
-      const bool ok = chol_lower<T, D>(M, rinv);
-      if (!ok && fail == 0) fail = (int32_t)(k0 + n + 1);
-#pragma unroll
-      for (int a = 0; a < D; ++a)
-#pragma unroll
-        for (int b = 0; b < D; ++b) Y[a * D + b] = Q[b * D + a];
-      trsm_left_lower<T, D>(M, rinv, Y);
-      trsm_left_lower_t<T, D>(M, rinv, Y);
-#pragma unroll
-      for (int i = 0; i < D; ++i) u[i] = zin[i] + rv[i];
-#pragma unroll
-      for (int i = 0; i < D; ++i) zin[i] = pv[i];
-      gemv_t_add<T, D>(zin, Y, u);
-#pragma unroll
-      for (int r = 0; r < D; ++r)
-#pragma unroll
-        for (int q = 0; q <= r; ++q) {
-          T v = Pm[r * D + q];
-#pragma unroll
-          for (int s = 0; s < D; ++s) v = Num<T>::fma(-Q[r * D + s], Y[s * D + q], v);
-          Din[r * D + q] = v;
-          Din[q * D + r] = v;
-        }
+    if (!X.then(e) && fail == 0) fail = (int32_t)(k0 + n + 1);
+  }
+  if (fail && info) atomicMax(info + c, fail);
+}
+
+struct NatFoldPolicy {
+  template <typename T, int D>
+  static __device__ __forceinline__ void load(LftElem<T, D, true>& e, const NatToSsmParams<T>& p,
+                                              int64_t c, int64_t k0, int64_t n, bool last) {
+    constexpr int DD = D * D;
+    e.clear();
+    e.empty = 0;
+    load_vec_rw<T, DD>(e.P, p.out_chol + (c * p.Tn + k0) * DD);
+    load_vec_rw<T, D>(e.p, p.out_off + (c * p.Tn + k0) * D);
+    if (!last) {
+      load_vec_rw<T, DD>(e.R, p.out_chol + (c * p.Tn + k0 + 1) * DD);
+      load_vec_rw<T, D>(e.r, p.out_off + (c * p.Tn + k0 + 1) * D);
+      load_vec_rw<T, DD>(e.Q, p.out_a + (c * (p.Tn - 1) + k0) * DD);
     }
   }
-  if (fail && p.info) atomicMax(p.info + c, fail);
+  template <typename T, int D>
+  static __device__ __forceinline__ void seed(const NatToSsmParams<T>& p, int64_t c, int64_t k0,
+                                              const LftElem<T, D, true>& X) {
+    store_vec<T, D * D>(p.out_chol + (c * p.Tn + k0) * D * D, X.P);
+    store_vec<T, D>(p.out_off + (c * p.Tn + k0) * D, X.p);
+  }
+};
+
+template <typename T, int D, bool WARP>
+__global__ void __launch_bounds__(128)
+nat_seed_kernel(const NatToSsmParams<T> p) {
+  lft_backward_fold<T, D, true, NatFoldPolicy, NatToSsmParams<T>, WARP>(p, p.info);
 }
 
 // ---------------------------------------------------------------------------------------------

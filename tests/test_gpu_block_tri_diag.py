@@ -473,7 +473,8 @@ def test_upper_diagonal_lower_parallel_in_time(d, dtype):
 
     _, S = _mods()
     lib = _lib.lib()
-    for b, t, seg in ((1, 1500, 0), (2, 301, 0), (3, 400, 7), (2, 131, 65), (2, 129, 2)):
+    # (3, 400, 3) and (2, 129, 2): more than 64 segments per chain -> warp-scan fold of the elements
+    for b, t, seg in ((1, 1500, 0), (2, 301, 0), (3, 400, 7), (3, 400, 3), (2, 131, 65), (2, 129, 2)):
         diag, sub, _, _ = random_well_conditioned_spd_btd((b,), t, d, rng=23 * d + t)
         if dtype == torch.float32:
             diag, sub = (a.astype(np.float32).astype(np.float64) for a in (diag, sub))

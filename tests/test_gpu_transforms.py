@@ -166,7 +166,8 @@ def test_naturals_to_ssm_params_parallel_in_time_short_segments_and_failure():
     mu0, l0, a, bb, lq = arrays
     th = mf.ssm_to_naturals(make_ssm(arrays))
     lib = _lib.lib()
-    for seg in (4, 7, 50, 100, 199):  # knob 3: steps per segment (ragged last segments included)
+    # knob 3: steps per segment (ragged last segments included); > 64 segments: warp-scan fold
+    for seg in (2, 3, 4, 7, 50, 100, 199):
         lib.mf_set_tuning(3, seg)
         try:
             got = mf.naturals_to_ssm_params(*th)
