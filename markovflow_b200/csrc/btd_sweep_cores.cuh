@@ -144,42 +144,14 @@ struct BtdSolveCore {
   }
 };
 
-// fold of the segment elements of one rhs chain (one thread per chain), in sweep order; parks the x
-// entering every segment in that segment's seed slot.
-template <typename T, int D, bool TRANSPOSE>
+// fold of the segment elements of one rhs chain in sweep order (affine_fold in ssm_sweep.cuh); parks
+// the x entering every segment in that segment's seed slot.
+template <typename T, int D, bool TRANSPOSE, bool WARP>
 __global__ void __launch_bounds__(128)
 btd_solve_seed_kernel(const BtdSolveParams<T> p) {
-  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (c >= p.n) return;
-  T x[D];
-#pragma unroll
-  for (int i = 0; i < D; ++i) x[i] = T(0);
-  const int64_t nseg = (p.Tn + p.L - 1) / p.L;
-  for (int64_t it = 0; it < nseg; ++it) {
-    const int64_t seg = TRANSPOSE ? nseg - 1 - it : it;
-    const int64_t k0 = seg * p.L;
-    const int64_t n = seg_steps(p.Tn, k0, p.L);
-    const bool live = it + 1 < nseg;  // feeds a later segment of the sweep
-    T cv[D], Phi[D * D];
-    if (live) {
-      load_vec_rw<T, D>(cv, p.out + (c * p.Tn + solve_slot<TRANSPOSE>(k0, n, 0)) * D);
-#pragma unroll
-      for (int q = 0; q < D; ++q)
-        load_vec_rw<T, D>(Phi + q * D, p.out + (c * p.Tn + solve_slot<TRANSPOSE>(k0, n, q + 1)) * D);
-    }
-    if (it > 0) store_vec<T, D>(p.out + (c * p.Tn + solve_slot<TRANSPOSE>(k0, n, 0)) * D, x);
-    if (!live) break;
-    T y[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-      T v = cv[i];
-#pragma unroll
-      for (int q = 0; q < D; ++q) v = Num<T>::fma(Phi[q * D + i], x[q], v);
-      y[i] = v;
-    }
-#pragma unroll
-    for (int i = 0; i < D; ++i) x[i] = y[i];
-  }
+  affine_fold<T, D, TRANSPOSE, WARP>(p.out, p.n, p.Tn, p.P, p.L, [](int64_t k0, int64_t n, int i) {
+    return solve_slot<TRANSPOSE>(k0, n, i);
+  });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -295,45 +267,109 @@ struct BtdInvSubsetCore {
   }
 };
 
-// fold from the last segment down; parks the Sigma entering every segment s < P-1 in od[k0]
+// Element of a range of steps of the inverse-subset recursion: Sigma_out = Phi^T Sigma_in Phi + Gt.
+// (e1 then e2): Phi = Phi1 Phi2, Gt = Phi2^T Gt1 Phi2 + Gt2.
 template <typename T, int D>
+struct CongElem {
+  T Phi[D * D], Gt[D * D];
+  int empty;
+  __device__ __forceinline__ void clear() {
+    empty = 1;
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) {
+      Phi[i] = (i / D == i % D) ? T(1) : T(0);
+      Gt[i] = T(0);
+    }
+  }
+  __device__ __forceinline__ void then(const CongElem& e2) {
+    if (e2.empty) return;
+    if (empty) {
+      *this = e2;
+      return;
+    }
+    T t[D * D], GP[D * D];
+    gemm<T, D>(t, Phi, e2.Phi);
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) Phi[i] = t[i];
+    gemm<T, D>(GP, Gt, e2.Phi);  // Gt1 Phi2
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+      for (int q = 0; q <= r; ++q) {
+        T v = e2.Gt[r * D + q];
+#pragma unroll
+        for (int s = 0; s < D; ++s) v = Num<T>::fma(e2.Phi[s * D + r], GP[s * D + q], v);
+        Gt[r * D + q] = v;
+        Gt[q * D + r] = v;
+      }
+  }
+  __device__ __forceinline__ void shfl_up_from(const CongElem& src, int delta) {
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) {
+      Phi[i] = __shfl_up_sync(0xffffffffu, src.Phi[i], delta);
+      Gt[i] = __shfl_up_sync(0xffffffffu, src.Gt[i], delta);
+    }
+    empty = __shfl_up_sync(0xffffffffu, src.empty, delta);
+  }
+};
+
+// fold from the last segment down (sweep position it <-> segment P-1-it); parks the Sigma entering
+// every segment s < P-1 in od[k0].  The last segment has nothing entering (its Phi is 0), so the
+// state after a prefix of the sweep is simply Gt of the combined element.  WARP: one warp per
+// chain, lane l owns sweep positions [l*m, (l+1)*m).
+template <typename T, int D, bool WARP>
 __global__ void __launch_bounds__(128)
 btd_inv_subset_seed_kernel(const BtdInvSubsetParams<T> p) {
   constexpr int DD = D * D;
-  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  using Elem = CongElem<T, D>;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t c = WARP ? tid / 32 : tid;
+  const int lane = WARP ? (int)(tid & 31) : 0;
   if (c >= p.B) return;
-  T sig[DD];
+  const int64_t m = WARP ? (p.P + 31) / 32 : p.P;
+  const int64_t i0 = lane * m;
+  int64_t i1 = i0 + m;
+  if (i1 > p.P) i1 = p.P;
+  auto load = [&](Elem& e, int64_t it) {
+    const int64_t k0 = (p.P - 1 - it) * p.L;
+    e.clear();
+    e.empty = 0;
+    load_vec_rw<T, DD>(e.Gt, p.od + (c * p.Tn + k0) * DD);
+    if (it > 0) load_vec_rw<T, DD>(e.Phi, p.od + (c * p.Tn + k0 + 1) * DD);
+    else {
 #pragma unroll
-  for (int i = 0; i < DD; ++i) sig[i] = T(0);
-  for (int64_t seg = p.P - 1; seg >= 0; --seg) {
-    const int64_t k0 = seg * p.L;
-    const int64_t n = seg_steps(p.Tn, k0, p.L);
-    if (n <= 0) continue;
-    const bool last = k0 + n >= p.Tn;
-    T Gt[DD], Phi[DD];
-    if (seg > 0) {
-      load_vec_rw<T, DD>(Gt, p.od + (c * p.Tn + k0) * DD);
-      if (!last) load_vec_rw<T, DD>(Phi, p.od + (c * p.Tn + k0 + 1) * DD);
+      for (int i = 0; i < DD; ++i) e.Phi[i] = T(0);
     }
-    if (!last) store_vec<T, DD>(p.od + (c * p.Tn + k0) * DD, sig);
-    if (seg == 0) break;
-    if (last) {
-#pragma unroll
-      for (int i = 0; i < DD; ++i) sig[i] = Gt[i];
-    } else {
-      T SP[DD];
-      gemm<T, D>(SP, sig, Phi);  // Sigma Phi
-#pragma unroll
-      for (int r = 0; r < D; ++r)
-#pragma unroll
-        for (int q = 0; q <= r; ++q) {
-          T v = Gt[r * D + q];
-#pragma unroll
-          for (int s = 0; s < D; ++s) v = Num<T>::fma(Phi[s * D + r], SP[s * D + q], v);
-          sig[r * D + q] = v;
-          sig[q * D + r] = v;
-        }
+  };
+  Elem X;
+  X.clear();
+  if (WARP) {
+    Elem e, other;
+    for (int64_t it = i0; it < i1 && it < p.P - 1; ++it) {  // segment 0 feeds nobody
+      load(e, it);
+      X.then(e);
     }
+#pragma unroll 1
+    for (int delta = 1; delta < 32; delta <<= 1) {
+      other.shfl_up_from(X, delta);
+      if (lane >= delta) {
+        other.then(X);
+        X = other;
+      }
+    }
+    other.shfl_up_from(X, 1);
+    X = other;
+    if (lane == 0) X.clear();
+  }
+  for (int64_t it = i0; it < i1; ++it) {
+    const int64_t k0 = (p.P - 1 - it) * p.L;
+    Elem e;
+    e.clear();
+    const bool live = it + 1 < p.P;
+    if (live) load(e, it);  // before its slot receives the seed
+    if (it > 0) store_vec<T, DD>(p.od + (c * p.Tn + k0) * DD, X.Gt);
+    if (!live) break;
+    X.then(e);
   }
 }
 

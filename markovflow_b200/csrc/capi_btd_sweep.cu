@@ -67,14 +67,15 @@ int btd_sweep_solve(int dtype, int64_t D, const void* ld, const void* ls, const 
     // few long chains with a recursion (sub-diagonal): parallel in time; the output slots serve as
     // scratch, so not when out aliases rhs
     // (block-diagonal matrices have no recursion at all: their segments are simply independent)
-    if (tuning(2) != 1 && T >= 128 && (!ls || out != rhs)) plan_pit(n, T, kD + 2, &p.P, &p.L);
+    if (tuning(2) != 1 && T >= 128 && (!ls || out != rhs)) plan_pit(n, T, kD + 2, &p.P, &p.L, false);
     const int v = (transpose ? 4 : 0) | (ld ? 0 : 2) | (ls ? 1 : 0);
     auto go = [&](auto tr, auto unit, auto sub) -> int {
       constexpr bool kT = decltype(tr)::value, kU = decltype(unit)::value, kS = decltype(sub)::value;
       if (p.P > 1 && kS) {
         int rc = run<BtdSolveCore<Tp, kD, kT, kU, kS, true>>(p, n * p.P, s);
         if (rc != MF_OK) return rc;
-        btd_solve_seed_kernel<Tp, kD, kT><<<grid_for(n, 128), 128, 0, s>>>(p);
+        if (p.P > 64) btd_solve_seed_kernel<Tp, kD, kT, true><<<grid_for(n * 32, 128), 128, 0, s>>>(p);
+        else btd_solve_seed_kernel<Tp, kD, kT, false><<<grid_for(n, 128), 128, 0, s>>>(p);
         rc = check_launch();
         if (rc != MF_OK) return rc;
       }
@@ -101,11 +102,12 @@ int btd_sweep_inverse_subset(int dtype, int64_t D, const void* ld, const void* l
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
     BtdInvSubsetParams<Tp> p{(const Tp*)ld, (const Tp*)ls, (Tp*)od, (Tp*)os, B, T, 1, T};
-    if (tuning(2) != 1 && T >= 128 && od != ld) plan_pit(B, T, 2, &p.P, &p.L);
+    if (tuning(2) != 1 && T >= 128 && od != ld) plan_pit(B, T, 2, &p.P, &p.L, false);
     if (p.P > 1) {
       int rc = run<BtdInvSubsetCore<Tp, kD, false, true>>(p, B * p.P, s);
       if (rc != MF_OK) return rc;
-      btd_inv_subset_seed_kernel<Tp, kD><<<grid_for(B, 128), 128, 0, s>>>(p);
+      if (p.P > 64) btd_inv_subset_seed_kernel<Tp, kD, true><<<grid_for(B * 32, 128), 128, 0, s>>>(p);
+      else btd_inv_subset_seed_kernel<Tp, kD, false><<<grid_for(B, 128), 128, 0, s>>>(p);
       rc = check_launch();
       if (rc != MF_OK) return rc;
     }

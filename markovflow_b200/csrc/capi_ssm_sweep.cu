@@ -87,10 +87,6 @@ int ssm_sweep_affine(int dtype, int64_t D, const void* mu0, const void* chol_p0,
                           (const Tp*)chol_q, (const Tp*)eps, (Tp*)out, n, Bm, T, 1, T};
     if (tuning(2) != 1 && T >= 128 && out != eps) {
       plan_segments(n, T, &p.P, &p.L);
-      if (p.P > 512) {  // the seeds are folded sequentially per chain
-        p.L = (T + 511) / 512;
-        p.P = (T + p.L - 1) / p.L;
-      }
       if (p.L < kD + 2) { p.P = 1; p.L = T; }
     }
     auto go = [&](auto noise) -> int {
@@ -98,7 +94,8 @@ int ssm_sweep_affine(int dtype, int64_t D, const void* mu0, const void* chol_p0,
       if (p.P > 1) {
         int rc = run<SsmAffineCore<Tp, kD, kN, true>>(p, n * p.P, s);
         if (rc != MF_OK) return rc;
-        ssm_affine_seed_kernel<Tp, kD><<<grid_for(n, 128), 128, 0, s>>>(p);
+        if (p.P > 64) ssm_affine_seed_kernel<Tp, kD, true><<<grid_for(n * 32, 128), 128, 0, s>>>(p);
+        else ssm_affine_seed_kernel<Tp, kD, false><<<grid_for(n, 128), 128, 0, s>>>(p);
         rc = check_launch();
         if (rc != MF_OK) return rc;
       }

@@ -412,6 +412,134 @@ ssm_moments_seed_kernel(const SsmMomentsParams<T> p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Element of a range of steps of a VECTOR-affine recursion x_out = Phi x_in + c (triangular solves,
+// means, samples).  Phi is stored column by column (column q at Phi[q*D ..]), as the summary passes
+// produce it.  (e1 then e2): Phi = Phi2 Phi1, c = Phi2 c1 + c2.
+template <typename T, int D>
+struct AffElem {
+  T Phi[D * D], c[D];
+  int empty;
+  __device__ __forceinline__ void clear() {
+    empty = 1;
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) Phi[i] = (i / D == i % D) ? T(1) : T(0);
+#pragma unroll
+    for (int i = 0; i < D; ++i) c[i] = T(0);
+  }
+  __device__ __forceinline__ void then(const AffElem& e2) {
+    if (e2.empty) return;
+    if (empty) {
+      *this = e2;
+      return;
+    }
+    T Pn[D * D], cn[D];
+#pragma unroll
+    for (int q = 0; q < D; ++q)  // column q of Phi2 Phi1 = Phi2 (column q of Phi1)
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        T v = T(0);
+#pragma unroll
+        for (int s2 = 0; s2 < D; ++s2) v = Num<T>::fma(e2.Phi[s2 * D + i], Phi[q * D + s2], v);
+        Pn[q * D + i] = v;
+      }
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      T v = e2.c[i];
+#pragma unroll
+      for (int s2 = 0; s2 < D; ++s2) v = Num<T>::fma(e2.Phi[s2 * D + i], c[s2], v);
+      cn[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) Phi[i] = Pn[i];
+#pragma unroll
+    for (int i = 0; i < D; ++i) c[i] = cn[i];
+  }
+  // x <- Phi x + c
+  __device__ __forceinline__ void apply(T* __restrict__ x) const {
+    T y[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      T v = c[i];
+#pragma unroll
+      for (int q = 0; q < D; ++q) v = Num<T>::fma(Phi[q * D + i], x[q], v);
+      y[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) x[i] = y[i];
+  }
+  __device__ __forceinline__ void shfl_up_from(const AffElem& src, int delta) {
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) Phi[i] = __shfl_up_sync(0xffffffffu, src.Phi[i], delta);
+#pragma unroll
+    for (int i = 0; i < D; ++i) c[i] = __shfl_up_sync(0xffffffffu, src.c[i], delta);
+    empty = __shfl_up_sync(0xffffffffu, src.empty, delta);
+  }
+};
+
+// Fold of the elements of a vector-affine sweep over `out` [n,T,D] in sweep order it = 0..P-1
+// (segment it, or P-1-it when BACKWARD).  slot(k0, n, i) is the output step that holds parked vector
+// i (0: c | seed, 1..D: columns of Phi) of segment [k0, k0+n).  The first segment of the sweep starts
+// from a known state (x0; its parked c already is the state at its end), so its Phi is ignored.
+// WARP: one warp per chain, lane l owns sweep positions [l*m, (l+1)*m).
+template <typename T, int D, bool BACKWARD, bool WARP, class Slot>
+__device__ __forceinline__ void affine_fold(T* out, int64_t nchains, int64_t Tn, int64_t P, int64_t L,
+                                            Slot slot) {
+  using Elem = AffElem<T, D>;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t c = WARP ? tid / 32 : tid;
+  const int lane = WARP ? (int)(tid & 31) : 0;
+  if (c >= nchains) return;
+  const int64_t m = WARP ? (P + 31) / 32 : P;
+  const int64_t i0 = lane * m;
+  int64_t i1 = i0 + m;
+  if (i1 > P) i1 = P;
+  T* o = out + c * Tn * D;
+  auto load = [&](Elem& e, int64_t it) {
+    const int64_t seg = BACKWARD ? P - 1 - it : it;
+    const int64_t k0 = seg * L, n = seg_steps(Tn, k0, L);
+    e.empty = 0;
+    load_vec_rw<T, D>(e.c, o + slot(k0, n, 0) * D);
+#pragma unroll
+    for (int q = 0; q < D; ++q) load_vec_rw<T, D>(e.Phi + q * D, o + slot(k0, n, q + 1) * D);
+    if (it == 0) {  // starts from the known initial state: x_out = c whatever enters
+#pragma unroll
+      for (int i = 0; i < D * D; ++i) e.Phi[i] = T(0);
+    }
+  };
+  Elem X;
+  X.clear();
+  if (WARP) {
+    Elem e, other;
+    for (int64_t it = i0; it < i1 && it < P - 1; ++it) {  // the last segment of the sweep feeds nobody
+      load(e, it);
+      X.then(e);
+    }
+#pragma unroll 1
+    for (int delta = 1; delta < 32; delta <<= 1) {
+      other.shfl_up_from(X, delta);
+      if (lane >= delta) {
+        other.then(X);
+        X = other;
+      }
+    }
+    other.shfl_up_from(X, 1);
+    X = other;
+    if (lane == 0) X.clear();
+  }
+  for (int64_t it = i0; it < i1; ++it) {
+    const int64_t seg = BACKWARD ? P - 1 - it : it;
+    const int64_t k0 = seg * L, n = seg_steps(Tn, k0, L);
+    Elem e;
+    e.clear();
+    const bool live = it + 1 < P;
+    if (live) load(e, it);  // before its slot receives the seed
+    if (it > 0) store_vec<T, D>(o + slot(k0, n, 0) * D, X.c);  // state entering = c of the prefix (Phi x0 term is 0)
+    if (!live) break;
+    X.then(e);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // x_k = A_k x_{k-1} + b_k (+ chol_q eps): affine in x, so few long chains run parallel in time: the
 // SUMMARY pass composes every segment into (Phi, c) by running the recursion on c and on the columns
 // of Phi, ssm_affine_seed_kernel folds them per chain, and the segments restart from their seeds.
@@ -530,43 +658,13 @@ struct SsmAffineCore {
   }
 };
 
-// fold of the segment elements of one chain; parks x_{k0-1} in the seed slot of every segment s >= 1.
-// Segment 0 starts from mu0 (+ noise), so its element already is the state at its end: Phi unused.
-template <typename T, int D>
+// fold of the segment elements of one chain (affine_fold): parks x_{k0-1} in the seed slot (the last
+// output step) of every segment s >= 1; the vectors of an element sit in the last D+1 steps.
+template <typename T, int D, bool WARP>
 __global__ void __launch_bounds__(128)
 ssm_affine_seed_kernel(const SsmAffineParams<T> p) {
-  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (c >= p.n) return;
-  T x[D];
-#pragma unroll
-  for (int i = 0; i < D; ++i) x[i] = T(0);
-  for (int64_t seg = 0; seg < p.P; ++seg) {
-    const int64_t k0 = seg * p.L;
-    const int64_t n = seg_steps(p.Tn, k0, p.L);
-    if (n <= 0) break;
-    const int64_t kl = k0 + n - 1;
-    const bool live = (seg + 1) * p.L < p.Tn;
-    T cv[D], Phi[D * D];
-    if (live) {
-      load_vec_rw<T, D>(cv, p.out + (c * p.Tn + kl) * D);
-#pragma unroll
-      for (int q = 0; q < D; ++q) load_vec_rw<T, D>(Phi + q * D, p.out + (c * p.Tn + kl - 1 - q) * D);
-    }
-    if (seg > 0) store_vec<T, D>(p.out + (c * p.Tn + kl) * D, x);
-    if (!live) break;
-    T y[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-      T v = cv[i];
-      if (seg > 0) {
-#pragma unroll
-        for (int q = 0; q < D; ++q) v = Num<T>::fma(Phi[q * D + i], x[q], v);
-      }
-      y[i] = v;
-    }
-#pragma unroll
-    for (int i = 0; i < D; ++i) x[i] = y[i];
-  }
+  affine_fold<T, D, false, WARP>(p.out, p.n, p.Tn, p.P, p.L,
+                                 [](int64_t k0, int64_t n, int i) { return k0 + n - 1 - i; });
 }
 
 // ---------------------------------------------------------------------------------------------

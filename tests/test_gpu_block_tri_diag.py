@@ -442,7 +442,8 @@ def test_solve_parallel_in_time(d, unit, transpose_left, dtype):
 
     L, _ = _mods()
     lib = _lib.lib()
-    for b, t, seg in ((1, 1500, 0), (2, 301, 0), (3, 400, 7), (2, 131, 65)):
+    # (3, 700, 7): 100 segments per chain -> warp-scan fold of the elements
+    for b, t, seg in ((1, 1500, 0), (2, 301, 0), (3, 400, 7), (3, 700, 7), (2, 131, 65)):
         _, _, ld, ls = random_well_conditioned_spd_btd((b,), t, d, rng=17 * d + t)
         if unit:
             ld = np.broadcast_to(np.eye(d), ld.shape).copy()

@@ -453,7 +453,8 @@ def test_means_and_samples_parallel_in_time(d, dtype):
     from markovflow_b200 import _lib
 
     lib = _lib.lib()
-    for b, t, seg in ((1, 1500, 0), (2, 301, 0), (3, 400, 9), (2, 131, 65)):
+    # (3, 700, 7): 100 segments per chain -> warp-scan fold of the elements
+    for b, t, seg in ((1, 1500, 0), (2, 301, 0), (3, 400, 9), (3, 700, 7), (2, 131, 65)):
         state = np.random.get_state()
         np.random.seed(t * 10 + d)
         arrays = random_ssm_arrays((b,), t - 1, d, scale_a=0.6 / np.sqrt(d))
