@@ -530,3 +530,57 @@ def test_inverse_subset_parallel_in_time(d, dtype):
             assert max_rel_err(got[knob][1], o_s) < TOL[dtype]
             assert max_rel_err(npy(only_d), o_d) < TOL[dtype]
         assert max_rel_err(got[0][0], got[1][0]) < TOL[dtype]
+
+
+def _block_cholesky_longdouble(diag, sub):
+    """Block Cholesky in np.longdouble: a reference that separates the error of the two float64 paths
+    from the conditioning of the input."""
+    diag, sub = diag.astype(np.longdouble), sub.astype(np.longdouble)
+    t, d = diag.shape[0], diag.shape[-1]
+    ld, ls = np.zeros_like(diag), np.zeros_like(sub)
+    prev = None
+    for k in range(t):
+        s = diag[k].copy()
+        if prev is not None:
+            s -= prev @ prev.T
+        low = np.zeros((d, d), dtype=np.longdouble)
+        for j in range(d):
+            low[j, j] = np.sqrt(s[j, j] - (low[j, :j] ** 2).sum())
+            for i in range(j + 1, d):
+                low[i, j] = (s[i, j] - (low[i, :j] * low[j, :j]).sum()) / low[j, j]
+        ld[k] = low
+        if k + 1 < t:
+            x = np.zeros((d, d), dtype=np.longdouble)
+            for j in range(d):
+                x[:, j] = (sub[k][:, j] - x[:, :j] @ low[j, :j]) / low[j, j]
+            ls[k] = x
+            prev = x
+    return ld, ls
+
+
+@pytest.mark.parametrize("ratio", [0.2, 0.02])
+def test_parallel_in_time_is_as_accurate_as_the_sequential_sweep_on_ill_conditioned_input(ratio):
+    """Matern52 posterior precision of ONE series with dt / lengthscale ~ ratio (block condition
+    numbers 4e5 / 4e9): against a long-double factorisation the parallel-in-time path must not lose
+    accuracy relative to the sequential sweep (tools/pit_conditioning.py has the wider table)."""
+    from markovflow_b200 import _lib
+
+    _, S = _mods()
+    rng = np.random.default_rng(3)
+    t = 1500
+    tp = np.cumsum(ratio * rng.uniform(0.5, 1.5, size=t))
+    k = O.Matern52(1.0, 1.0)
+    diag, sub = O.kalman_k_inv_post(k.state_space_model(tp), k.emission_matrix(tp), np.array([[100.0]]))
+    ref_ld, ref_ls = _block_cholesky_longdouble(diag, sub)
+    lib = _lib.lib()
+    err = {}
+    for knob in (0, 1):
+        lib.mf_set_tuning(2, knob)
+        try:
+            c = S(tt(diag[None]), tt(sub[None])).cholesky
+        finally:
+            lib.mf_set_tuning(2, 0)
+        err[knob] = max(max_rel_err(npy(c.block_diagonal[0]), ref_ld.astype(np.float64)),
+                        max_rel_err(npy(c.block_sub_diagonal[0]), ref_ls.astype(np.float64)))
+    assert err[0] < 3.0 * err[1] + 1e-14, err
+    assert err[0] < 1e-10
