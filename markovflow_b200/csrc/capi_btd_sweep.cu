@@ -44,8 +44,9 @@ int run(const typename Core::Params& p, int64_t nchains, cudaStream_t s) {
 // segments per chain for a parallel-in-time sweep whose seeds are folded by one thread per chain
 static void plan_pit(int64_t chains, int64_t T, int min_len, int64_t* P, int64_t* L,
                      bool sequential_fold = true) {
+  // the three passes move ~1.5-2x the bytes of the sequential sweep: pays off below ~2000 chains
   const int64_t target = (int64_t)148 * 192;
-  int64_t np = chains >= target / 2 ? 1 : (target + chains - 1) / chains;
+  int64_t np = chains > 2048 ? 1 : (target + chains - 1) / chains;
   if (np > T / 64) np = T / 64;
   if (sequential_fold && np > 512) np = 512;
   if (tuning(3) > 1 && tuning(3) < T) np = (T + tuning(3) - 1) / tuning(3);

@@ -43,8 +43,10 @@ int run(const typename Core::Params& p, int64_t nchains, cudaStream_t s) {
 // Segments per chain for the parallel-in-time evaluation of an exact (affine) recurrence: enough
 // virtual chains to occupy the GPU, segments of at least 64 steps.
 static void plan_segments(int64_t B, int64_t T, int64_t* P, int64_t* L) {
+  // The three passes move ~1.5-2x the bytes of the sequential sweep, whose cost is T x (latency of a
+  // step) whatever B: parallel in time pays off below ~2000 chains (measured: B = 4096 is slower).
   const int64_t target = (int64_t)148 * 192;
-  int64_t p = B >= target / 2 ? 1 : (target + B - 1) / B;
+  int64_t p = B > 2048 ? 1 : (target + B - 1) / B;
   if (p > T / 64) p = T / 64;
   if (p < 1) p = 1;
   if (tuning(3) > 0 && tuning(3) < T) p = (T + tuning(3) - 1) / tuning(3);

@@ -137,10 +137,11 @@ struct SsmMomentsCore {
     return vgeom_states<T>(i == 0 ? p.o_vec : p.o_diag, c, p.Tn, eout(i), k0, n);
   }
   T mu[D], P[DD];
-  int64_t k0_;
+  int64_t k0_, n_;
   __device__ __forceinline__ void init(const Params& p, int64_t v) {
     const int64_t c = v / p.P;
     k0_ = (v % p.P) * p.L;
+    n_ = seg_steps(p.Tn, k0_, p.L);
     if (k0_ == 0) {
       T L[DD];
       load_vec<T, D>(mu, p.mu0 + c * D);
@@ -159,6 +160,7 @@ struct SsmMomentsCore {
   }
   __device__ __forceinline__ void tile(const Params& p, const T* const* in, T* const* out,
                                        int64_t j0, int ns) {
+    if (n_ - j0 < ns) ns = (int)(n_ - j0);  // ragged last segment
     for (int j = 0; j < ns; ++j) {
       if (k0_ + j0 + j > 0) {
         T A[DD], off[D], L[DD], AP[DD], E[DD];
@@ -1287,6 +1289,8 @@ struct SweepAuto {
       if (nchains <= (int64_t)148 * 48) return launch_chain_sweep<Core, 32, 8, 2, 2>(prm, nchains, s, true);
       // (measured: <32, 16, 2, 2> -- half the bulk copies per step but one compute warp per CTA --
       // is 0-45 % slower on the config-5 transforms: resident compute warps matter more)
+      // (measured: DIRECT stores, <64, 8, 2, 0> -- no output stages / storer threads, twice the CTAs
+      // per SM -- are 15-40 % slower than bulk stores from the output ring on the same transforms)
       return launch_chain_sweep<Core, 64, 8, 2, 2>(prm, nchains, s, true);
     } else if constexpr (choice == 1) {
       return launch_chain_sweep<Core, 32, 8, 2, 2>(prm, nchains, s, true);

@@ -69,18 +69,32 @@ struct SweepCfg {
   static constexpr int STAGE_IN = off_in(NIN);
   static constexpr int STAGE_OUT = off_out(NOUT);
   static constexpr int NSO_EFF = NOUT > 0 ? NSO : 0;
-  static constexpr int NJ_IN = NIN * C, NJ_OUT = NOUT * C;
+  // NSO == 0 with outputs: DIRECT mode -- the compute threads store their results straight to
+  // global memory (no output stages, no storer threads); one dump tile per stream absorbs the
+  // writes of streams that have no destination (optional outputs)
+  static constexpr bool DIRECT = NOUT > 0 && NSO == 0;
+  static constexpr int dump_bytes() {
+    int o = 0;
+    for (int i = 0; i < NOUT; ++i) o += (K * Core::eout(i) * ES + 15) / 16 * 16;
+    return DIRECT ? o : 0;
+  }
+  static constexpr int dump_off(int i) {
+    int o = 0;
+    for (int q = 0; q < i; ++q) o += (K * Core::eout(q) * ES + 15) / 16 * 16;
+    return o;
+  }
+  static constexpr int NJ_IN = NIN * C, NJ_OUT = DIRECT ? 0 : NOUT * C;
   static constexpr int NCW = C / 32;                               // compute warps
   static constexpr int NPW = (NJ_IN + NJ_OUT + 31) / 32;           // producer warps
   static constexpr int THREADS = 32 * (NCW + NPW);
   static constexpr int NBAR = 2 * NSI + 2 * NSO_EFF;
   static constexpr size_t SMEM_BYTES =
-      (size_t)STAGE_IN * NSI + (size_t)STAGE_OUT * NSO_EFF + sizeof(uint64_t) * NBAR + 16;
+      (size_t)STAGE_IN * NSI + (size_t)STAGE_OUT * NSO_EFF + dump_bytes() + sizeof(uint64_t) * NBAR + 16;
   static constexpr bool align_ok() {
     for (int i = 0; i < NIN; ++i)
       if ((K * Core::ein(i) * ES) % 16 != 0) return false;
     for (int i = 0; i < NOUT; ++i)
-      if ((K * Core::eout(i) * ES) % 16 != 0) return false;
+      if (!DIRECT && (K * Core::eout(i) * ES) % 16 != 0) return false;
     return true;
   }
   static constexpr bool FITS = align_ok() && SMEM_BYTES <= (size_t)232448 && THREADS <= 1024 &&
@@ -128,7 +142,8 @@ chain_sweep_kernel(const typename Core::Params prm, const int cpb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   char* in_stages = reinterpret_cast<char*>(smem_raw);
   char* out_stages = in_stages + (size_t)Cfg::STAGE_IN * NSI;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stages + (size_t)Cfg::STAGE_OUT * NSOE);
+  char* dump = out_stages + (size_t)Cfg::STAGE_OUT * NSOE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dump + Cfg::dump_bytes());
   uint64_t* full_in = bars;
   uint64_t* consumed = bars + NSI;
   uint64_t* full_out = bars + 2 * NSI;
@@ -192,7 +207,7 @@ chain_sweep_kernel(const typename Core::Params prm, const int cpb) {
         mbar_wait(consumed + (int)(t % NSI), (uint32_t)((t / NSI) & 1));  // tile t consumed
         issue_load(t + NSI);
       }
-    } else if (NOUT > 0) {
+    } else if (NOUT > 0 && !Cfg::DIRECT) {
       const int job = p - Cfg::NJ_IN;
       const int stream = job / C, c = job % C;
       const int64_t ch = chain0 + c;
@@ -204,8 +219,8 @@ chain_sweep_kernel(const typename Core::Params prm, const int cpb) {
       const bool valid = c < cpb && ch < nchains;
       const SweepSeg sg = make_seg(valid ? Core::out_geom(prm, stream, ch) : StreamGeom{nullptr, 0, 0}, valid);
       for (int64_t t = 0; t < ntiles; ++t) {
-        const int so = (int)(t % NSO);
-        mbar_wait(full_out + so, (uint32_t)((t / NSO) & 1));
+        const int so = (int)(t % (NSO > 0 ? NSO : 1));
+        mbar_wait(full_out + so, (uint32_t)((t / (NSO > 0 ? NSO : 1)) & 1));
         if (sg.g) {
           const int64_t j0 = tile_id(t) * K;
           int lo, hi, head;
@@ -239,10 +254,12 @@ chain_sweep_kernel(const typename Core::Params prm, const int cpb) {
     const StreamGeom g = valid ? Core::in_geom(prm, i, chain) : StreamGeom{nullptr, 0, 0};
     in_off[i] = Cfg::off_in(i) + c * Cfg::rs_in(i) + (int)(reinterpret_cast<uintptr_t>(g.step0) & 15);
   }
+  char* out_g[NOUT > 0 ? NOUT : 1];  // DIRECT: global address of the chain's local step 0
 #pragma unroll
   for (int i = 0; i < NOUT; ++i) {
     const StreamGeom g = valid ? Core::out_geom(prm, i, chain) : StreamGeom{nullptr, 0, 0};
     out_off[i] = Cfg::off_out(i) + c * Cfg::rs_out(i) + (int)(reinterpret_cast<uintptr_t>(g.step0) & 15);
+    out_g[i] = g.step0;
   }
   Core core;
   if (valid) core.init(prm, chain);
@@ -252,9 +269,9 @@ chain_sweep_kernel(const typename Core::Params prm, const int cpb) {
     const char* ist = in_stages + (size_t)si * Cfg::STAGE_IN;
     char* ost = nullptr;
     int so = 0;
-    if (NOUT > 0) {
-      so = (int)(t % NSO);
-      mbar_wait(empty_out + so, (uint32_t)(((t / NSO) & 1) ^ 1));
+    if (NOUT > 0 && !Cfg::DIRECT) {
+      so = (int)(t % (NSO > 0 ? NSO : 1));
+      mbar_wait(empty_out + so, (uint32_t)(((t / (NSO > 0 ? NSO : 1)) & 1) ^ 1));
       ost = out_stages + (size_t)so * Cfg::STAGE_OUT;
     }
     const int64_t j0 = tile_id(t) * K;
@@ -265,11 +282,17 @@ chain_sweep_kernel(const typename Core::Params prm, const int cpb) {
 #pragma unroll
       for (int i = 0; i < NIN; ++i) in[i] = reinterpret_cast<const T*>(ist + in_off[i]);
 #pragma unroll
-      for (int i = 0; i < NOUT; ++i) out[i] = reinterpret_cast<T*>(ost + out_off[i]);
+      for (int i = 0; i < NOUT; ++i) {
+        if (Cfg::DIRECT)
+          out[i] = out_g[i] ? reinterpret_cast<T*>(out_g[i] + j0 * (int64_t)(Core::eout(i) * ES))
+                            : reinterpret_cast<T*>(dump + Cfg::dump_off(i));
+        else
+          out[i] = reinterpret_cast<T*>(ost + out_off[i]);
+      }
       core.tile(prm, in, out, j0, ns);
     }
     mbar_arrive(consumed + si);
-    if (NOUT > 0) {
+    if (NOUT > 0 && !Cfg::DIRECT) {
       fence_proxy_async_smem();  // our shared-memory writes -> visible to the bulk stores
       mbar_arrive(full_out + so);
     }

@@ -38,6 +38,20 @@ def _seed():
     yield
 
 
+@pytest.fixture(autouse=True)
+def _tuning_from_env(request):
+    """A/B runs of the GPU suite under a kernel-variant knob: MF_TUNING="5=8,4=0" applies
+    mf_set_tuning(knob, value) before every GPU test (tests that set knobs restore them to 0)."""
+    spec = os.environ.get("MF_TUNING", "")
+    if spec and "gpu" in request.keywords:
+        from markovflow_b200 import _lib
+
+        for item in spec.split(","):
+            k, v = item.split("=")
+            _lib.lib().mf_set_tuning(int(k), int(v))
+    yield
+
+
 @pytest.fixture(params=[(3,), (), (2, 1)], ids=["b3", "b0", "b21"])
 def batch_shape(request):
     return request.param
