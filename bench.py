@@ -224,8 +224,9 @@ def extra_measurements(dev, rank, world, dist, peak):
             return kf.log_likelihood(), post.marginals
 
         ms = _timed(gpr_job, warm=2, reps=5)
+        ms_graph = _timed(mf.Graphed(gpr_job), warm=2, reps=10) if t1 <= 100_000 else None
         out[f"config1_gpr_single_series_T{t1}"] = {
-            "ms": ms, "state_steps_per_s": t1 / (ms * 1e-3),
+            "ms": ms, "ms_cuda_graph_replay": ms_graph, "state_steps_per_s": t1 / (ms * 1e-3),
             "workload": f"Matern32 D=2, ONE series T={t1}, f64: KalmanFilter.log_likelihood + "
                         "posterior_state_space_model + posterior marginals; every sweep parallel in time"}
         del ssm1, h1, y1, kf

@@ -16,6 +16,7 @@ from .conditionals import (
 from .config import set_check_numerics
 from .emission_model import EmissionModel
 from .gauss_markov import GaussMarkovDistribution, check_compatible
+from .graphs import Graphed
 from .kalman_filter import (
     BaseKalmanFilter,
     GaussianSites,
@@ -40,6 +41,7 @@ from .state_space_model import (
 )
 
 __all__ = [
+    "Graphed",
     "base_conditional_predict",
     "conditional_predict_from_transitions",
     "conditional_statistics_from_transitions",

@@ -511,3 +511,28 @@ def test_kl_divergence_parallel_in_time(d, dtype):
                 lib.mf_set_tuning(3, 0)
             assert max_rel_err(got[knob], want) < (1e-9 if dtype == torch.float64 else 2e-4)
         assert max_rel_err(got[0], got[1]) < (1e-10 if dtype == torch.float64 else 2e-4)
+
+
+def test_cuda_graph_replay_of_the_single_series_job():
+    """``markovflow_b200.Graphed``: log-likelihood + posterior SSM + posterior marginals of one series
+    recorded into a CUDA graph; replays track in-place updates of the inputs."""
+    import markovflow_b200 as mf
+
+    g, ssm_ref, h, _ = _filter_from_golden("b0")
+    y = tt(g["y"])
+    kf = mf.KalmanFilter(to_gpu_ssm(ssm_ref), mf.EmissionModel(tt(h)), y, tt(g["chol_R"]))
+
+    def job():
+        post = kf.posterior_state_space_model()
+        return kf.log_likelihood(), post.marginals
+
+    graphed = mf.Graphed(job)
+    ll_e, (m_e, c_e) = job()
+    ll_g, (m_g, c_g) = graphed()
+    assert max_rel_err(npy(ll_g), npy(ll_e)) < 1e-12
+    assert max_rel_err(npy(m_g), npy(m_e)) < 1e-12 and max_rel_err(npy(c_g), npy(c_e)) < 1e-12
+    y.mul_(1.5)  # new observations, same buffers
+    ll_e2, (m_e2, _) = job()
+    ll_g2, (m_g2, _) = graphed()
+    assert max_rel_err(npy(ll_g2), npy(ll_e2)) < 1e-12 and max_rel_err(npy(m_g2), npy(m_e2)) < 1e-12
+    assert abs(float(ll_e2) - float(ll_e)) > 1e-6

@@ -137,6 +137,14 @@ def gpr1():
             post = kf.posterior_state_space_model()
             return ll, post.marginals
 
+        if t <= 100_000:
+            g = mf.Graphed(job)
+            ms = timeit(g, warm=2, reps=10)
+            report(f"GPR single series T={t} D=2 f64: log-lik + posterior SSM + marginals [CUDA graph replay]", t,
+                   (2 * 4 + 2 + 2 + 1 + 3 * 4 + 2 * 2) * 8, ms)
+            ll_e, (m_e, c_e) = job()
+            ll_g, (m_g, c_g) = g()
+            assert torch.allclose(ll_e, ll_g) and torch.allclose(m_e, m_g) and torch.allclose(c_e, c_g)
         for knob, label in ((0, "parallel in time"), (1, "sequential sweeps")):
             if knob == 1 and t > 1_000_000:
                 continue  # ~10 s per call
