@@ -209,6 +209,34 @@ def extra_measurements(dev, rank, world, dist, peak):
             f"over {world} GPUs: local segment element, NCCL all-gather of {world} x 136 B, ordered fold",
             loglik=ll, loglik_single_gpu=ref, scaling="strong",
             frac_note="fraction of the AGGREGATE peak = frac_of_hbm_peak / n_gpus")
+    # ---- config 3 again with the SSM built INSIDE the kernel from the time deltas ------
+    # same series (same deltas, same observations): a step reads (dt_k, y_k) = 16 B instead of 104 B
+    from markovflow_b200.parallel import matern_time_segment, time_sharded_matern_log_likelihood
+    dts = bench_inputs.matern32_time_deltas(1, t3, dev)
+    y2 = y.reshape(1, t3).contiguous()
+    one = torch.ones(1, dtype=torch.float64, device=dev)
+    ll_mat = out["config3_kalman_loglik"].get("loglik_single_gpu") or out["config3_kalman_loglik"]["loglik"]
+    if world == 1:
+        fused = lambda: mf.matern_kalman_log_likelihood(2, one, one, y2, lr, time_deltas=dts)
+        ms = _timed(fused)
+        ll2 = float(fused()[0])
+        extra_kw = dict(scaling="single GPU", ms_cuda_graph_replay=_timed(mf.Graphed(fused), warm=2, reps=10))
+    else:
+        first, seg_dt, seg_y = matern_time_segment(dts, y2, rank, world)
+        fused = lambda: time_sharded_matern_log_likelihood(2, one, one, seg_dt, seg_y, lr, first)
+        ms = _timed(fused)
+        tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+        ll2 = float(fused()[0])
+        extra_kw = dict(scaling="strong", frac_note="fraction of the AGGREGATE peak = frac_of_hbm_peak / n_gpus")
+    e = entry(t3, 16, ms, workload="same series as config3_kalman_loglik, Matern32 A_k/Q_k built in "
+              "registers from dt_k (mf_kalman_matern_log_likelihood): arithmetic-bound, 16 B per step "
+              "cross HBM; speed-up over the materialised-SSM kernel = ratio of the two ms",
+              loglik=ll2, rel_diff_vs_materialised=abs(ll2 - ll_mat) / abs(ll_mat), **extra_kw)
+    e["equivalent_GBps_of_materialised_ssm"] = t3 * 104 / (ms * 1e-3) / 1e9
+    out["config3_kalman_loglik_from_time_deltas"] = e
+    del dts, y2
     del ssm, h, y
     torch.cuda.empty_cache()
     if rank != 0:

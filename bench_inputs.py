@@ -106,6 +106,19 @@ def matern32_ssm(b: int, t: int, device, seed: int = SEED, dt_lo: float = 0.05, 
     return mu0, chol_p0, a, offsets, chol_q, h
 
 
+def matern32_time_deltas(b: int, t: int, device, seed: int = SEED, dt_lo: float = 0.05,
+                         dt_hi: float = 0.15, chunk_t: int = 1 << 21):
+    """The time deltas ``[b, t-1]`` that :func:`matern32_ssm` (``jitter_hyper=False``: lengthscale =
+    variance = 1) drew for the same ``seed`` -- the input of the in-kernel SSM construction path."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    out = torch.empty(b, t - 1, dtype=torch.float64, device=device)
+    for k0 in range(0, t - 1, chunk_t):
+        n = min(chunk_t, t - 1 - k0)
+        out[:, k0:k0 + n] = dt_lo + (dt_hi - dt_lo) * torch.rand(b, n, generator=g, dtype=torch.float64,
+                                                                 device=device)
+    return out
+
+
 def kalman_inputs_config3(t: int, device, seed: int = SEED, noise: float = 0.1):
     """Config 3: ONE Matern32 series of ``t`` states, observations sampled from the model + noise."""
     from markovflow_b200 import StateSpaceModel

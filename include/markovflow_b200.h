@@ -51,7 +51,8 @@ const char* mf_last_cuda_error(void);
  * per chain, 2 parallel-in-time; also: 1 = no parallel-in-time evaluation of the moment recursions);
  * knob 3: steps per parallel-in-time segment (0 auto); knob 4: 1 = direct-load kernels instead of
  * the TMA chain sweeps; knob 7: large-block Cholesky (0/1 one warp per chain, 2 experimental
- * one-CTA-per-chain kernel). */
+ * one-CTA-per-chain kernel); knob 8: Matern-prior Kalman kernel (0 all-warps-compute kernel,
+ * 1..4 TMA chain-sweep geometries); knob 9: its virtual chains per SM, in warps (0 auto). */
 int mf_set_tuning(int knob, int value);
 
 /* ---------------------------------------------------------------------------------------------
@@ -184,10 +185,10 @@ int mf_kalman_log_likelihood(int dtype, const void* mu0, const void* chol_p0, co
  * segment of T local steps).  first_is_initial = 1: the segment starts at the prior (mu0, chol_p0)
  * and a/b/chol_q hold T-1 transitions; first_is_initial = 0: a/b/chol_q hold T transitions, a[k]
  * leading INTO local step k (mu0/chol_p0 unused).
- *   1. mf_kalman_segment_summary    -> out_elem [B, 3D^2+2D]: the segment's scan element
- *      (A, b, C, eta, J) (Sarkka & Garcia-Fernandez 2021); leaves per-thread summaries in workspace
+ *   1. mf_kalman_segment_summary    -> out_elem [B, 3D^2+2D+1]: the segment's scan element
+ *      (A, b, C, eta, J, ell) (Sarkka & Garcia-Fernandez 2021); leaves per-thread summaries in workspace
  *   2. all-gather the elements over ranks (NCCL), mf_kalman_fold_elements joins those of the
- *      earlier ranks: elems [n,B,3D^2+2D] -> out [B,3D^2+2D]
+ *      earlier ranks: elems [n,B,3D^2+2D+1] -> out [B,3D^2+2D+1]
  *   3. mf_kalman_log_likelihood_seeded  -> out [B]: this segment's share of the log-likelihood,
  *      given prefix_elem (NULL on the first rank); summaries_valid = 1 reuses step 1's workspace. */
 int mf_kalman_segment_summary(int dtype, const void* mu0, const void* chol_p0, const void* a,
@@ -204,6 +205,30 @@ int mf_kalman_log_likelihood_seeded(int dtype, const void* mu0, const void* chol
                                     int64_t h_batch, int64_t r_steps, int first_is_initial,
                                     int summaries_valid, void* workspace, size_t workspace_bytes,
                                     void* stream);
+
+/* KalmanFilter.log_likelihood of a stationary Matern prior with the state-space
+ * model built INSIDE the kernel from the time deltas.  Replaces, in one launch (+ one reduction),
+ *   SDEKernel.state_space_model (kernels/sde_kernel.py:153-171)
+ *     -> StationaryKernel.transition_statistics (:421-446,  Q_k = Pinf - A_k Pinf A_k^T + jitter I)
+ *     -> Matern12/32/52.state_transitions (kernels/matern.py:80-86, :299-324, :434-460)
+ *   SDEKernel.generate_emission_model (sde_kernel.py:173-211,  H = [1, 0, ...])
+ *   KalmanFilter.log_likelihood (kalman_filter.py:184-255)
+ * so that a step reads two values (dt_k, y_k) instead of the 2D^2+2D+1 of the materialised SSM.
+ *   D = 1: Matern12, 2: Matern32, 3: Matern52 (state_dim);  zero mean, output_dim 1.
+ *   lengthscale [B], variance [B] (per series), jitter (the kernel's jitter, sde_kernel.py:83-96),
+ *   time_deltas [B, T - first_is_initial], obs [B,T], chol_r [1].
+ *   first_is_initial = 1: the series starts at the stationary prior N(0, Pinf + jitter I);
+ *   first_is_initial = 0: a later time segment of a longer series (time_deltas[k] leads INTO local
+ *   step k), only out_elem is meaningful -- the time-sharded protocol of mf_kalman_segment_summary.
+ *   out [B] log-likelihoods (may be NULL), out_elem [B, 3D^2+2D+1] scan element (A, b, C, eta, J, ell)
+ *   of the whole segment (may be NULL; join with mf_kalman_fold_elements).
+ *   workspace: mf_kalman_matern_workspace_bytes; without it few long series are not cut in time. */
+size_t mf_kalman_matern_workspace_bytes(int dtype, int64_t B, int64_t T, int64_t D);
+int mf_kalman_matern_log_likelihood(int dtype, const void* lengthscale, const void* variance,
+                                    double jitter, const void* time_deltas, const void* obs,
+                                    const void* chol_r, void* out, void* out_elem, int64_t B,
+                                    int64_t T, int64_t D, int first_is_initial, void* workspace,
+                                    size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Natural / expectation parameter transforms (markovflow/ssm_gaussian_transformations.py)

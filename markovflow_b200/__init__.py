@@ -34,6 +34,7 @@ from .ssm_gaussian_transformations import (
     ssm_to_naturals,
     ssm_to_naturals_no_smoothing,
 )
+from .kernels import Matern12, Matern32, Matern52, matern_kalman_log_likelihood
 from .state_space_model import (
     StateSpaceModel,
     cholesky_or_zero,
@@ -63,6 +64,10 @@ __all__ = [
     "KalmanFilterWithSparseSites",
     "UnivariateGaussianSitesNat",
     "kalman_log_likelihood",
+    "Matern12",
+    "Matern32",
+    "Matern52",
+    "matern_kalman_log_likelihood",
     "StateSpaceModel",
     "expectations_to_ssm_params",
     "naturals_to_ssm_params",

@@ -35,10 +35,10 @@ namespace {
 // Tuning knobs (mf_set_tuning): 0 = variant of the Cholesky sweep (0 auto = TMA, 1 direct,
 // 2 cp.async-staged),
 // 1 = steps per shared-memory stage for the staged sweep (0 auto).
-int g_tuning[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+int g_tuning[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 }  // namespace
 namespace mf {
-int tuning(int knob) { return (knob >= 0 && knob < 8) ? g_tuning[knob] : 0; }
+int tuning(int knob) { return (knob >= 0 && knob < 12) ? g_tuning[knob] : 0; }
 }  // namespace mf
 namespace {
 
@@ -132,7 +132,7 @@ int launch_chol_fast(const void* diag, const void* sub, const void* rhs, void* o
 extern "C" {
 
 int mf_set_tuning(int knob, int value) {
-  if (knob < 0 || knob >= 8) return MF_ERR_BAD_ARG;
+  if (knob < 0 || knob >= 12) return MF_ERR_BAD_ARG;
   g_tuning[knob] = value;
   return MF_OK;
 }

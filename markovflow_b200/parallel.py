@@ -195,3 +195,41 @@ def time_sharded_log_likelihood_local(ssm, emission_matrix, observations, chol_o
         share = e.seeded_log_likelihood(s, prefix, summaries_valid=True)
         total = share if total is None else total + share
     return total.reshape(tuple(ssm.batch_shape))
+
+
+# ---- Matern prior with the SSM built in the kernel -------------------------------
+
+def matern_time_segment(time_deltas: torch.Tensor, observations: torch.Tensor, rank: int, world: int):
+    """Rank ``rank``'s slice of ``time_deltas [B,T-1]`` / ``observations [B,T]``:
+    ``(first, deltas, obs)`` in the "incoming delta" convention of ``mf_kalman_matern_log_likelihood``."""
+    t = int(observations.shape[-1])
+    lo, hi = shard_bounds(t, rank, world)
+    if hi - lo < 1:
+        raise ValueError("every rank needs at least one time step")
+    first = lo == 0
+    tlo = 0 if first else lo - 1
+    return first, time_deltas[:, tlo:hi - 1].contiguous(), observations[:, lo:hi].contiguous()
+
+
+def time_sharded_matern_log_likelihood(state_dim: int, lengthscale, variance, seg_deltas, seg_obs,
+                                       chol_obs_covariance, first: bool, jitter: float = 0.0,
+                                       group=None, engine=None) -> torch.Tensor:
+    """Collective per-series log-likelihood ``[B]`` of a long series split in time over the ranks
+    (rank order == time order): local scan element -> all-gather -> ordered fold, as
+    :func:`time_sharded_log_likelihood`, with the SSM built inside the kernel from the deltas."""
+    import torch.distributed as dist
+
+    from .kernels import matern_kalman_log_likelihood
+
+    engine = engine or CudaKalmanEngine()
+    world = dist.get_world_size(group)
+    if first != (dist.get_rank(group) == 0):
+        raise ValueError("rank 0 (and only rank 0) must hold the segment that starts at the prior")
+    _, elem = matern_kalman_log_likelihood(state_dim, lengthscale, variance, seg_obs,
+                                           chol_obs_covariance, time_deltas=seg_deltas, jitter=jitter,
+                                           first_is_initial=first, return_element=True)
+    if world > 1:
+        gathered = [torch.empty_like(elem) for _ in range(world)]
+        dist.all_gather(gathered, elem, group=group)
+        elem = engine.fold(torch.stack(gathered), state_dim)
+    return elem[:, -1].clone()

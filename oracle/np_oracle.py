@@ -929,6 +929,26 @@ class _Stationary:
         return np.broadcast_to(self.emission_row(), t.shape + (1, self.state_dim)).copy()
 
 
+class Matern12(_Stationary):
+    """``kernels/matern.py:27-143``: ``A = exp(−Δt/ℓ)``, ``P∞ = σ²``."""
+
+    state_dim = 1
+
+    def __init__(self, lengthscale: float, variance: float, jitter: float = 0.0):
+        self.lam = 1.0 / lengthscale
+        self.variance = variance
+        self.jitter = jitter
+
+    def feedback(self):
+        return np.array([[-self.lam]])
+
+    def steady_state_covariance(self):
+        return self.variance * np.eye(1)
+
+    def state_transitions(self, dt):
+        return np.exp(-self.lam * np.asarray(dt))[..., None, None]
+
+
 class Matern32(_Stationary):
     """``kernels/matern.py:237-372``."""
 
@@ -1000,6 +1020,39 @@ class HarmonicOscillator(_Stationary):
         return np.concatenate(
             [np.concatenate([c, -s], axis=-1), np.concatenate([s, c], axis=-1)], axis=-2
         )
+
+
+def stationary_ssm_extended_precision(kernel: "_Stationary", time_points: Array) -> SSM:
+    """``kernel.state_space_model(time_points)`` with ``A_k`` and ``Q_k = P∞ − A_k P∞ A_kᵀ + jitter·I``
+    (``kernels/sde_kernel.py:421-446``) evaluated in ``np.longdouble`` and rounded once.
+
+    For small ``Δt`` the subtraction cancels (Matern52: ``Q_00 = O(Δt⁵)`` against ``‖P∞‖ = O(λ⁴)``), so the
+    float64 evaluation of the reference formula -- in TF as much as in numpy -- carries a relative error
+    of ``eps·‖P∞‖/Q_00`` that shows up at 1e-9 in a log-likelihood.  This variant separates that rounding
+    of the restated reference from the error of an implementation under test.
+    Matern12/32/52 only (closed form ``exp(−λΔt)·Σ_j (NΔt)ʲ/j!`` with nilpotent ``N = F + λI``)."""
+    ld = np.longdouble
+    t = np.asarray(time_points, dtype=np.float64)
+    if t.ndim != 1:
+        raise ValueError("one series at a time")
+    dt = (t[1:] - t[:-1]).astype(ld)
+    d = kernel.state_dim
+    eye = np.eye(d, dtype=ld)
+    lam = ld(kernel.lam)
+    n = kernel.feedback().astype(ld) + lam * eye
+    a = []
+    for x in dt:
+        term, acc = eye, eye.copy()
+        for j in range(1, d):
+            term = term @ n * x / ld(j)
+            acc = acc + term
+        a.append(np.exp(-lam * x) * acc)
+    a = np.stack(a) if len(a) else np.zeros((0, d, d), dtype=ld)
+    pinf = kernel.steady_state_covariance().astype(ld)
+    q = pinf - a @ pinf @ _t(a) + ld(kernel.jitter) * eye
+    p0 = (pinf + ld(kernel.jitter) * eye).astype(np.float64)
+    return ssm_from_covariances(np.zeros(d), p0, a.astype(np.float64), np.zeros((len(dt), d)),
+                                q.astype(np.float64))
 
 
 def _block_diag(mats: Sequence[Array]) -> Array:

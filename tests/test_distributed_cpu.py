@@ -135,3 +135,27 @@ def test_time_segments_tile_the_series():
     for s in segs[1:]:
         assert s.a.shape[1] == s.num_steps
     assert torch.equal(torch.cat([s.a for s in segs], dim=1), a)
+
+
+def test_matern_time_segments_tile_the_series():
+    """Host-side slicing of the in-kernel-SSM path: segments cover every step once; a later segment
+    carries the delta leading INTO its first step."""
+    import torch
+
+    from markovflow_b200.parallel import matern_time_segment
+
+    t = 23
+    dts = torch.arange(1, t, dtype=torch.float64)[None]  # delta k leads into step k+1
+    obs = torch.arange(t, dtype=torch.float64)[None]
+    for world in (1, 2, 3, 8):
+        seen = []
+        for r in range(world):
+            first, d, y = matern_time_segment(dts, obs, r, world)
+            assert first == (r == 0)
+            assert d.shape[-1] == y.shape[-1] - (1 if first else 0)
+            into = d[0] if first else d[0, 1:]
+            assert torch.equal(into, y[0, 1:])  # delta into step k is k by construction
+            if not first:
+                assert d[0, 0] == y[0, 0]
+            seen.append(y[0])
+        assert torch.equal(torch.cat(seen), obs[0])

@@ -280,3 +280,41 @@ def test_matern_and_harmonic_ssm_covariance_equals_kernel_function():
         v * (1 + np.sqrt(3) / l * r) * np.exp(-np.sqrt(3) / l * r) + 0.5 * np.cos(2 * np.pi / 0.7 * r),
         atol=1e-7,
     )
+
+
+# ---- the kernel -> SSM -> Kalman log-likelihood chain the fused CUDA path replaces ----
+
+
+@pytest.mark.parametrize("name", ["m12", "m32", "m52"])
+def test_matern_kalman_log_likelihood_equals_dense_gp_marginal_likelihood(name):
+    """tests/integration/models/test_gaussian_process_regression.py:78-115 restated: the SSM-based
+    log-likelihood equals log N(y; 0, K + R) with the closed-form Matern kernel matrix K."""
+    rng = np.random.default_rng(71892305)
+    tp = np.cumsum(rng.uniform(0.05, 0.4, size=40))
+    y = np.sin(tp) + 0.1 * rng.standard_normal(40)
+    l, v, noise = 0.7, 1.9, 0.3
+    r = np.abs(tp[:, None] - tp[None, :])
+    if name == "m12":
+        kern, kmat = O.Matern12(l, v), v * np.exp(-r / l)
+    elif name == "m32":
+        lam = np.sqrt(3) / l
+        kern, kmat = O.Matern32(l, v), v * (1 + lam * r) * np.exp(-lam * r)
+    else:
+        lam = np.sqrt(5) / l
+        kern, kmat = O.Matern52(l, v), v * (1 + lam * r + lam ** 2 * r ** 2 / 3) * np.exp(-lam * r)
+    ssm = kern.state_space_model(tp)
+    h = kern.emission_matrix(tp)
+    got = O.kalman_log_likelihood(ssm, h, y[:, None], np.array([[1.0 / noise ** 2]]))
+    c = kmat + noise ** 2 * np.eye(40)
+    want = -0.5 * (y @ np.linalg.solve(c, y) + np.linalg.slogdet(c)[1] + 40 * np.log(2 * np.pi))
+    np.testing.assert_allclose(got, want, rtol=1e-9)
+
+
+def test_extended_precision_transition_statistics_agree_with_the_float64_restatement():
+    tp = np.cumsum(np.random.default_rng(1).uniform(0.05, 0.3, 20))
+    for kern, tol in ((O.Matern12(0.7, 1.3, 1e-8), 1e-14), (O.Matern32(0.7, 1.3, 1e-8), 1e-11),
+                      (O.Matern52(0.7, 1.3, 1e-8), 1e-8)):
+        a, b = kern.state_space_model(tp), O.stationary_ssm_extended_precision(kern, tp)
+        np.testing.assert_allclose(a.a_s, b.a_s, rtol=0, atol=1e-15)
+        np.testing.assert_allclose(a.chol_q_s, b.chol_q_s, rtol=0, atol=tol)
+        np.testing.assert_allclose(a.chol_p0, b.chol_p0, rtol=0, atol=1e-15)
