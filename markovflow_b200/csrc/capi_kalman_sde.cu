@@ -22,7 +22,7 @@ SdePlan make_sde_plan(int64_t B, int64_t T) {
   SdePlan p;
   p.P = 1;
   p.L = T;
-  const int warps_per_sm = tuning(9) > 0 ? tuning(9) : (tuning(8) > 0 ? 8 : 12);
+  const int warps_per_sm = tuning(9) > 0 ? tuning(9) : ((tuning(8) > 0 && tuning(8) < 5) ? 8 : 12);
   const int64_t wave = (int64_t)148 * 32 * warps_per_sm;
   int64_t ptarget = wave / (B > 0 ? B : 1);
   if (tuning(2) == 1 || ptarget < 32) return p;  // enough series: one chain per series
@@ -55,6 +55,12 @@ int launch_core(const KalmanSdeParams<T>& prm, int64_t nchains, cudaStream_t s) 
       case 2: return launch_fixed<Core, 64, 16, 2>(prm, nchains, s);
       case 3: return launch_fixed<Core, 128, 16, 2>(prm, nchains, s);
       case 4: return launch_fixed<Core, 64, 32, 2>(prm, nchains, s);
+      case 5:  // register caps of the direct kernel: 5 / 6 CTAs of 128 threads per SM
+        kalman_sde_direct_kernel<T, D, SUMMARY, 128, 5><<<grid_for(nchains, 128), 128, 0, s>>>(prm);
+        return check_launch();
+      case 6:
+        kalman_sde_direct_kernel<T, D, SUMMARY, 128, 6><<<grid_for(nchains, 128), 128, 0, s>>>(prm);
+        return check_launch();
       default: break;
     }
   }

@@ -473,8 +473,8 @@ struct KalmanSdeFilterCore : KalmanSdeCoreBase<T_, D> {
 // there is nothing to stage, so thread = virtual chain, all warps compute, loads run R steps ahead.
 // SUMMARY: range element per virtual chain (+ per-warp join when reduce_warp); otherwise the plain
 // filter with out[chain] = log-likelihood (P == 1).
-template <typename T, int D, bool SUMMARY, int NT>
-__global__ void __launch_bounds__(NT)
+template <typename T, int D, bool SUMMARY, int NT, int MINB = 1>
+__global__ void __launch_bounds__(NT, MINB)
 kalman_sde_direct_kernel(const KalmanSdeParams<T> p) {
   using Core = typename std::conditional<SUMMARY, KalmanSdeSummaryCore<T, D>, KalmanSdeFilterCore<T, D>>::type;
   const int64_t chain = (int64_t)blockIdx.x * NT + threadIdx.x;

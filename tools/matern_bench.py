@@ -37,8 +37,8 @@ def main():
     y2 = y.reshape(1, t).contiguous()
     one = torch.ones(1, dtype=torch.float64, device=dev)
     lib = _lib.lib()
-    for variant in (0, 1, 2, 3, 4):
-        for wps in ((6, 8, 12, 16, 24) if variant == 0 else (2, 4, 8)):
+    for variant in (0, 5, 6, 1, 4):
+        for wps in {0: (8, 12, 16), 5: (12, 16, 20), 6: (12, 16, 20, 24)}.get(variant, (4,)):
             lib.mf_set_tuning(8, variant)
             lib.mf_set_tuning(9, wps)
             fn = lambda: mf.matern_kalman_log_likelihood(2, one, one, y2, lr, time_deltas=dts)
