@@ -430,7 +430,13 @@ def run_gpu(args):
     if not args.no_extras:
         del diag, sub, rhs, od, os_, ox
         torch.cuda.empty_cache()
-        extras = extra_measurements(dev, rank, world, dist, peak)
+        try:
+            extras = extra_measurements(dev, rank, world, dist, peak)
+        except Exception as exc:  # noqa: BLE001 -- the headline line must survive a failing extra
+            import traceback
+
+            traceback.print_exc(file=sys.stderr)
+            extras = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank != 0:
         if dist is not None:
