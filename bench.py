@@ -272,7 +272,8 @@ def extra_measurements(dev, rank, world, dist, peak):
         out[f"config5_naturals_to_ssm_params_{tag}"] = entry(
             b5 * t5, 20 * es, ms, workload="Matern32 prior + sites, B=1024 x M=1e4, D=2",
             max_rel_err_vs_f64=err)
-        q = mf.StateSpaceModel(got[4], got[2], got[0], got[1], got[3])
+        # dense parameter arrays (the transform returns slices of its concatenated outputs)
+        q = mf.StateSpaceModel(*(g.contiguous() for g in (got[4], got[2], got[0], got[1], got[3])))
         ms = _timed(lambda: mf.ssm_to_expectations(q))
         out[f"config5_ssm_to_expectations_{tag}"] = entry(b5 * t5, 20 * es, ms)
     del th64, ref, th, got, q

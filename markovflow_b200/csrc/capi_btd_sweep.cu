@@ -75,7 +75,7 @@ int btd_sweep_solve(int dtype, int64_t D, const void* ld, const void* ls, const 
       if (p.P > 1 && kS) {
         int rc = run<BtdSolveCore<Tp, kD, kT, kU, kS, true>>(p, n * p.P, s);
         if (rc != MF_OK) return rc;
-        if (p.P > 64) btd_solve_seed_kernel<Tp, kD, kT, true><<<grid_for(n * 32, 128), 128, 0, s>>>(p);
+        if (warp_fold(p.P)) btd_solve_seed_kernel<Tp, kD, kT, true><<<grid_for(n * 32, 128), 128, 0, s>>>(p);
         else btd_solve_seed_kernel<Tp, kD, kT, false><<<grid_for(n, 128), 128, 0, s>>>(p);
         rc = check_launch();
         if (rc != MF_OK) return rc;
@@ -107,7 +107,7 @@ int btd_sweep_inverse_subset(int dtype, int64_t D, const void* ld, const void* l
     if (p.P > 1) {
       int rc = run<BtdInvSubsetCore<Tp, kD, false, true>>(p, B * p.P, s);
       if (rc != MF_OK) return rc;
-      if (p.P > 64) btd_inv_subset_seed_kernel<Tp, kD, true><<<grid_for(B * 32, 128), 128, 0, s>>>(p);
+      if (warp_fold(p.P)) btd_inv_subset_seed_kernel<Tp, kD, true><<<grid_for(B * 32, 128), 128, 0, s>>>(p);
       else btd_inv_subset_seed_kernel<Tp, kD, false><<<grid_for(B, 128), 128, 0, s>>>(p);
       rc = check_launch();
       if (rc != MF_OK) return rc;
@@ -128,7 +128,7 @@ int btd_sweep_udu(int dtype, int64_t D, const void* diag, const void* sub, void*
       if (info && cudaMemsetAsync(info, 0, sizeof(int32_t) * B, s) != cudaSuccess) return check_launch();
       int rc = run<BtdUduCore<Tp, kD, true>>(p, B * p.P, s);
       if (rc != MF_OK) return rc;
-      if (p.P > 64) btd_udu_seed_kernel<Tp, kD, true><<<grid_for(B * 32, 128), 128, 0, s>>>(p);
+      if (warp_fold(p.P)) btd_udu_seed_kernel<Tp, kD, true><<<grid_for(B * 32, 128), 128, 0, s>>>(p);
       else btd_udu_seed_kernel<Tp, kD, false><<<grid_for(B, 128), 128, 0, s>>>(p);
       rc = check_launch();
       if (rc != MF_OK) return rc;
@@ -165,7 +165,7 @@ int btd_sweep_cholesky_pit(int dtype, int64_t D, const void* diag, const void* s
     else rc = run<CholPitSummaryCore<Tp, kD, false>>(p, B * p.P, s);
     if (rc != MF_OK) return rc;
     // many segments per chain: the fold is a warp scan over the elements
-    if (p.P > 64) {
+    if (warp_fold(p.P)) {
       if (rhs) chol_pit_seed_kernel<Tp, kD, true, true><<<grid_for(B * 32, 128), 128, 0, s>>>(p);
       else chol_pit_seed_kernel<Tp, kD, false, true><<<grid_for(B * 32, 128), 128, 0, s>>>(p);
     } else {

@@ -69,7 +69,7 @@ int ssm_sweep_moments(int dtype, int64_t D, int expectations, const void* mu0, c
     if (p.P > 1) {
       int rc = run<SsmMomSummaryCore<Tp, kD>>(p, B * p.P, s);
       if (rc != MF_OK) return rc;
-      if (p.P > 64) ssm_moments_seed_kernel<Tp, kD, true><<<grid_for(B * 32, 128), 128, 0, s>>>(p);
+      if (warp_fold(p.P)) ssm_moments_seed_kernel<Tp, kD, true><<<grid_for(B * 32, 128), 128, 0, s>>>(p);
       else ssm_moments_seed_kernel<Tp, kD, false><<<grid_for(B, 128), 128, 0, s>>>(p);
       rc = check_launch();
       if (rc != MF_OK) return rc;
@@ -96,7 +96,7 @@ int ssm_sweep_affine(int dtype, int64_t D, const void* mu0, const void* chol_p0,
       if (p.P > 1) {
         int rc = run<SsmAffineCore<Tp, kD, kN, true>>(p, n * p.P, s);
         if (rc != MF_OK) return rc;
-        if (p.P > 64) ssm_affine_seed_kernel<Tp, kD, true><<<grid_for(n * 32, 128), 128, 0, s>>>(p);
+        if (warp_fold(p.P)) ssm_affine_seed_kernel<Tp, kD, true><<<grid_for(n * 32, 128), 128, 0, s>>>(p);
         else ssm_affine_seed_kernel<Tp, kD, false><<<grid_for(n, 128), 128, 0, s>>>(p);
         rc = check_launch();
         if (rc != MF_OK) return rc;
@@ -134,7 +134,7 @@ int ssm_sweep_kl(int dtype, int64_t D, const void* q_mu0, const void* q_chol_p0,
                            (const Tp*)q_chol_q, nullptr, nullptr, nullptr, B, T, p.P, p.L, ws_vec, ws_diag, 1};
     int rc = run<SsmMomSummaryCore<Tp, kD>>(m, B * p.P, s);
     if (rc == MF_OK) {
-      if (p.P > 64) ssm_moments_seed_kernel<Tp, kD, true><<<grid_for(B * 32, 128), 128, 0, s>>>(m);
+      if (warp_fold(p.P)) ssm_moments_seed_kernel<Tp, kD, true><<<grid_for(B * 32, 128), 128, 0, s>>>(m);
       else ssm_moments_seed_kernel<Tp, kD, false><<<grid_for(B, 128), 128, 0, s>>>(m);
       rc = check_launch();
     }
@@ -164,7 +164,7 @@ int nat_sweep_to_ssm(int dtype, int64_t D, const void* th_lin, const void* th_di
       int rc = run<NatSummaryCore<Tp, kD>>(p, B * p.P, s);
       if (rc != MF_OK) return rc;
       // many segments per chain: the fold is a warp scan over the elements
-      if (p.P > 64) nat_seed_kernel<Tp, kD, true><<<grid_for(B * 32, 128), 128, 0, s>>>(p);
+      if (warp_fold(p.P)) nat_seed_kernel<Tp, kD, true><<<grid_for(B * 32, 128), 128, 0, s>>>(p);
       else nat_seed_kernel<Tp, kD, false><<<grid_for(B, 128), 128, 0, s>>>(p);
       rc = check_launch();
       if (rc != MF_OK) return rc;

@@ -50,6 +50,12 @@ int big_solve(int dtype, const void* ld, const void* ls, const void* rhs, void* 
 int exp_chol_d3(int variant, const void* diag, const void* sub, const void* rhs, void* od, void* os,
                 void* ox, void* logdet, int32_t* info, int64_t B, int64_t T, cudaStream_t s);
 
+// Seed folds of the parallel-in-time paths: one warp per chain (shuffle scan over the segment
+// elements, log2 depth) from this many segments per chain on, else one thread per chain (sequential
+// fold).  Measured on config 5 (B=1024, 28 segments): nat_seed_kernel 99 us thread-per-chain.
+// tuning knob 10 overrides the threshold.
+inline bool warp_fold(int64_t P) { return P >= (tuning(10) > 0 ? tuning(10) : 8); }
+
 inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
 }  // namespace mf

@@ -105,6 +105,15 @@ class StateSpaceModel(GaussMarkovDistribution):
 
     # -- flattened contiguous parameter views for the C ABI ---------------------------------------
     def _flat(self):
+        """Dense ``[B, ...]`` views of the parameters for the C ABI.  Parameters that arrive as strided
+        views (``naturals_to_ssm_params`` returns slices of its concatenated outputs) are compacted
+        ONCE per object -- the parameters are immutable, as in the reference -- not once per method."""
+        flat = getattr(self, "_flat_cache", None)
+        if flat is None:
+            flat = self._flat_cache = self._flatten()
+        return flat
+
+    def _flatten(self):
         require_cuda(self._A_s, "state_transitions")
         bsz, n, d = _prod(self.batch_shape), self.num_transitions, self.state_dim
         return (
