@@ -1,0 +1,69 @@
+"""BASELINE config 4 at its NAMED size: Sum(Matern52 + 7 harmonics) D=17, B=256 x T=1e5, float64
+block-tridiagonal Cholesky + solve, factored IN PLACE (inputs 118 GB + outputs 118 GB do not fit one
+B200 otherwise).  One timed launch (the inputs are consumed), then the first 8 chains
+are regenerated and factored out of place for comparison.  Usage: python tools/config4_full.py [T] [B]"""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import bench_inputs
+from markovflow_b200 import _lib
+
+
+def chol(diag, sub, rhs, od, os_, ox, info, b, t):
+    lib = _lib.lib()
+    _lib.check(lib.mf_btd_cholesky(_lib.MF_F64, _lib.ptr(diag), _lib.ptr(sub), _lib.ptr(rhs), _lib.ptr(od),
+                                   _lib.ptr(os_), _lib.ptr(ox), None, _lib.ptr(info), _lib.i64(b),
+                                   _lib.i64(t), _lib.i64(17), _lib.current_stream()), "mf_btd_cholesky")
+
+
+def run(b: int, t: int, dev) -> dict:
+    # warm-up on a small problem (lazy kernel configuration)
+    d, s, r = bench_inputs.sum_kernel_posterior_precision(8, 256, dev)
+    chol(d, s, r, d, s, torch.empty_like(r), torch.empty(8, dtype=torch.int32, device=dev), 8, 256)
+    del d, s, r
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    diag, sub, rhs = bench_inputs.sum_kernel_posterior_precision(b, t, dev)
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - w0
+    x = torch.empty_like(rhs)
+    info = torch.empty(b, dtype=torch.int32, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    chol(diag, sub, rhs, diag, sub, x, info, b, t)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    assert int(info.abs().max()) == 0
+    # the generator draws chunk by chunk: the first 8 chains of a (8, t) problem are the same chains
+    d8, s8, _ = bench_inputs.sum_kernel_posterior_precision(8, t, dev)
+    r8 = rhs[:8].contiguous()
+    od, os_, ox = torch.empty_like(d8), torch.empty_like(s8), torch.empty_like(r8)
+    chol(d8, s8, r8, od, os_, ox, torch.empty(8, dtype=torch.int32, device=dev), 8, t)
+    torch.cuda.synchronize()
+    rel = lambda a, ref: float((a - ref).abs().max() / ref.abs().max())
+    errs = {"Ld": rel(torch.tril(diag[:8]), torch.tril(od)), "Ls": rel(sub[:8], os_), "x": rel(x[:8], ox)}
+    # size-independent property on those chains: L L^T reproduces the input blocks
+    ld = torch.tril(od)
+    rec = ld @ ld.transpose(-1, -2)
+    rec[:, 1:] += os_ @ os_.transpose(-1, -2)
+    errs["LLt_diag"] = float((torch.tril(rec) - torch.tril(d8)).abs().max() / d8.abs().max())
+    errs["LLt_sub"] = rel(os_ @ ld[:, :-1].transpose(-1, -2), s8)
+    steps = b * t
+    gbs = steps * 9520 / (ms * 1e-3) / 1e9
+    return {"workload": f"config 4 at the named size: Matern52 + 7 harmonics (D=17), B={b} x T={t}, f64, "
+                        "Cholesky+solve IN PLACE (one launch: the inputs are consumed), one warp per chain",
+            "ms": ms, "state_steps_per_s": steps / (ms * 1e-3), "bytes_per_state_step": 9520,
+            "achieved_GBps": gbs, "input_generation_s": gen_s,
+            "device_memory_GB": torch.cuda.max_memory_allocated() / 1e9,
+            "in_place_vs_out_of_place_first_8_chains_max_rel": errs}
+
+
+if __name__ == "__main__":
+    print(json.dumps(run(int(sys.argv[2]) if len(sys.argv) > 2 else 256,
+                         int(float(sys.argv[1])) if len(sys.argv) > 1 else 100_000, torch.device("cuda:0"))))
