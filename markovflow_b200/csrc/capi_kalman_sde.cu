@@ -103,11 +103,11 @@ int mf_kalman_matern_log_likelihood(int dtype, const void* lengthscale, const vo
                                     size_t workspace_bytes, void* stream) {
   if (B < 0 || T < 1 || D < 1) return MF_ERR_BAD_ARG;
   if (D > 3) return MF_ERR_UNSUPPORTED;
+  if (B == 0) return MF_OK;
   if (!lengthscale || !variance || !obs || !chol_r) return MF_ERR_BAD_ARG;
   if ((T - (first_is_initial ? 1 : 0)) > 0 && !time_deltas) return MF_ERR_BAD_ARG;
   if (!out && !out_elem) return MF_ERR_BAD_ARG;
   if (!first_is_initial && !out_elem) return MF_ERR_BAD_ARG;  // a later time segment has no ell of its own
-  if (B == 0) return MF_OK;
   if (B > 65535) return MF_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   SdePlan pl = make_sde_plan(B, T);

@@ -207,3 +207,41 @@ def test_rejects_bad_arguments():
     with pytest.raises(RuntimeError):
         matern_kalman_log_likelihood(2, 1.0, 1.0, torch.zeros(2, 5, dtype=torch.float64), 0.1,
                                      time_points=torch.zeros(2, 5, dtype=torch.float64))
+
+
+def test_element_of_uncut_series_and_many_series():
+    """P == 1 paths: the element written directly by the summary kernel (ell copied out of it), and a
+    batch large enough that series are not cut at all (plain filter core)."""
+    from markovflow_b200 import _lib, matern_kalman_log_likelihood
+
+    rng = np.random.default_rng(3)
+    d, b, t = 2, 3, 700
+    ls, var, tps, y = _case(d, b, t, rng)
+    dts = np.diff(tps, axis=-1)
+    args = (d, tt(ls), tt(var), tt(y), 0.1)
+    ll_cut, el_cut = matern_kalman_log_likelihood(*args, time_deltas=tt(dts), return_element=True)
+    lib = _lib.lib()
+    try:
+        lib.mf_set_tuning(2, 1)
+        ll_one, el_one = matern_kalman_log_likelihood(*args, time_deltas=tt(dts), return_element=True)
+    finally:
+        lib.mf_set_tuning(2, 0)
+    assert max_rel_err(npy(ll_one), npy(ll_cut)) < 1e-10
+    assert max_rel_err(npy(el_one), npy(el_cut)) < 1e-9
+    assert max_rel_err(npy(el_one[:, -1]), npy(ll_one)) == 0.0
+    # many series: 2500 > 148 * 12 warps, one chain per series
+    b2, t2 = 2500, 40
+    ls, var, tps, y = _case(d, b2, t2, rng)
+    got = npy(matern_kalman_log_likelihood(d, tt(ls), tt(var), tt(y), 0.2, time_points=tt(tps)))
+    pick = np.array([0, 1, 777, 2499])
+    want = _dense_gp(d, ls[pick], var[pick], tps[pick], y[pick], 0.2)
+    assert max_rel_err(got[pick], want) < 1e-10
+    assert np.all(np.isfinite(got))
+
+
+def test_empty_batch():
+    from markovflow_b200 import matern_kalman_log_likelihood
+
+    out = matern_kalman_log_likelihood(2, tt(np.zeros(0)), tt(np.zeros(0)), tt(np.zeros((0, 5))), 0.1,
+                                       time_deltas=tt(np.zeros((0, 4))))
+    assert tuple(out.shape) == (0,)
