@@ -1283,7 +1283,16 @@ struct SweepAuto {
   static constexpr bool fits() { return SweepCfg<Core, C, K, NSI, NSO>::FITS; }
   static constexpr int choice = fits<64, 8, 2, 2>() ? 0 : (fits<32, 8, 2, 2>() ? 1 : (fits<32, 4, 2, 2>() ? 2 : -1));
   static constexpr bool ok = choice >= 0;
+  // small records (float32, D <= 2) of a pass WITHOUT outputs: tiles of 16 steps fit beside 64 chains --
+  // half the bulk copies per step at the same number of compute warps (the D <= 2 sweeps are bound by
+  // TMA issue).  Measured on config 5 in f32: summary passes 190 -> 168 us and 138 -> 116 us;
+  // passes with outputs got slower (282 -> 342 us, 265 -> 280 us) and keep K = 8.  Knob 11 = 1: off.
+  // float64 summary passes lose a resident CTA per SM to the longer tiles (config 5: 290 -> 426 us).
+  static constexpr bool long_tiles = fits<64, 16, 2, 2>() && Core::NOUT == 0 && sizeof(typename Core::T) == 4;
   static cudaError_t launch(const typename Core::Params& prm, int64_t nchains, cudaStream_t s) {
+    if constexpr (long_tiles) {
+      if (nchains > (int64_t)148 * 48 && tuning(11) != 1) return launch_chain_sweep<Core, 64, 16, 2, 2>(prm, nchains, s, true);
+    }
     if constexpr (choice == 0) {
       // few chains: one compute warp per CTA so that more SMs get a CTA
       if (nchains <= (int64_t)148 * 48) return launch_chain_sweep<Core, 32, 8, 2, 2>(prm, nchains, s, true);

@@ -14,6 +14,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 3:
         from markovflow_b200 import _lib
         _lib.lib().mf_set_tuning(10, int(sys.argv[3]))
+    if len(sys.argv) > 4:
+        from markovflow_b200 import _lib
+        _lib.lib().mf_set_tuning(11, int(sys.argv[4]))
     dev = torch.device("cuda:0")
     th = tuple(x.to(dtype) for x in bench_inputs.cvi_naturals_config5(1024, 10_000, dev, dtype=torch.float64))
     got = mf.naturals_to_ssm_params(*th)
