@@ -53,8 +53,9 @@ const char* mf_last_cuda_error(void);
  * the TMA chain sweeps; knob 7: large-block Cholesky (0/1 one warp per chain, 2 experimental
  * one-CTA-per-chain kernel); knob 8: Matern-prior Kalman kernel (0 all-warps-compute kernel,
  * 1..4 TMA chain-sweep geometries); knob 9: its virtual chains per SM, in warps (0 auto); knob 10: segments per chain from which
- * the parallel-in-time seed folds run as warp scans (0 auto = 8); knob 11: 1 = no 16-step tiles for
- * output-less float32 sweeps. */
+ * the parallel-in-time seed folds run as warp scans (0 auto = 8); knob 11: 1 = the default
+ * 8-step tiles everywhere (no 16-step tiles for output-less float32 sweeps, no 4-step tiles for the
+ * float64 D = 2 naturals -> SSM sweep). */
 int mf_set_tuning(int knob, int value);
 
 /* ---------------------------------------------------------------------------------------------

@@ -1276,6 +1276,12 @@ nat_seed_kernel(const NatToSsmParams<T> p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// 4-step tiles (half the ring, two resident CTAs per SM, twice the bulk copies): measured on config 5
+// in float64 they pay only for the arithmetic-heaviest sweep, NatToSsmCore 561 -> 516 us; the moment
+// sweep and both summary passes lose 15-55 % (TMA issue).  Knob 11 = 1: off.
+template <class Core> struct PrefersShortTiles { static constexpr bool value = false; };
+template <> struct PrefersShortTiles<NatToSsmCore<double, 2>> { static constexpr bool value = true; };
+
 // Compile-time choice of a ring geometry that fits (chains per CTA, steps per tile, stages).
 template <class Core>
 struct SweepAuto {
@@ -1292,6 +1298,9 @@ struct SweepAuto {
   static cudaError_t launch(const typename Core::Params& prm, int64_t nchains, cudaStream_t s) {
     if constexpr (long_tiles) {
       if (nchains > (int64_t)148 * 48 && tuning(11) != 1) return launch_chain_sweep<Core, 64, 16, 2, 2>(prm, nchains, s, true);
+    }
+    if constexpr (PrefersShortTiles<Core>::value && fits<64, 4, 2, 2>()) {
+      if (tuning(11) != 1 && nchains > (int64_t)148 * 48) return launch_chain_sweep<Core, 64, 4, 2, 2>(prm, nchains, s, true);
     }
     if constexpr (choice == 0) {
       // few chains: one compute warp per CTA so that more SMs get a CTA

@@ -178,3 +178,37 @@ def test_naturals_to_ssm_params_parallel_in_time_short_segments_and_failure():
     bad[1, 120] *= -1.0
     with pytest.raises(mf.CholeskyError):
         mf.naturals_to_ssm_params(th[0], bad, th[2])
+
+
+@pytest.mark.parametrize("b,t", [(300, 700), (8000, 33)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 5e-4)])
+def test_naturals_to_ssm_params_many_chains_tile_geometries(b, t, dtype, tol):
+    """More than 148 x 48 virtual chains at D = 2 (the config-5 regime): the float64 naturals -> SSM
+    sweep runs on 4-step tiles and output-less float32 passes on 16-step tiles; tuning knob 11 = 1
+    restores 8-step tiles everywhere.  Both must recover the SSM the naturals came from and agree;
+    ssm_to_expectations -> expectations_to_ssm_params closes the loop on the same sizes."""
+    import markovflow_b200 as mf
+    from markovflow_b200 import _lib
+
+    d = 2
+    state = np.random.get_state()
+    np.random.seed(b + t)
+    arrays = random_ssm_arrays((b,), t - 1, d, scale_a=0.6 / np.sqrt(d))
+    np.random.set_state(state)
+    mu0, l0, a, bb, lq = arrays
+    want = (a, bb, l0, lq, mu0)
+    th = tuple(x.to(dtype) for x in mf.ssm_to_naturals(make_ssm(arrays)))
+    lib = _lib.lib()
+    res = {}
+    for knob in (0, 1):
+        lib.mf_set_tuning(11, knob)
+        try:
+            res[knob] = mf.naturals_to_ssm_params(*th)
+            q = mf.StateSpaceModel(res[knob][4], res[knob][2], res[knob][0], res[knob][1], res[knob][3])
+            back = mf.expectations_to_ssm_params(*mf.ssm_to_expectations(q))
+        finally:
+            lib.mf_set_tuning(11, 0)
+        _check_params(res[knob], want, tol)
+        _check_params(back, want, 10 * tol)
+    for g, w in zip(res[0], res[1]):
+        assert max_rel_err(npy(g), npy(w)) < tol
