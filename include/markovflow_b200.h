@@ -52,7 +52,7 @@ const char* mf_last_cuda_error(void);
  * knob 3: steps per parallel-in-time segment (0 auto); knob 4: 1 = direct-load kernels instead of
  * the TMA chain sweeps; knob 7: large-block Cholesky (0/1 one warp per chain, 2 experimental
  * one-CTA-per-chain kernel); knob 8: Matern-prior Kalman kernel (0 all-warps-compute kernel,
- * 1..4 TMA chain-sweep geometries); knob 9: its virtual chains per SM, in warps (0 auto); knob 10: segments per chain from which
+ * 1..4 TMA chain-sweep geometries, 5/6 register-capped variants); knob 9: its virtual chains per SM, in warps (0 auto); knob 10: segments per chain from which
  * the parallel-in-time seed folds run as warp scans (0 auto = 8); knob 11: 1 = the default
  * 8-step tiles everywhere (no 16-step tiles for output-less float32 sweeps, no 4-step tiles for the
  * float64 D = 2 naturals -> SSM sweep). */

@@ -12,7 +12,8 @@ size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
 
 // Segments per series.  The recursion is arithmetic-bound (two values per step cross HBM), so the
 // series are cut until every SM holds many compute warps.
-// tuning knob 8: 0 = direct kernel (every warp computes), 1..6 = TMA chain-sweep geometries;
+// tuning knob 8: 0 = direct kernel (every warp computes), 1..4 = TMA chain-sweep geometries, 5 / 6 =
+// direct kernel capped at the registers of 5 / 6 CTAs per SM (all measured slower);
 // knob 9: virtual chains per SM aimed at, in warps (0 auto); knob 3: steps per segment override.
 struct SdePlan {
   int64_t P, L;

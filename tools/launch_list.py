@@ -1,3 +1,5 @@
+"""Per-launch durations of an `ncu --metrics gpu__time_duration.sum --csv` log, in launch order:
+    python tools/launch_list.py <csv>"""
 import csv,sys
 from collections import OrderedDict
 rows=[r for r in csv.reader(open(sys.argv[1])) if r and r[0].isdigit()]
