@@ -26,7 +26,14 @@ SdePlan make_sde_plan(int64_t B, int64_t T) {
   const int warps_per_sm = tuning(9) > 0 ? tuning(9) : ((tuning(8) > 0 && tuning(8) < 5) ? 8 : 12);
   const int64_t wave = (int64_t)148 * 32 * warps_per_sm;
   int64_t ptarget = wave / (B > 0 ? B : 1);
-  if (tuning(2) == 1 || ptarget < 32) return p;  // enough series: one chain per series
+  if (tuning(2) == 1) return p;
+  if (ptarget < 32) {
+    // segment slots come in whole warps (the join is a warp scan).  A batch that cannot fill the GPU
+    // with one thread per series (4096 series = 128 warps on 148 SMs: 1.95 ms for T = 1e4, latency
+    // bound) is still cut into 32 segments per series as long as those have >= 64 steps each.
+    if (B * 4 > wave || T < 32 * 64) return p;  // enough series (or too short): one chain per series
+    ptarget = 32;
+  }
   int64_t L = (T + ptarget - 1) / ptarget;
   if (L < 64) L = 64;
   L = (L + 15) / 16 * 16;
@@ -109,7 +116,6 @@ int mf_kalman_matern_log_likelihood(int dtype, const void* lengthscale, const vo
   if ((T - (first_is_initial ? 1 : 0)) > 0 && !time_deltas) return MF_ERR_BAD_ARG;
   if (!out && !out_elem) return MF_ERR_BAD_ARG;
   if (!first_is_initial && !out_elem) return MF_ERR_BAD_ARG;  // a later time segment has no ell of its own
-  if (B > 65535) return MF_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   SdePlan pl = make_sde_plan(B, T);
   const size_t need = mf_kalman_matern_workspace_bytes(dtype, B, T, D);

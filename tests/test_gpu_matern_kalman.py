@@ -245,3 +245,31 @@ def test_empty_batch():
     out = matern_kalman_log_likelihood(2, tt(np.zeros(0)), tt(np.zeros(0)), tt(np.zeros((0, 5))), 0.1,
                                        time_deltas=tt(np.zeros((0, 4))))
     assert tuple(out.shape) == (0,)
+
+
+def test_mid_size_batch_is_cut_in_time_and_huge_batch_is_not_limited():
+    """2000 series cannot fill the GPU with one thread each: they are cut into 32 segments per series
+    (same value as the uncut filter and the dense closed form); 70000 series run one chain each."""
+    from markovflow_b200 import _lib, matern_kalman_log_likelihood
+
+    rng = np.random.default_rng(21)
+    d, b, t = 2, 2000, 2100
+    ls, var, tps, y = _case(d, b, t, rng)
+    dts = np.diff(tps, axis=-1)
+    args = (d, tt(ls), tt(var), tt(y), 0.15)
+    cut = npy(matern_kalman_log_likelihood(*args, time_deltas=tt(dts)))
+    lib = _lib.lib()
+    try:
+        lib.mf_set_tuning(2, 1)
+        uncut = npy(matern_kalman_log_likelihood(*args, time_deltas=tt(dts)))
+    finally:
+        lib.mf_set_tuning(2, 0)
+    assert max_rel_err(cut, uncut) < 1e-10
+    pick = np.array([0, 999, 1999])
+    assert max_rel_err(cut[pick], _dense_gp(d, ls[pick], var[pick], tps[pick], y[pick], 0.15)) < 1e-10
+    b2, t2 = 70000, 10
+    ls, var, tps, y = _case(3, b2, t2, rng)
+    got = npy(matern_kalman_log_likelihood(3, tt(ls), tt(var), tt(y), 0.2, time_points=tt(tps)))
+    pick = np.array([0, 65535, 65536, 69999])
+    assert max_rel_err(got[pick], _dense_gp(3, ls[pick], var[pick], tps[pick], y[pick], 0.2)) < 1e-10
+    assert np.all(np.isfinite(got))
