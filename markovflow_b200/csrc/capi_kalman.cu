@@ -52,7 +52,13 @@ SweepPlan make_sweep_plan(int64_t B, int64_t T, int64_t D, int64_t m) {
   int64_t ptarget = wave / (B > 0 ? B : 1);
   // segment slots come in whole warps (32), so cutting series pays only when a wave holds >= 32
   // segments per series; otherwise one chain per series
-  if (tuning(2) == 1 || (tuning(2) == 0 && ptarget < 32)) return p;
+  if (tuning(2) == 1) return p;
+  if (tuning(2) == 0 && ptarget < 32) {
+    // A batch that leaves most SMs without a CTA when every series is one chain (1024 series = 16
+    // CTAs) is still cut into 32 segments per series, as long as those keep >= 64 steps; from about
+    // half a wave of series on, the cheaper plain filter with one chain per series wins.
+    if (B * 2 > wave || T < 32 * 64) return p;
+  }
   if (ptarget < 32) ptarget = 32;
   int64_t L = (T + ptarget - 1) / ptarget;
   if (L < 64) L = 64;

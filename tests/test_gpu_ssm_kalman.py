@@ -536,3 +536,28 @@ def test_cuda_graph_replay_of_the_single_series_job():
     ll_g2, (m_g2, _) = graphed()
     assert max_rel_err(npy(ll_g2), npy(ll_e2)) < 1e-12 and max_rel_err(npy(m_g2), npy(m_e2)) < 1e-12
     assert abs(float(ll_e2) - float(ll_e)) > 1e-6
+
+
+def test_mid_size_batch_log_likelihood_is_cut_in_time():
+    """1000 series leave most SMs idle as one chain each: they are cut into 32 segments per series
+    (scan elements -> warp joins -> ordered reduction); same value as the uncut filter and the oracle."""
+    from markovflow_b200 import _lib, kalman_log_likelihood
+
+    rng = np.random.default_rng(77)
+    b, t = 1000, 2100
+    ssm, h, y = _long_case(O.Matern32(1.0, 1.0), t, rng, b)
+    lr = np.array([[0.1]])
+    gssm = to_gpu_ssm(ssm)
+    lib = _lib.lib()
+    cut = npy(kalman_log_likelihood(gssm, tt(h), tt(y), tt(lr)))
+    try:
+        lib.mf_set_tuning(2, 1)
+        uncut = npy(kalman_log_likelihood(gssm, tt(h), tt(y), tt(lr)))
+    finally:
+        lib.mf_set_tuning(2, 0)
+    assert cut.shape == (b,)
+    assert max_rel_err(cut, uncut) < 1e-10
+    pick = [0, 499, 999]
+    sub = O.SSM(ssm.mu0[pick], ssm.chol_p0[pick], ssm.a_s[pick], ssm.b_s[pick], ssm.chol_q_s[pick])
+    want = O.kalman_log_likelihood(sub, h[pick], y[pick], O._r_inv_from_chol(lr), per_chain=True)
+    assert max_rel_err(cut[pick], want) < 1e-10
