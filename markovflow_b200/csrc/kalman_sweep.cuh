@@ -360,6 +360,15 @@ kalman_reduce_kernel(const T* __restrict__ elems, T* __restrict__ total_out,
   __shared__ T smem[NW * N];
   const int64_t c = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (P == 1) {  // batches cut into one warp of segments per series: the warp join already is the total
+    if (threadIdx.x == 0) {
+      ScanElem<T, D> e;
+      elem_load<T, D>(e, elems + c * N);
+      if (total_out) elem_store<T, D>(total_out + c * N, e);
+      if (ell_out) ell_out[c] = e.ell;
+    }
+    return;
+  }
   const int64_t r = (P + NT - 1) / NT;
   const int64_t p0 = threadIdx.x * r;
   const int64_t p1 = (p0 + r < P) ? p0 + r : P;
