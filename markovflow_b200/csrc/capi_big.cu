@@ -5,10 +5,6 @@
 
 namespace mf {
 
-int team_cholesky(int dtype, const void* diag, const void* sub, const void* rhs, void* out_diag,
-                  void* out_sub, void* out_x, void* out_logdet, int32_t* info, int64_t B, int64_t T,
-                  int64_t D, cudaStream_t s);  // capi_team.cu
-
 namespace {
 
 template <typename F>
@@ -29,7 +25,7 @@ int dispatch_big(int dtype, int64_t D, F&& f) {
 }
 
 template <typename K>
-int set_smem(K kern, size_t bytes) {
+int set_smem(K kern, size_t bytes) {  // set on every launch: per-device attribute, cheap
   if (bytes > 48 * 1024 &&
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
     return check_launch();
@@ -41,14 +37,6 @@ int set_smem(K kern, size_t bytes) {
 int big_cholesky(int dtype, const void* diag, const void* sub, const void* rhs, void* out_diag,
                  void* out_sub, void* out_x, void* out_logdet, int32_t* info, int64_t B, int64_t T,
                  int64_t D, cudaStream_t s) {
-  // Knob 7 = 2 selects the experimental team kernel (one CTA of role-specialised warps per chain,
-  // btd_team.cuh).  Measured on B200 it is issue-bound in its pivot warp and does not yet beat the
-  // warp-per-chain kernel, so it is never chosen automatically.
-  const int tv = tuning(7);
-  if (sub && T > 1 && tv == 2) {
-    const int rc = team_cholesky(dtype, diag, sub, rhs, out_diag, out_sub, out_x, out_logdet, info, B, T, D, s);
-    if (rc != MF_ERR_UNSUPPORTED) return rc;
-  }
   return dispatch_big(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;

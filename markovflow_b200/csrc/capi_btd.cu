@@ -60,13 +60,8 @@ int launch_chol_staged(const void* diag, const void* sub, const void* rhs, void*
                        cudaStream_t s) {
   using Cfg = CholStagedCfg<T, D, RHS, C, K, NSI, NSO>;
   auto kern = btd_chol_staged_kernel<T, D, RHS, C, K, NSI, NSO>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)Cfg::SMEM_BYTES) != cudaSuccess)
-      return check_launch();
-    configured = true;
-  }
+  static SmemOnce once;  // per instantiation, per device
+  if (ensure_smem(once, kern, Cfg::SMEM_BYTES) != cudaSuccess) return check_launch();
   kern<<<grid_for(B, C), Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(
       (const T*)diag, (const T*)sub, (const T*)rhs, (T*)od, (T*)os, (T*)ox, (T*)logdet, info, B, Tn);
   return check_launch();
@@ -104,13 +99,8 @@ int launch_chol_tma(const void* diag, const void* sub, const void* rhs, void* od
                     void* ox, void* logdet, int32_t* info, int64_t B, int64_t Tn, cudaStream_t s) {
   using Cfg = CholTmaCfg<T, D, RHS, C, K, 3, 2>;
   auto kern = btd_chol_tma_kernel<T, D, RHS, C, K, 3, 2>;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)Cfg::SMEM_BYTES) != cudaSuccess)
-      return check_launch();
-    configured = true;
-  }
+  static SmemOnce once;  // per instantiation, per device
+  if (ensure_smem(once, kern, Cfg::SMEM_BYTES) != cudaSuccess) return check_launch();
   kern<<<grid_for(B, C), Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(
       (const T*)diag, (const T*)sub, (const T*)rhs, (T*)od, (T*)os, (T*)ox, (T*)logdet, info, B, Tn);
   return check_launch();
@@ -151,8 +141,6 @@ int mf_btd_cholesky(int dtype, const void* diag, const void* sub, const void* rh
   if ((rhs != nullptr) != (out_x != nullptr)) return MF_ERR_BAD_ARG;
   if (T == 1) { sub = nullptr; out_sub = nullptr; }
   cudaStream_t s = (cudaStream_t)stream;
-  if (tuning(6) > 0 && D == 3 && dtype == MF_F64 && sub && rhs && T > 1)
-    return exp_chol_d3(tuning(6) - 1, diag, sub, rhs, out_diag, out_sub, out_x, out_logdet, info, B, T, s);
   if (D > MF_SMALL_D_MAX)
     return big_cholesky(dtype, diag, sub, rhs, out_diag, out_sub, out_x, out_logdet, info, B, T, D, s);
   if (D <= kSsmSweepMaxD && tuning(4) != 1) {

@@ -61,16 +61,11 @@ int launch_fixed(const typename Core::Params& prm, int64_t nchains, cudaStream_t
 }
 
 }  // namespace
-int exp_kalman_summary_d2(int variant, const KalmanSweepParams<double>& p, int64_t nchains,
-                          cudaStream_t s);
 namespace {
 
 template <class Core>
 int launch_core(const typename Core::Params& prm, int64_t nchains, cudaStream_t s) {
   using P = SweepPick<Core>;
-  if constexpr (std::is_same<Core, KalmanSummaryCore<double, 2, false>>::value) {
-    if (tuning(6) > 0) return exp_kalman_summary_d2(tuning(6) - 1, prm, nchains, s);
-  }
   // experiment hook (tuning knob 5) for the config-3 summary core only
   if constexpr (std::is_same<Core, KalmanSummaryCore<double, 2, false>>::value) {
     switch (tuning(5)) {

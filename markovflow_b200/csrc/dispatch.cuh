@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 
 #include "../../include/markovflow_b200.h"
@@ -46,15 +47,29 @@ int big_cholesky(int dtype, const void* diag, const void* sub, const void* rhs, 
 int big_solve(int dtype, const void* ld, const void* ls, const void* rhs, void* out, int64_t n_rhs,
               int64_t Bm, int64_t T, int64_t D, int transpose, cudaStream_t s);
 
-// experimental engine variants (capi_exp.cu), selected with mf_set_tuning knob 6 (> 0: variant - 1)
-int exp_chol_d3(int variant, const void* diag, const void* sub, const void* rhs, void* od, void* os,
-                void* ox, void* logdet, int32_t* info, int64_t B, int64_t T, cudaStream_t s);
-
 // Seed folds of the parallel-in-time paths: one warp per chain (shuffle scan over the segment
 // elements, log2 depth) from this many segments per chain on, else one thread per chain (sequential
 // fold).  Measured on config 5 (B=1024, 28 segments): nat_seed_kernel 99 us thread-per-chain.
 // tuning knob 10 overrides the threshold.
 inline bool warp_fold(int64_t P) { return P >= (tuning(10) > 0 ? tuning(10) : 8); }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: it is set once per (kernel
+// instantiation, device), tracked in a bit mask that each launcher keeps as a function-local static.
+struct SmemOnce {
+  std::atomic<uint64_t> mask{0};
+};
+template <class K>
+inline cudaError_t ensure_smem(SmemOnce& once, K kern, size_t bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const uint64_t bit = 1ull << (dev & 63);
+  if (once.mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return e;
+  once.mask.fetch_or(bit, std::memory_order_release);
+  return cudaSuccess;
+}
 
 inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 

@@ -33,6 +33,7 @@
 //       range hold garbage and must not be used); process steps j0..j0+ns-1 (descending if BACKWARD)
 //   __device__ void finish(const Params&, int64_t chain, bool valid)   called by ALL compute threads
 #pragma once
+#include "dispatch.cuh"
 #include "pipe.cuh"
 
 namespace mf {
@@ -306,12 +307,10 @@ inline cudaError_t launch_chain_sweep(const typename Core::Params& prm, int64_t 
                                       cudaStream_t s, bool spread = false) {
   using Cfg = SweepCfg<Core, C, K, NSI, NSO>;
   auto kern = chain_sweep_kernel<Core, C, K, NSI, NSO>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)Cfg::SMEM_BYTES);
+  static SmemOnce once;  // per instantiation, per device
+  {
+    cudaError_t e = ensure_smem(once, kern, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   // few chains: spread them over all 148 SMs (a CTA then serves fewer than C chains)
   int64_t cpb = C;

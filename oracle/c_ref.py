@@ -18,6 +18,8 @@ def lib():
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.ref_chol_solve_batch.restype = ctypes.c_int64
         _lib.ref_max_threads.restype = ctypes.c_int
+        for name in ("ref_kalman_loglik_batch", "ref_nat_to_ssm_batch", "ref_ssm_to_expectations_batch"):
+            getattr(_lib, name).restype = ctypes.c_int64
     return _lib
 
 
@@ -45,3 +47,53 @@ def chol_solve_batch(diag, sub, rhs=None, nthreads=0):
 
 def max_threads() -> int:
     return int(lib().ref_max_threads())
+
+
+def _c(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def kalman_loglik_batch(mu0, chol_p0, a_s, b_s, chol_q, h, y, chol_r, nthreads=0):
+    """``KalmanFilter.log_likelihood`` per chain through the reference's SpInGP route
+    (``kalman_filter.py:184-255``).  ``a_s [B,T-1,D,D]``, ``h [T,m,D]`` or ``[B,T,m,D]``, ``y [B,T,m]``,
+    ``chol_r [m,m]``.  Returns ``[B]``."""
+    mu0, chol_p0, a_s, b_s, chol_q, h, y, chol_r = map(_c, (mu0, chol_p0, a_s, b_s, chol_q, h, y, chol_r))
+    b, n, d, _ = a_s.shape
+    m = h.shape[-2]
+    hb = 1 if h.ndim == 3 else b
+    out = np.empty(b)
+    nfail = lib().ref_kalman_loglik_batch(
+        _p(mu0), _p(chol_p0), _p(a_s), _p(b_s), _p(chol_q), _p(h), _p(y), _p(chol_r), _p(out),
+        ctypes.c_int64(b), ctypes.c_int64(n + 1), ctypes.c_int(d), ctypes.c_int(m), ctypes.c_int64(hb),
+        ctypes.c_int(nthreads))
+    if nfail:
+        raise ArithmeticError(f"Banded Cholesky decomposition failure in {nfail} chains")
+    return out
+
+
+def nat_to_ssm_batch(theta_lin, theta_diag, theta_sub, nthreads=0):
+    """``naturals_to_ssm_params`` (``ssm_gaussian_transformations.py:332-511``) for ``[B,T,...]`` inputs.
+    Returns ``(As, offsets, chol_P0, chol_Qs, mu0)``."""
+    theta_lin, theta_diag, theta_sub = map(_c, (theta_lin, theta_diag, theta_sub))
+    b, t, d = theta_lin.shape
+    a_s, offs = np.empty((b, t - 1, d, d)), np.empty((b, t - 1, d))
+    l0, lq, mu0 = np.empty((b, d, d)), np.empty((b, t - 1, d, d)), np.empty((b, d))
+    nfail = lib().ref_nat_to_ssm_batch(
+        _p(theta_lin), _p(theta_diag), _p(theta_sub), _p(a_s), _p(offs), _p(l0), _p(lq), _p(mu0),
+        ctypes.c_int64(b), ctypes.c_int64(t), ctypes.c_int(d), ctypes.c_int(nthreads))
+    if nfail:
+        raise ArithmeticError(f"Cholesky failure in {nfail} chains")
+    return a_s, offs, l0, lq, mu0
+
+
+def ssm_to_expectations_batch(mu0, chol_p0, a_s, b_s, chol_q, nthreads=0):
+    """``ssm_to_expectations`` (``ssm_gaussian_transformations.py:31-89``) for ``[B,...]`` parameters."""
+    mu0, chol_p0, a_s, b_s, chol_q = map(_c, (mu0, chol_p0, a_s, b_s, chol_q))
+    b, n, d, _ = a_s.shape
+    el, ed, es = np.empty((b, n + 1, d)), np.empty((b, n + 1, d, d)), np.empty((b, n, d, d))
+    nfail = lib().ref_ssm_to_expectations_batch(
+        _p(mu0), _p(chol_p0), _p(a_s), _p(b_s), _p(chol_q), _p(el), _p(ed), _p(es),
+        ctypes.c_int64(b), ctypes.c_int64(n + 1), ctypes.c_int(d), ctypes.c_int(nthreads))
+    if nfail:
+        raise ArithmeticError(f"Cholesky failure in {nfail} chains")
+    return el, ed, es

@@ -90,6 +90,42 @@ def cholesky_solve(l: Array, b: Array) -> Array:
     return tri_solve_lower_t(l, tri_solve_lower(l, b))
 
 
+def lu_solve(a: Array, b: Array) -> Array:
+    """Batched ``a⁻¹ b`` by LU with partial pivoting (what ``tf.linalg.solve`` / ``np.linalg.solve`` do).
+    float64 goes to LAPACK; other precisions (long double for the extended-precision adjudication of the
+    parity tests, float32 for the same-arithmetic comparison) run the same elimination in loops."""
+    a, b = np.asarray(a), np.asarray(b)
+    dt = np.result_type(a.dtype, b.dtype)
+    if dt == np.float64:
+        return np.linalg.solve(a, b)
+    shape = np.broadcast_shapes(a.shape[:-2], b.shape[:-2])
+    a = np.broadcast_to(a, shape + a.shape[-2:]).astype(dt, copy=True)
+    x = np.broadcast_to(b, shape + b.shape[-2:]).astype(dt, copy=True)
+    d = a.shape[-1]
+    for j in range(d):
+        piv = j + np.argmax(np.abs(a[..., j:, j]), axis=-1)
+        rows_a = np.take_along_axis(a, piv[..., None, None], axis=-2)
+        rows_x = np.take_along_axis(x, piv[..., None, None], axis=-2)
+        np.put_along_axis(a, piv[..., None, None], a[..., j:j + 1, :], axis=-2)
+        np.put_along_axis(x, piv[..., None, None], x[..., j:j + 1, :], axis=-2)
+        a[..., j:j + 1, :], x[..., j:j + 1, :] = rows_a, rows_x
+        for i in range(j + 1, d):
+            f = a[..., i, j] / a[..., j, j]
+            a[..., i, :] = a[..., i, :] - f[..., None] * a[..., j, :]
+            x[..., i, :] = x[..., i, :] - f[..., None] * x[..., j, :]
+    for j in range(d - 1, -1, -1):
+        x[..., j, :] = (x[..., j, :] - np.sum(a[..., j, j + 1:, None] * x[..., j + 1:, :], axis=-2)) / a[..., j, j, None]
+    return x
+
+
+def spd_log_det(a: Array) -> Array:
+    """``log det`` of symmetric positive-definite blocks, in the precision of the input."""
+    a = np.asarray(a)
+    if a.dtype == np.float64:
+        return np.linalg.slogdet(a)[1]
+    return 2.0 * np.sum(np.log(np.diagonal(chol_lower(a), axis1=-2, axis2=-1)), axis=-1)
+
+
 def sym_from_lower(a: Array) -> Array:
     """Mirror the lower triangle (what ``band_to_block(symmetric=True)`` does to diagonal blocks)."""
     low = np.tril(a)
@@ -240,7 +276,7 @@ def solve_triang_band(l_band: Array, r_band: Array, transpose_left: bool = False
     low = unpack_banded_matrix_to_dense(l_band)
     r = unpack_banded_matrix_to_dense(r_band)  # tril(P): right_upper_bandwidth=0
     left = low.T if transpose_left else low
-    x = np.linalg.solve(left, r)
+    x = lu_solve(left, r)
     return pack_dense_to_band(x, r_band.shape[0] - 1)
 
 
@@ -454,7 +490,7 @@ def ssm_build_precision(ssm: SSM) -> Tuple[Array, Array]:
     inv_q_a = cholesky_solve(ssm.chol_q_s, ssm.a_s)
     aqa = _t(ssm.a_s) @ inv_q_a
     chols = ssm.concatenated_cholesky_process_covariance
-    inv_q = cholesky_solve(chols, np.broadcast_to(np.eye(d), chols.shape))
+    inv_q = cholesky_solve(chols, np.broadcast_to(np.eye(d, dtype=chols.dtype), chols.shape))
     diag = inv_q.copy()
     diag[..., :-1, :, :] += aqa
     return diag, -inv_q_a
@@ -553,7 +589,7 @@ def ssm_from_covariances(mu0, p0, a_s, b_s, q_s) -> SSM:
 def _r_inv_from_chol(chol_r: Array) -> Array:
     """``KalmanFilter._r_inv`` (``kalman_filter.py:341-348``)."""
     m = chol_r.shape[-1]
-    return cholesky_solve(chol_r, np.eye(m))
+    return cholesky_solve(chol_r, np.eye(m, dtype=np.asarray(chol_r).dtype))
 
 
 def kalman_k_inv_post(ssm: SSM, h: Array, r_inv: Array) -> Tuple[Array, Array]:
@@ -588,9 +624,9 @@ def kalman_log_likelihood(
     obs_proj = kalman_back_project(h, r_inv, disp)
     term2 = 0.5 * np.sum(np.square(btd_solve(ld, ls, obs_proj)), axis=(-1, -2))
     if r_inv.ndim == 2:
-        log_det_obs = t * np.linalg.slogdet(r_inv)[1]
+        log_det_obs = t * spd_log_det(r_inv)
     else:
-        log_det_obs = np.sum(np.linalg.slogdet(r_inv)[1], axis=-1)
+        log_det_obs = np.sum(spd_log_det(r_inv), axis=-1)
     term3 = 0.5 * ssm_log_det_precision(ssm) - btd_abs_log_det(ld) + 0.5 * log_det_obs
     out = cst + term1 + term2 + term3
     return out if per_chain else np.sum(out)
@@ -601,7 +637,7 @@ def kalman_posterior_ssm(ssm: SSM, h: Array, obs: Array, r_inv: Array) -> SSM:
     d = ssm.state_dim
     post_d, post_s = kalman_k_inv_post(ssm, h, r_inv)
     u_s, chol_d = btd_upper_diagonal_lower(post_d, post_s)
-    eye = np.broadcast_to(np.eye(d), chol_d.shape)
+    eye = np.broadcast_to(np.eye(d, dtype=chol_d.dtype), chol_d.shape)
     obs_proj = kalman_back_project(h, r_inv, obs)
     pd, ps = ssm_build_precision(ssm)
     k_inv_mu = btd_dense_mult(pd, ps, ssm_marginal_means(ssm), symmetric=True)
@@ -831,7 +867,7 @@ def ssm_to_naturals(ssm: SSM):
     )[..., 0]
     aqa = _t(linv_a) @ linv_a
     aqa = np.concatenate([aqa, np.zeros_like(aqa[..., :1, :, :])], axis=-3)
-    prec = cholesky_solve(chols, np.broadcast_to(np.eye(d), chols.shape))
+    prec = cholesky_solve(chols, np.broadcast_to(np.eye(d, dtype=chols.dtype), chols.shape))
     return theta_lin, -0.5 * (prec + aqa), theta_sub
 
 
@@ -841,7 +877,7 @@ def ssm_to_naturals_no_smoothing(ssm: SSM):
     d = ssm.state_dim
     theta_sub = cholesky_solve(chols[..., 1:, :, :], ssm.a_s)
     theta_lin = cholesky_solve(chols, ssm.concatenated_state_offsets[..., None])[..., 0]
-    prec = cholesky_solve(chols, np.broadcast_to(np.eye(d), chols.shape))
+    prec = cholesky_solve(chols, np.broadcast_to(np.eye(d, dtype=chols.dtype), chols.shape))
     return theta_lin, -0.5 * prec, theta_sub
 
 
@@ -853,15 +889,15 @@ def naturals_to_ssm_params(theta_linear, theta_diag, theta_subdiag):
     ld, ls = btd_cholesky(prec_d, prec_s)
     covs, covs_sub = btd_inverse_subset(ld, ls, want_sub=True)
     # As = (Σ_kk⁻¹ Σ_{k,k+1})ᵀ, general (LU) solve as in tf.linalg.solve (:461)
-    a_s = _t(np.linalg.solve(covs[..., :-1, :, :], _t(covs_sub)))
+    a_s = _t(lu_solve(covs[..., :-1, :, :], _t(covs_sub)))
     # block diagonal of (A⁻ᵀ)⁻¹ tril(P): lower triangle of P_kk + A_{k+1}ᵀ P_{k+1,k}, mirrored (:473-490)
     cond_prec = prec_d.copy()
     cond_prec[..., :-1, :, :] += _t(a_s) @ prec_s
     cond_prec = sym_from_lower(cond_prec)
     chol_cond_prec = chol_lower(cond_prec)
-    covariances = cholesky_solve(chol_cond_prec, np.broadcast_to(np.eye(d), cond_prec.shape))
+    covariances = cholesky_solve(chol_cond_prec, np.broadcast_to(np.eye(d, dtype=cond_prec.dtype), cond_prec.shape))
     chols = chol_lower(covariances)
-    eye = np.broadcast_to(np.eye(d), prec_d.shape)
+    eye = np.broadcast_to(np.eye(d, dtype=prec_d.dtype), prec_d.shape)
     prec_times_offsets = btd_solve(eye, -a_s, theta_linear, transpose_left=True)
     offsets = (covariances @ prec_times_offsets[..., None])[..., 0]
     return a_s, offsets[..., 1:, :], chols[..., 0, :, :], chols[..., 1:, :, :], offsets[..., 0, :]
@@ -873,7 +909,7 @@ def naturals_to_ssm_params_no_smoothing(theta_linear, theta_diag, theta_subdiag)
     chol_cp = chol_lower(-2.0 * theta_diag)
     a_s = cholesky_solve(chol_cp[..., 1:, :, :], theta_subdiag)
     offsets = cholesky_solve(chol_cp, theta_linear[..., None])[..., 0]
-    cond_covs = cholesky_solve(chol_cp, np.broadcast_to(np.eye(d), chol_cp.shape))
+    cond_covs = cholesky_solve(chol_cp, np.broadcast_to(np.eye(d, dtype=chol_cp.dtype), chol_cp.shape))
     chols = chol_lower(cond_covs)
     return a_s, offsets[..., 1:, :], chols[..., 0, :, :], chols[..., 1:, :, :], offsets[..., 0, :]
 
@@ -1116,12 +1152,13 @@ def conditional_statistics_from_transitions(a_mt: Array, q_mt: Array, a_tp: Arra
     """``conditionals._conditional_statistics_from_transitions`` (``conditionals.py:128-205``)."""
     a_tp_q_mt = a_tp @ q_mt
     q_mp = q_tp + a_tp @ np.swapaxes(a_tp_q_mt, -1, -2)
-    chol = np.linalg.cholesky(q_mp)
-    v = np.linalg.solve(chol, a_tp_q_mt)
-    e = np.swapaxes(np.linalg.solve(np.swapaxes(chol, -1, -2), v), -1, -2)
+    chol = chol_lower(q_mp)
+    v = tri_solve_lower(chol, a_tp_q_mt)
+    e = np.swapaxes(tri_solve_lower_t(chol, v), -1, -2)
     d = a_mt - e @ a_tp @ a_mt
     if return_precision:
-        t = np.linalg.inv(q_mt) + np.swapaxes(a_tp, -1, -2) @ np.linalg.solve(q_tp, a_tp)
+        eye = np.broadcast_to(np.eye(q_mt.shape[-1], dtype=q_mt.dtype), q_mt.shape)
+        t = lu_solve(q_mt, eye) + np.swapaxes(a_tp, -1, -2) @ lu_solve(q_tp, a_tp)
     else:
         t = q_mt - np.swapaxes(v, -1, -2) @ v
     return d, e, t

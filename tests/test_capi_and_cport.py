@@ -95,3 +95,38 @@ def test_c_port_no_subdiag_and_failure_index(built):
     diag[1, 4] = -np.eye(2)
     _, _, _, info = c_ref.chol_solve_batch(diag, sub, None)
     assert list(info) == [0, 5, 0]
+
+
+@pytest.mark.parametrize("d,m,t,hb", [(1, 1, 9, 1), (2, 1, 40, 1), (3, 2, 17, 3), (5, 3, 6, 3)])
+def test_c_port_kalman_log_likelihood_matches_numpy_oracle(built, d, m, t, hb):
+    """oracle/ssm_ref.c::ref_kalman_loglik_batch walks kalman_filter.py:184-255 like the numpy restatement."""
+    from oracle import c_ref
+    from tests.helpers import random_ssm_arrays
+
+    np.random.seed(d * 100 + t)
+    b = 3
+    mu0, l0, a, bb, lq = random_ssm_arrays((b,), t - 1, d)
+    rng = np.random.default_rng(d + t)
+    h = rng.standard_normal((t, m, d) if hb == 1 else (b, t, m, d))
+    y = rng.standard_normal((b, t, m))
+    lr = np.tril(rng.standard_normal((m, m))) * 0.2 + 0.5 * np.eye(m)
+    got = c_ref.kalman_loglik_batch(mu0, l0, a, bb, lq, h, y, lr)
+    want = O.kalman_log_likelihood(O.SSM(mu0, l0, a, bb, lq), h, y, O._r_inv_from_chol(lr), per_chain=True)
+    assert max_rel_err(got, want) < 1e-12
+
+
+@pytest.mark.parametrize("d,t", [(1, 8), (2, 33), (3, 12), (4, 7)])
+def test_c_port_transforms_match_numpy_oracle(built, d, t):
+    """ref_nat_to_ssm_batch / ref_ssm_to_expectations_batch against the numpy restatements of
+    ssm_gaussian_transformations.py:332-511 and :31-89."""
+    from oracle import c_ref
+    from tests.helpers import random_ssm_arrays
+
+    np.random.seed(d * 10 + t)
+    arrays = random_ssm_arrays((4,), t - 1, d)
+    ssm = O.SSM(*arrays)
+    for g, w in zip(c_ref.ssm_to_expectations_batch(*arrays), O.ssm_to_expectations(ssm)):
+        assert max_rel_err(g, w) < 1e-12
+    th = O.ssm_to_naturals(ssm)
+    for g, w in zip(c_ref.nat_to_ssm_batch(*th), O.naturals_to_ssm_params(*th)):
+        assert max_rel_err(g, w) < 1e-11

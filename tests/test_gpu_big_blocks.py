@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import np_oracle as O
-from tests.helpers import max_rel_err
+from tests.helpers import assert_parity, ld, max_rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = {torch.float64: 1e-10, torch.float32: 1e-4}
@@ -120,58 +120,25 @@ def test_config4_sum_kernel_d17_posterior_precision():
     rhs = rng.standard_normal((b, t, 17))
     chol, x, logdet = SymmetricBlockTriDiagonal(tt(diag), tt(sub)).cholesky_and_solve(tt(rhs), True)
     o_ld, o_ls = O.btd_cholesky(diag, sub)
-    # the jittered process covariances are ill-conditioned (cond ~1e10): compare the factor loosely,
-    # and the well-posed quantities (reconstruction, log-det, solve residual) tightly
-    assert max_rel_err(npy(chol.block_diagonal), o_ld) < 1e-6
+    o_x = O.btd_solve(o_ld, o_ls, rhs)
+    # the jittered process covariances make the posterior precision ill-conditioned (cond ~1e10), so the
+    # float64 restatement of the reference is itself ~1e-7 from the exact factor: SURVEY.md §7's rule --
+    # the long-double block Cholesky of the same float64 blocks is the truth, and the CUDA factor / solve
+    # must be at least as close to it as the restated reference (or within 1e-10)
+    hi = {}
+
+    def truth(key):
+        if not hi:
+            hi["ld"], hi["ls"] = O.btd_cholesky(*ld(diag, sub))
+            hi["x"] = O.btd_solve(hi["ld"], hi["ls"], ld(rhs))
+        return hi[key]
+
+    assert_parity(npy(chol.block_diagonal), o_ld, 1e-10, what="config-4 Ld", truth=lambda: truth("ld"))
+    assert_parity(npy(chol.block_sub_diagonal), o_ls, 1e-10, what="config-4 Ls", truth=lambda: truth("ls"))
+    assert_parity(npy(x), o_x, 1e-10, what="config-4 x", truth=lambda: truth("x"))
     assert max_rel_err(npy(logdet), O.btd_abs_log_det(o_ld)) < 1e-10
     gd, gs = npy(chol.block_diagonal), npy(chol.block_sub_diagonal)
     rec_d = gd @ np.swapaxes(gd, -1, -2)
     rec_d[:, 1:] += gs @ np.swapaxes(gs, -1, -2)
     assert max_rel_err(np.tril(rec_d), np.tril(diag)) < 1e-12
     assert max_rel_err(gs @ np.swapaxes(gd[:, :-1], -1, -2), sub) < 1e-12
-    assert max_rel_err(O.btd_dense_mult(gd, gs, npy(x)), rhs) < 1e-8
-
-
-@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-@pytest.mark.parametrize("t,offset", [(2, 0), (5, 1), (8, 0), (33, 1), (100, 0)])
-def test_team_kernel_variant_matches_oracle(t, offset, dtype):
-    """The experimental one-CTA-per-chain kernel (tuning knob 7 = 2; fraction-free elimination in
-    role-specialised warps, btd_team.cuh) must produce the same factor, solve, log-det and failure
-    report as the oracle, for aligned and misaligned (offset) arrays, out of place and in place."""
-    from markovflow_b200 import _lib
-    from markovflow_b200._lib import check, current_stream, i64, ptr
-
-    d, b = 17, 4
-    diag, sub, _, _ = random_well_conditioned_spd_btd((b,), t, d, rng=t)
-    rhs = np.random.default_rng(t).standard_normal((b, t, d))
-    o_ld, o_ls = O.btd_cholesky(diag, sub)
-    o_x = O.btd_solve(o_ld, o_ls, rhs)
-
-    def shifted(x):
-        flat = torch.empty(x.size + offset, dtype=dtype, device=dev())
-        v = flat[offset:].view(x.shape)
-        v.copy_(torch.as_tensor(x).to(dtype))
-        return v
-
-    lib = _lib.lib()
-    for inplace in (False, True):
-        gd, gs, gr = shifted(diag), shifted(sub), shifted(rhs)
-        od, os_, ox = (gd, gs, gr) if inplace else (torch.full_like(gd, float("nan")),
-                                                    torch.full_like(gs, float("nan")),
-                                                    torch.full_like(gr, float("nan")))
-        logdet = torch.empty(b, dtype=dtype, device=dev())
-        info = torch.empty(b, dtype=torch.int32, device=dev())
-        lib.mf_set_tuning(7, 2)
-        try:
-            check(lib.mf_btd_cholesky(_lib.MF_F64 if dtype == torch.float64 else _lib.MF_F32, ptr(gd), ptr(gs),
-                                      ptr(gr), ptr(od), ptr(os_), ptr(ox), ptr(logdet), ptr(info), i64(b),
-                                      i64(t), i64(d), current_stream()), "mf_btd_cholesky")
-            torch.cuda.synchronize()
-        finally:
-            lib.mf_set_tuning(7, 0)
-        tol = TOL[dtype]
-        assert int(info.abs().max()) == 0
-        assert max_rel_err(npy(od), o_ld) < tol and max_rel_err(npy(os_), o_ls) < tol
-        assert max_rel_err(npy(ox), o_x) < tol
-        assert max_rel_err(npy(logdet), O.btd_abs_log_det(o_ld)) < tol
-        assert np.all(np.triu(npy(od), 1) == 0.0)

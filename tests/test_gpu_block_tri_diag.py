@@ -7,7 +7,9 @@ import pytest
 import torch
 
 from oracle import np_oracle as O
+from tests.helpers import ld as as_ld
 from tests.helpers import (
+    assert_parity,
     blocks_from_dense,
     max_rel_err,
     random_lower_btd,
@@ -217,8 +219,11 @@ def test_solve(batch_shape, with_sub, d, transpose_left, t):
     right = np.random.normal(size=batch_shape + (t, d))
     got = npy(L(tt(diag), tt(sub)).solve(tt(right), transpose_left=transpose_left))
     want = O.btd_solve(diag, sub, right, transpose_left=transpose_left)
-    # ill-conditioned generator: compare to the oracle loosely and check the residual tightly
-    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-8 * np.max(np.abs(want)))
+    # the reference's generator (tests/unit/test_block_tri_diag.py:228-312: N(0,1) diagonal entries) is
+    # ill-conditioned: where 1e-10 from the float64 oracle is out of reach, the long-double substitution
+    # decides (CUDA result at least as close to it as the restated reference); residual checked tightly
+    assert_parity(got, want, 1e-10, what="solve, reference generator",
+                  truth=lambda: O.btd_solve(*as_ld(diag, sub, right), transpose_left=transpose_left))
     es = "...ji,...j->...i" if transpose_left else "...ij,...j->...i"
     resid = np.einsum(es, dense, got.reshape(batch_shape + (t * d,))) - right.reshape(batch_shape + (t * d,))
     assert np.max(np.abs(resid)) < 1e-9 * max(1.0, np.max(np.abs(got)))
@@ -283,8 +288,10 @@ def test_diagonal_of_inverse(batch_shape, with_sub, d, t):
     ld, ls = blocks_from_dense(np.linalg.cholesky(dense), d, with_sub)
     got = npy(L(tt(ld), tt(ls)).block_diagonal_of_inverse())
     want, _ = blocks_from_dense(np.linalg.inv(dense), d, False)
-    np.testing.assert_allclose(got, want, rtol=1e-3, atol=1e-8 * np.max(np.abs(want)))
-    assert max_rel_err(got, O.btd_inverse_subset(ld, ls)[0]) < 1e-7  # ill-conditioned generator
+    np.testing.assert_allclose(got, want, rtol=1e-3, atol=1e-8 * np.max(np.abs(want)))  # reference's own check
+    # ill-conditioned generator (M = L Lᵀ with N(1,1) diagonal entries): long double decides past 1e-10
+    assert_parity(got, O.btd_inverse_subset(ld, ls)[0], 1e-10, what="block_diagonal_of_inverse, reference generator",
+                  truth=lambda: O.btd_inverse_subset(*as_ld(ld, ls))[0])
 
 
 @pytest.mark.parametrize("d", [1, 2, 3, 4, 6, 8])

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import np_oracle as O
-from tests.helpers import max_rel_err, random_ssm_arrays
+from tests.helpers import assert_parity, ld, max_rel_err, random_ssm_arrays
 
 pytestmark = pytest.mark.gpu
 TOL = {torch.float64: 1e-10, torch.float32: 1e-4}
@@ -48,8 +48,13 @@ def test_pairwise_marginals(batch_shape, t, d, dtype):
         assert tuple(jm.shape) == batch_shape + (t + 1, 2 * d)
         assert tuple(jc.shape) == batch_shape + (t + 1, 2 * d, 2 * d)
         assert max_rel_err(npy(jm), want_m) < TOL[dtype]
-        # the oracle takes the covariances through the precision route (less accurate)
-        assert max_rel_err(npy(jc), want_c) < (1e-8 if dtype == torch.float64 else 1e-3)
+        # the oracle takes the covariances through the precision route (state_space_model.py:253-262);
+        # past the tolerance the long-double / float32 evaluation of that route decides
+        adj = (dict(truth=lambda: O.pairwise_marginals(O.SSM(*ld(*arrays)), ld(im), ld(ic))[1])
+               if dtype == torch.float64 else
+               dict(peer=lambda: O.pairwise_marginals(O.SSM(*(a.astype(np.float32) for a in arrays)),
+                                                      im.astype(np.float32), ic.astype(np.float32))[1]))
+        assert_parity(npy(jc), want_c, TOL[dtype], what="pairwise marginal covariances", **adj)
         assert torch.equal(jc, jc.transpose(-1, -2))
 
 

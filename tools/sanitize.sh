@@ -1,0 +1,13 @@
+#!/bin/bash
+# compute-sanitizer memcheck + racecheck over a curated set of GPU tests that covers every ring kernel
+# (TMA Cholesky ring, generic chain sweep fwd/bwd, parallel-in-time paths, in-place / misaligned arrays,
+# Kalman sweeps, large-block kernels).  Usage (on a GPU box): tools/sanitize.sh [outdir]
+out=${1:-gpurun_out}
+mkdir -p "$out"
+SEL='test_cholesky_reads_lower_triangle_only_and_in_place_alias or test_cholesky_parallel_in_time_segments_alias_and_failure or test_config2_shape_slice or test_solve_vs_oracle_tight or test_inverse_subset_with_subdiag_vs_oracle_tight or test_upper_diagonal_lower_vs_oracle_tight or test_in_place_factorisation_and_failure_report or test_config4_sum_kernel or test_log_likelihood_matches_reference_kalman_filter or test_mid_size_batch or test_cvi_style_site_update or test_naturals_to_ssm_params_parallel_in_time_short_segments or test_dense_gp_closed_form or test_marginals_parallel_in_time_segment_length_knob or test_sparse_sites or test_cholesky_solve_logdet_vs_oracle'
+for tool in memcheck racecheck; do
+  timeout 1500 compute-sanitizer --tool $tool --print-limit 20 --error-exitcode 0 \
+    python -m pytest tests -m gpu -q -x -k "$SEL" -p no:cacheprovider > "$out/sanitizer_$tool.log" 2>&1
+  echo "rc=$?" >> "$out/sanitizer_$tool.log"
+  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed|rc=" "$out/sanitizer_$tool.log" | tail -5
+done
