@@ -17,8 +17,8 @@
  *     kernels); mf_btd_cholesky and mf_btd_solve also take MF_SMALL_D_MAX < D <= MF_BIG_D_MAX
  *     (one warp per chain, rows in registers) -- MF_ERR_UNSUPPORTED otherwise.
  *
- * The mf_host_* variants take HOST pointers and perform the host<->device copies themselves
- * (chunked over the batch and pipelined on internal streams); they are what a host-resident
+ * The mf_host_* variants (end of this header) take HOST pointers and perform the host<->device
+ * copies themselves (chunked and pipelined on internal streams); they are what a host-resident
  * framework (TensorFlow CPU tensors) would bind.
  */
 #ifndef MARKOVFLOW_B200_H
@@ -293,6 +293,38 @@ int mf_conditional_statistics(int dtype, const void* a_mt, const void* q_mt, con
 int mf_conditional_predict(int dtype, const void* proj, const void* tcov, const void* pair_means,
                            const void* pair_covs, const int64_t* indices, void* out_mean,
                            void* out_cov, int64_t B, int64_t N, int64_t M, int64_t D, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-buffer variants: same operators, arrays in HOST memory (pinned for asynchronous copies;
+ * pageable memory works, synchronously).  The library stages chunks through per-device slots it
+ * keeps between calls (freed by mf_host_release), overlapping host->device copies, the sweeps and
+ * device->host copies on three internal streams; the call returns when the results are in host
+ * memory.  device < 0: the current device.  bytes_moved (may be NULL) receives
+ * {host->device bytes, device->host bytes}.
+ * ------------------------------------------------------------------------------------------- */
+
+/* mf_btd_cholesky on host arrays, `chunk` chains per stage (<= 0: 128). */
+int mf_host_btd_cholesky(int dtype, const void* diag, const void* sub, const void* rhs,
+                         void* out_diag, void* out_sub, void* out_x, void* out_logdet,
+                         int32_t* info, int64_t B, int64_t T, int64_t D, int64_t chunk, int device,
+                         int64_t* bytes_moved);
+
+/* mf_kalman_log_likelihood on host arrays (layouts as above; out [B] on the host).  The series are
+ * cut into chunks of `chunk_steps` time steps (<= 0: auto); every chunk is reduced on the device to
+ * one scan element while the next one is copied, and the elements are joined at the end, so
+ * (2D^2+D+mD+m) values per step travel to the device and ONE value per series travels back. */
+int mf_host_kalman_log_likelihood(int dtype, const void* mu0, const void* chol_p0, const void* a,
+                                  const void* b, const void* chol_q, const void* h,
+                                  const void* obs, const void* chol_r, void* out, int64_t B,
+                                  int64_t T, int64_t D, int64_t m, int64_t h_batch,
+                                  int64_t r_steps, int64_t chunk_steps, int device,
+                                  int64_t* bytes_moved);
+
+/* cudaHostRegister / cudaHostUnregister for callers whose framework owns pageable buffers. */
+int mf_host_pin(void* ptr, size_t bytes);
+int mf_host_unpin(void* ptr);
+/* Free the staging slots of a device (device < 0: current). */
+int mf_host_release(int device);
 
 #ifdef __cplusplus
 }

@@ -22,7 +22,7 @@ import torch
 from . import _lib
 from ._lib import CholeskyError, check, current_stream, dtype_code, i64, ptr
 from .config import check_numerics
-from .interop import as_torch, require_cuda
+from .interop import framework_of, as_torch, boundary, require_cuda
 
 
 def _prod(shape) -> int:
@@ -45,6 +45,7 @@ class BlockTriDiagonal(abc.ABC):
     """Abstract block-tridiagonal matrix (reference ``block_tri_diag.py:37-288``)."""
 
     def __init__(self, diagonal, symmetric: bool, sub_diagonal=None) -> None:
+        self._fw = framework_of(diagonal, sub_diagonal)  # results come back in the caller's framework
         diagonal = as_torch(diagonal)
         if diagonal.dim() < 3:
             raise ValueError("diagonal must have shape [..., outer_dim, inner_dim, inner_dim]")
@@ -64,6 +65,10 @@ class BlockTriDiagonal(abc.ABC):
                 raise ValueError("diagonal and sub_diagonal must share dtype and device")
         self._sub_diag = sub_diagonal
         self._symmetric = symmetric
+
+    @property
+    def _dev(self) -> torch.device:
+        return self._diag.device
 
     # -- shape properties (reference :100-148) ------------------------------------------------
     @property
@@ -86,10 +91,12 @@ class BlockTriDiagonal(abc.ABC):
         return int(self._diag.shape[-3])
 
     @property
+    @boundary
     def block_diagonal(self) -> torch.Tensor:
         return self._diag
 
     @property
+    @boundary
     def block_sub_diagonal(self) -> Optional[torch.Tensor]:
         return self._sub_diag
 
@@ -106,6 +113,7 @@ class BlockTriDiagonal(abc.ABC):
 
     # -- band view: API compatibility / debugging only (reference :90-98, :206-237) ------------
     @property
+    @boundary
     def as_band(self) -> torch.Tensor:
         """Lower band ``[..., bandwidth+1, outer*inner]`` with ``band[r, j] = M[j+r, j]``."""
         t, d = self.outer_dim, self.inner_dim
@@ -127,6 +135,7 @@ class BlockTriDiagonal(abc.ABC):
             band = torch.where(in_sub, vals, band)
         return band
 
+    @boundary
     def to_dense(self) -> torch.Tensor:
         """Dense ``[..., outer*inner, outer*inner]`` (debugging; reference :150-173)."""
         t, d = self.outer_dim, self.inner_dim
@@ -172,6 +181,7 @@ class BlockTriDiagonal(abc.ABC):
         right = right.expand(tuple(fb) + (t, d)).reshape(_prod(fb), t, d).contiguous()
         return diag, sub, right, tuple(fb), bm
 
+    @boundary
     def dense_mult(self, right, transpose_left: bool = False) -> torch.Tensor:
         """``L x``, ``Lᵀ x`` or (symmetric) ``M x`` (reference :175-199)."""
         diag, sub, rhs, fb, bm = self._prepare_right(right)
@@ -210,6 +220,7 @@ class LowerTriangularBlockTriDiagonal(BlockTriDiagonal):
         # reading them (``diagonal`` may be an expanded, unmaterialised view)
         self._unit_diagonal = bool(unit_diagonal)
 
+    @boundary
     def cholesky_of_block_inverses(self) -> torch.Tensor:
         """``chol((L_k L_kᵀ)⁻¹)`` for every diagonal block ``L_k`` (``kalman_filter.py:170-174``)."""
         require_cuda(self._diag, "block diagonal")
@@ -224,6 +235,7 @@ class LowerTriangularBlockTriDiagonal(BlockTriDiagonal):
         )
         return out.reshape(self._diag.shape)
 
+    @boundary
     def block_diagonal_of_inverse(self) -> torch.Tensor:
         """Block diagonal of ``(L Lᵀ)⁻¹`` (reference :318-337)."""
         return self._inverse_subset(False)[0]
@@ -242,6 +254,7 @@ class LowerTriangularBlockTriDiagonal(BlockTriDiagonal):
         bs = tuple(self.batch_shape)
         return out_d.reshape(bs + (t, d, d)), (None if out_s is None else out_s.reshape(bs + (t - 1, d, d)))
 
+    @boundary
     def solve(self, right, transpose_left: bool = False) -> torch.Tensor:
         """``L⁻¹ x`` or ``L⁻ᵀ x`` (reference :339-351)."""
         diag, sub, rhs, fb, bm = self._prepare_right(right, skip_diag=self._unit_diagonal)
@@ -256,6 +269,7 @@ class LowerTriangularBlockTriDiagonal(BlockTriDiagonal):
         )
         return out.reshape(fb + (t, d))
 
+    @boundary
     def abs_log_det(self) -> torch.Tensor:
         """``Σ log|L_nn|`` with shape ``batch_shape`` (reference :353-366)."""
         diag, _, b, t, d = self._flat()
@@ -268,6 +282,7 @@ class LowerTriangularBlockTriDiagonal(BlockTriDiagonal):
         )
         return out.reshape(tuple(self.batch_shape))
 
+    @boundary
     def __add__(self, other: "LowerTriangularBlockTriDiagonal") -> "LowerTriangularBlockTriDiagonal":
         return LowerTriangularBlockTriDiagonal(*self._added_blocks(other))
 
@@ -278,14 +293,17 @@ class SymmetricBlockTriDiagonal(BlockTriDiagonal):
     def __init__(self, diagonal, sub_diagonal=None) -> None:
         super().__init__(diagonal, symmetric=True, sub_diagonal=sub_diagonal)
 
+    @boundary
     def __add__(self, other: "SymmetricBlockTriDiagonal") -> "SymmetricBlockTriDiagonal":
         return SymmetricBlockTriDiagonal(*self._added_blocks(other))
 
     @property
+    @boundary
     def cholesky(self) -> LowerTriangularBlockTriDiagonal:
         """Block Cholesky ``L Lᵀ = M``; reads the lower triangle only (reference :423-436)."""
         return self.cholesky_and_solve(None)[0]
 
+    @boundary
     def cholesky_and_solve(self, right=None, want_log_det: bool = False):
         """Fused sweep: factor ``M = L Lᵀ`` and, in the same pass, ``L⁻¹ right`` and ``log|L|``.
 
@@ -321,6 +339,7 @@ class SymmetricBlockTriDiagonal(BlockTriDiagonal):
         ld = None if logdet is None else logdet.reshape(bs)
         return chol, x, ld
 
+    @boundary
     def upper_diagonal_lower(
         self,
     ) -> Tuple[LowerTriangularBlockTriDiagonal, LowerTriangularBlockTriDiagonal]:

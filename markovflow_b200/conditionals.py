@@ -17,7 +17,7 @@ import torch
 
 from . import _lib
 from ._lib import check, current_stream, dtype_code, i64, ptr
-from .interop import as_torch, require_cuda
+from .interop import as_torch, boundary, require_cuda
 
 
 def _prod(shape) -> int:
@@ -27,6 +27,7 @@ def _prod(shape) -> int:
     return n
 
 
+@boundary
 def pairwise_marginals(dist, initial_mean, initial_covariance) -> Tuple[torch.Tensor, torch.Tensor]:
     """Mean ``batch + [T+1, 2D]`` and covariance ``batch + [T+1, 2D, 2D]`` of every pair of
     subsequent states, starting from and reverting to ``N(initial_mean, initial_covariance)``."""
@@ -56,6 +57,7 @@ def pairwise_marginals(dist, initial_mean, initial_covariance) -> Tuple[torch.Te
     return o_mean.reshape(bs + (t + 1, 2 * d)), o_cov.reshape(bs + (t + 1, 2 * d, 2 * d))
 
 
+@boundary
 def conditional_statistics_from_transitions(
     state_transitions_to_t, process_covariances_to_t, state_transitions_from_t,
     process_covariances_from_t, return_precision: bool = False,
@@ -105,6 +107,7 @@ def _predict(proj, tcov, pair_means, pair_covs, indices):
     return o_mean.reshape(bs + (n, d)), o_cov.reshape(bs + (n, d, d))
 
 
+@boundary
 def base_conditional_predict(conditional_projections, conditional_covariances, adjacent_states,
                              pairwise_state_covariances=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """``N(P_t m_t, T_t + P_t S_t P_t^T)`` (``T_t`` alone when no pairwise covariance is given)."""
@@ -112,12 +115,14 @@ def base_conditional_predict(conditional_projections, conditional_covariances, a
                     pairwise_state_covariances, None)
 
 
+@boundary
 def insertion_indices(new_time_points, training_time_points) -> torch.Tensor:
     """Index of the pair of training states around every new time point (``tf.searchsorted``,
     reference ``conditionals.py:243``); both inputs sorted along the last axis."""
     return torch.searchsorted(as_torch(training_time_points).contiguous(), as_torch(new_time_points).contiguous())
 
 
+@boundary
 def conditional_predict_from_transitions(
     indices, state_transitions_to_t, process_covariances_to_t, state_transitions_from_t,
     process_covariances_from_t, training_pairwise_means, training_pairwise_covariances=None,

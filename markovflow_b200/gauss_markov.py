@@ -6,6 +6,8 @@ from typing import Tuple
 
 import torch
 
+from .interop import boundary
+
 from .block_tri_diag import SymmetricBlockTriDiagonal
 
 
@@ -33,6 +35,7 @@ class GaussMarkovDistribution(abc.ABC):
     def _build_precision(self) -> SymmetricBlockTriDiagonal: ...
 
     @property
+    @boundary
     def precision(self) -> SymmetricBlockTriDiagonal:
         """Block-tridiagonal precision ``K⁻¹`` (reference ``gauss_markov.py:72-78``)."""
         return self._build_precision()
@@ -49,6 +52,7 @@ class GaussMarkovDistribution(abc.ABC):
     def covariance_blocks(self) -> Tuple[torch.Tensor, torch.Tensor]: ...
 
     @property
+    @boundary
     def marginals(self) -> Tuple[torch.Tensor, torch.Tensor]:
         """``(μ_k, Σ_kk)`` (reference ``gauss_markov.py:107-117``)."""
         return self.marginal_means, self.marginal_covariances
@@ -82,3 +86,6 @@ def check_compatible(dist_1: GaussMarkovDistribution, dist_2: GaussMarkovDistrib
         raise ValueError("batch_shape differs")
     if dist_1.num_transitions != dist_2.num_transitions:
         raise ValueError("num_transitions differs")
+    d1, d2 = getattr(dist_1, "_A_s", None), getattr(dist_2, "_A_s", None)
+    if d1 is not None and d2 is not None and (d1.dtype != d2.dtype or d1.device != d2.device):
+        raise ValueError(f"dtype / device differ: {d1.dtype} on {d1.device} vs {d2.dtype} on {d2.device}")

@@ -1,125 +1,121 @@
-"""Host-buffer entry point: block-tridiagonal Cholesky + solve for data that lives in HOST memory.
+"""Host-buffer entry points: the operators for data that lives in HOST memory.
 
-This is what a host-resident caller (the reference runs TensorFlow on CPU tensors) would use: the
-batch is cut into chunks of chains, and host->device copies, the fused CUDA sweep and device->host
-copies of successive chunks overlap on three streams (PCIe is full duplex).  Device staging slots
-are cached between calls.  Inputs/outputs should be pinned for the copies to be asynchronous.
+This is what a host-resident caller (the reference runs TensorFlow on CPU tensors) binds: thin
+ctypes wrappers of the C ABI's ``mf_host_*`` functions (``include/markovflow_b200.h``,
+``csrc/capi_host.cu``).  The chunking, the three-stream copy/compute pipeline and the device staging
+slots live in the library; nothing here touches the data.  Inputs / outputs should be pinned
+(``torch.empty(..., pin_memory=True)`` or ``mf_host_pin``) for the copies to be asynchronous.
 """
 from __future__ import annotations
 
-from typing import Dict, Optional, Tuple
+import ctypes
+from typing import Optional, Tuple
 
 import torch
 
 from . import _lib
-from ._lib import check, dtype_code, i64, ptr
+from ._lib import check, dtype_code, i64
 from .block_tri_diag import _raise_if_failed
 
-_SLOTS: Dict[tuple, dict] = {}
-NSLOT = 3
+
+def _host(t: Optional[torch.Tensor], name: str, dtype=None) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t)
+    if t.is_cuda:
+        raise ValueError(f"{name}: the host entry points take CPU tensors")
+    if dtype is not None and t.dtype != dtype:
+        raise ValueError(f"{name} must have dtype {dtype}")
+    return t.contiguous()
 
 
-def _slots(chunk: int, t: int, d: int, dtype, device, with_rhs: bool) -> dict:
-    key = (chunk, t, d, dtype, str(device), with_rhs)
-    if key not in _SLOTS:
-        def buf(*shape):
-            return [torch.empty(shape, dtype=dtype, device=device) for _ in range(NSLOT)]
+def _hp(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
 
-        _SLOTS[key] = {
-            "diag": buf(chunk, t, d, d), "sub": buf(chunk, t - 1, d, d),
-            "rhs": buf(chunk, t, d) if with_rhs else None,
-            "ld": buf(chunk, t, d, d), "ls": buf(chunk, t - 1, d, d),
-            "x": buf(chunk, t, d) if with_rhs else None,
-            "info": [torch.empty(chunk, dtype=torch.int32, device=device) for _ in range(NSLOT)],
-            "streams": [torch.cuda.Stream(device=device) for _ in range(3)],
-        }
-    return _SLOTS[key]
+
+def _device_index(device) -> int:
+    if device is None:
+        return -1
+    device = torch.device(device)
+    return -1 if device.index is None else int(device.index)
 
 
 def cholesky_solve_host(
     diag: torch.Tensor,
-    sub: torch.Tensor,
+    sub: Optional[torch.Tensor],
     rhs: Optional[torch.Tensor] = None,
     out: Optional[Tuple[torch.Tensor, ...]] = None,
     chunk: int = 128,
     device: Optional[torch.device] = None,
 ):
-    """``SymmetricBlockTriDiagonal(diag, sub).cholesky`` (+ ``.solve(rhs)``) on host tensors.
+    """``SymmetricBlockTriDiagonal(diag, sub).cholesky`` (+ ``.solve(rhs)``) on host tensors
+    (``mf_host_btd_cholesky``).
 
     ``diag [B,T,D,D]``, ``sub [B,T-1,D,D]``, ``rhs [B,T,D]`` are CPU tensors; returns CPU tensors
     ``(Ld, Ls, x_or_None, info)`` (written into ``out`` when given).  Returns after all copies have
-    landed.  Counts of bytes moved: ``(h2d_bytes, d2h_bytes)`` are attached as attributes of the
-    function (``cholesky_solve_host.last_bytes``).
+    landed.  ``cholesky_solve_host.last_bytes`` = ``(h2d_bytes, d2h_bytes)`` of the last call.
     """
-    assert not diag.is_cuda and not sub.is_cuda, "host entry point takes CPU tensors"
-    device = device or torch.device("cuda", torch.cuda.current_device())
-    b, t, d, _ = diag.shape
+    diag = _host(diag, "diag")
     dtype = diag.dtype
-    chunk = min(chunk, b)
-    s = _slots(chunk, t, d, dtype, device, rhs is not None)
-    h2d, comp, d2h = s["streams"]
+    sub, rhs = _host(sub, "sub", dtype), _host(rhs, "rhs", dtype)
+    b, t, d, _ = diag.shape
     if out is None:
         pin = diag.is_pinned()
         ld_h = torch.empty_like(diag, pin_memory=pin)
-        ls_h = torch.empty_like(sub, pin_memory=pin)
+        ls_h = torch.empty_like(sub, pin_memory=pin) if sub is not None else None
         x_h = torch.empty_like(rhs, pin_memory=pin) if rhs is not None else None
         info_h = torch.empty(b, dtype=torch.int32, pin_memory=pin)
     else:
         ld_h, ls_h, x_h, info_h = out
-    lib = _lib.lib()
-    code = dtype_code(dtype)
-    start = torch.cuda.current_stream(device)
-    ev_start = torch.cuda.Event()
-    ev_start.record(start)
-    h2d.wait_event(ev_start)
-    slot_free = [None] * NSLOT
-    nchunks = (b + chunk - 1) // chunk
-    h2d_bytes = d2h_bytes = 0
-    for c in range(nchunks):
-        b0, b1 = c * chunk, min(b, (c + 1) * chunk)
-        nb = b1 - b0
-        k = c % NSLOT
-        with torch.cuda.stream(h2d):
-            if slot_free[k] is not None:
-                h2d.wait_event(slot_free[k])
-            s["diag"][k][:nb].copy_(diag[b0:b1], non_blocking=True)
-            s["sub"][k][:nb].copy_(sub[b0:b1], non_blocking=True)
-            h2d_bytes += diag[b0:b1].numel() * diag.element_size() + sub[b0:b1].numel() * sub.element_size()
-            if rhs is not None:
-                s["rhs"][k][:nb].copy_(rhs[b0:b1], non_blocking=True)
-                h2d_bytes += rhs[b0:b1].numel() * rhs.element_size()
-            ev_in = torch.cuda.Event()
-            ev_in.record(h2d)
-        with torch.cuda.stream(comp):
-            comp.wait_event(ev_in)
-            check(
-                lib.mf_btd_cholesky(
-                    code, ptr(s["diag"][k]), ptr(s["sub"][k]),
-                    ptr(s["rhs"][k]) if rhs is not None else None,
-                    ptr(s["ld"][k]), ptr(s["ls"][k]),
-                    ptr(s["x"][k]) if rhs is not None else None, None, ptr(s["info"][k]),
-                    i64(nb), i64(t), i64(d), _lib.ctypes.c_void_p(comp.cuda_stream),
-                ),
-                "mf_btd_cholesky",
-            )
-            ev_done = torch.cuda.Event()
-            ev_done.record(comp)
-        with torch.cuda.stream(d2h):
-            d2h.wait_event(ev_done)
-            ld_h[b0:b1].copy_(s["ld"][k][:nb], non_blocking=True)
-            ls_h[b0:b1].copy_(s["ls"][k][:nb], non_blocking=True)
-            d2h_bytes += ld_h[b0:b1].numel() * ld_h.element_size() + ls_h[b0:b1].numel() * ls_h.element_size()
-            if rhs is not None:
-                x_h[b0:b1].copy_(s["x"][k][:nb], non_blocking=True)
-                d2h_bytes += x_h[b0:b1].numel() * x_h.element_size()
-            info_h[b0:b1].copy_(s["info"][k][:nb], non_blocking=True)
-            d2h_bytes += nb * 4
-            ev_out = torch.cuda.Event()
-            ev_out.record(d2h)
-            slot_free[k] = ev_out
-    start.wait_stream(d2h)
-    d2h.synchronize()
-    cholesky_solve_host.last_bytes = (h2d_bytes, d2h_bytes)
-    cholesky_solve_host.last_launches = nchunks
+        for o in (ld_h, ls_h, x_h, info_h):
+            if o is not None and (o.is_cuda or not o.is_contiguous()):
+                raise ValueError("out tensors must be contiguous CPU tensors")
+    moved = (ctypes.c_int64 * 2)()
+    check(
+        _lib.lib().mf_host_btd_cholesky(
+            dtype_code(dtype), _hp(diag), _hp(sub), _hp(rhs), _hp(ld_h), _hp(ls_h), _hp(x_h), None,
+            _hp(info_h), i64(b), i64(t), i64(d), i64(chunk), ctypes.c_int(_device_index(device)), moved),
+        "mf_host_btd_cholesky",
+    )
+    cholesky_solve_host.last_bytes = (int(moved[0]), int(moved[1]))
+    cholesky_solve_host.last_launches = (b + chunk - 1) // max(1, min(chunk, b))
     _raise_if_failed(info_h, "cholesky_solve_host")
     return ld_h, ls_h, x_h, info_h
+
+
+def kalman_log_likelihood_host(
+    initial_mean, chol_initial_covariance, state_transitions, state_offsets, chol_process_covariances,
+    emission_matrix, observations, chol_obs_covariance, chunk_steps: int = 0,
+    device: Optional[torch.device] = None, out: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """``KalmanFilter.log_likelihood`` per series (``kalman_filter.py:184-255``) for state-space-model
+    parameters held in HOST memory (``mf_host_kalman_log_likelihood``): ``state_transitions
+    [B,T-1,D,D]`` ... ``observations [B,T,m]``, ``emission_matrix [T,m,D]`` or ``[B,T,m,D]``,
+    ``chol_obs_covariance [m,m]`` or ``[T,m,m]``.  The series are streamed to the device in chunks of
+    time and reduced there; only ``[B]`` values come back.  ``.last_bytes`` as above."""
+    a = _host(state_transitions, "state_transitions")
+    dtype = a.dtype
+    mu0, l0 = _host(initial_mean, "initial_mean", dtype), _host(chol_initial_covariance, "chol_P0", dtype)
+    bb, lq = _host(state_offsets, "state_offsets", dtype), _host(chol_process_covariances, "chol_Q", dtype)
+    h, y = _host(emission_matrix, "emission_matrix", dtype), _host(observations, "observations", dtype)
+    lr = _host(chol_obs_covariance, "chol_obs_covariance", dtype)
+    bsz, n, d, _ = a.shape
+    t = n + 1
+    m = int(h.shape[-2])
+    hb = 1 if h.dim() == 3 else bsz
+    rs = 1 if lr.dim() == 2 else t
+    if tuple(y.shape) != (bsz, t, m) or tuple(h.shape[-3:]) != (t, m, d):
+        raise ValueError("observations / emission matrix do not match the state-space model")
+    if out is None:
+        out = torch.empty(bsz, dtype=dtype, pin_memory=a.is_pinned())
+    moved = (ctypes.c_int64 * 2)()
+    check(
+        _lib.lib().mf_host_kalman_log_likelihood(
+            dtype_code(dtype), _hp(mu0), _hp(l0), _hp(a), _hp(bb), _hp(lq), _hp(h), _hp(y), _hp(lr),
+            _hp(out), i64(bsz), i64(t), i64(d), i64(m), i64(hb), i64(rs), i64(chunk_steps),
+            ctypes.c_int(_device_index(device)), moved),
+        "mf_host_kalman_log_likelihood",
+    )
+    kalman_log_likelihood_host.last_bytes = (int(moved[0]), int(moved[1]))
+    return out

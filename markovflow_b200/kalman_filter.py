@@ -19,24 +19,19 @@ from . import _lib
 from ._lib import check, current_stream, dtype_code, i64, ptr
 from .block_tri_diag import LowerTriangularBlockTriDiagonal, SymmetricBlockTriDiagonal, _prod
 from .emission_model import EmissionModel
-from .interop import as_torch, require_cuda
+from .interop import framework_of, as_torch, boundary, require_cuda
 from .state_space_model import StateSpaceModel, cholesky_or_zero
 
-_WORKSPACES = {}
-
-
 def _workspace(nbytes: int, device) -> Optional[torch.Tensor]:
-    """Cached scratch buffer for the parallel-in-time path (caller-provided workspace of the ABI)."""
+    """Scratch for the parallel-in-time path (the caller-provided workspace of the ABI), allocated per
+    call: torch's caching allocator is stream-ordered and CUDA-graph safe, so concurrent streams never
+    share a buffer and a captured graph keeps its own (a process-wide cache did neither)."""
     if nbytes == 0:
         return None
-    key = str(device)
-    ws = _WORKSPACES.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        _WORKSPACES[key] = ws
-    return ws
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
 
 
+@boundary
 def kalman_log_likelihood(ssm: StateSpaceModel, emission_matrix: torch.Tensor,
                           observations: torch.Tensor, chol_obs_covariance: torch.Tensor
                           ) -> torch.Tensor:
@@ -87,6 +82,11 @@ class BaseKalmanFilter(abc.ABC):
     def __init__(self, state_space_model: StateSpaceModel, emission_model: EmissionModel) -> None:
         self.prior_ssm = state_space_model
         self.emission = emission_model
+        self._fw = framework_of(state_space_model, emission_model)
+
+    @property
+    def _dev(self) -> torch.device:
+        return self.prior_ssm._dev
 
     @property
     @abc.abstractmethod
@@ -103,10 +103,12 @@ class BaseKalmanFilter(abc.ABC):
     def observations(self) -> torch.Tensor: ...
 
     @property
+    @boundary
     def _k_inv_prior(self) -> SymmetricBlockTriDiagonal:
         return self.prior_ssm.precision
 
     @property
+    @boundary
     def _k_inv_post(self) -> SymmetricBlockTriDiagonal:
         """``K⁻¹ + GᵀΣ⁻¹G`` (reference :85-101), built in one kernel."""
         return SymmetricBlockTriDiagonal(
@@ -120,6 +122,7 @@ class BaseKalmanFilter(abc.ABC):
             return t * torch.logdet(r_inv)
         return torch.sum(torch.logdet(r_inv), dim=-1)
 
+    @boundary
     def _back_project_y_to_state(self, observations) -> torch.Tensor:
         """``HᵀR⁻¹y`` (reference :257-271)."""
         h = self.emission.emission_matrix
@@ -127,14 +130,17 @@ class BaseKalmanFilter(abc.ABC):
         ry = (r_inv @ as_torch(observations, h.device)[..., None])
         return (h.transpose(-1, -2) @ ry)[..., 0]
 
+    @boundary
     def log_likelihood_per_chain(self) -> torch.Tensor:
         return kalman_log_likelihood(self.prior_ssm, self.emission.emission_matrix,
                                      self.observations, self._chol_r)
 
+    @boundary
     def log_likelihood(self) -> torch.Tensor:
         """Marginal log-likelihood, summed over the batch (reference :184-255)."""
         return torch.sum(self.log_likelihood_per_chain())
 
+    @boundary
     def posterior_state_space_model(self) -> StateSpaceModel:
         """The posterior as a state-space model (reference :109-182)."""
         a_inv_post, chol_q_inv_post = self._k_inv_post.upper_diagonal_lower()
@@ -171,6 +177,7 @@ class KalmanFilter(BaseKalmanFilter):
                 "The shape of the observations and the state-space-model parameters are not compatible")
         self._chol_obs_covariance = lr
         self._observations = obs
+        self._fw = framework_of(state_space_model, emission_model, observations, chol_obs_covariance)
 
     @property
     def _chol_r(self) -> torch.Tensor:
@@ -207,6 +214,7 @@ class UnivariateGaussianSitesNat(GaussianSites):
     """Univariate sites in natural parameters ``nat1 [T,1]``, ``nat2 [T,1,1]`` (reference :382-433)."""
 
     def __init__(self, nat1, nat2, log_norm=None) -> None:
+        self._fw = framework_of(nat1, nat2, log_norm)
         self.num_data, self.output_dim = nat1.shape
         if tuple(nat2.shape) != (self.num_data, 1, 1) or self.output_dim != 1:
             raise ValueError("nat1 must be [N, 1] and nat2 [N, 1, 1]")
@@ -215,14 +223,17 @@ class UnivariateGaussianSitesNat(GaussianSites):
         self.log_norm = torch.zeros_like(self.nat1) if log_norm is None else as_torch(log_norm)
 
     @property
+    @boundary
     def means(self) -> torch.Tensor:
         return -0.5 * self.nat1 / self.nat2[..., 0]
 
     @property
+    @boundary
     def precisions(self) -> torch.Tensor:
         return -2.0 * self.nat2
 
     @property
+    @boundary
     def log_det_precisions(self) -> torch.Tensor:
         return torch.log(-2.0 * self.nat2)
 
@@ -241,6 +252,7 @@ class KalmanFilterWithSites(BaseKalmanFilter):
                  sites: GaussianSites) -> None:
         self.sites = sites
         super().__init__(state_space_model, emission_model)
+        self._fw = framework_of(state_space_model, emission_model, sites)
 
     @property
     def _r_inv(self) -> torch.Tensor:
@@ -270,6 +282,7 @@ class KalmanFilterWithSparseSites(BaseKalmanFilter):
         self.sparse_observations = self._drop_batch_shape(as_torch(observations))
         self.grid_shape = (int(num_grid_points), 1)
         super().__init__(state_space_model, emission_model)
+        self._fw = framework_of(state_space_model, emission_model, sites, observations_index, observations)
 
     @staticmethod
     def _drop_batch_shape(tensor: torch.Tensor) -> torch.Tensor:
@@ -310,6 +323,7 @@ class KalmanFilterWithSparseSites(BaseKalmanFilter):
     def observations(self) -> torch.Tensor:
         return self.sparse_to_dense(self.sparse_observations, self.grid_shape)
 
+    @boundary
     def log_likelihood_per_chain(self) -> torch.Tensor:
         ssm = self.prior_ssm
         obs = self.observations

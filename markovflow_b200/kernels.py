@@ -20,10 +20,11 @@ import torch
 
 from . import _lib
 from ._lib import check, current_stream, dtype_code, i64, ptr
-from .interop import as_torch, require_cuda
+from .interop import as_torch, boundary, require_cuda
 from .kalman_filter import _workspace
 
 
+@boundary
 def matern_kalman_log_likelihood(state_dim: int, lengthscale, variance, observations,
                                  chol_obs_covariance, time_points=None, time_deltas=None,
                                  jitter: float = 0.0, first_is_initial: bool = True,
@@ -119,11 +120,13 @@ class _Matern:
         self.jitter = float(jitter)
         self.output_dim = output_dim
 
+    @boundary
     def kalman_log_likelihood_per_chain(self, time_points, observations, chol_obs_covariance):
         return matern_kalman_log_likelihood(self.state_dim, self.lengthscale, self.variance,
                                             observations, chol_obs_covariance,
                                             time_points=time_points, jitter=self.jitter)
 
+    @boundary
     def kalman_log_likelihood(self, time_points, observations, chol_obs_covariance) -> torch.Tensor:
         """``KalmanFilter(kernel.state_space_model(t), kernel.generate_emission_model(t), R, y)
         .log_likelihood()`` (reference ``kalman_filter.py:184-255``: summed over the batch)."""

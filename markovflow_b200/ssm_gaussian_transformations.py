@@ -15,7 +15,7 @@ import torch
 from . import _lib
 from ._lib import check, current_stream, dtype_code, i64, ptr
 from .block_tri_diag import _prod, _raise_if_failed
-from .interop import as_torch, require_cuda
+from .interop import as_torch, boundary, require_cuda
 from .state_space_model import StateSpaceModel
 
 Tensor = torch.Tensor
@@ -60,6 +60,7 @@ def _ssm_outputs(entry: str, lin, diag, sub, *extra) -> Tuple[Tensor, Tensor, Te
     return a, off[..., 1:, :], chol[..., 0, :, :], chol[..., 1:, :, :], off[..., 0, :]
 
 
+@boundary
 def ssm_to_expectations(ssm: StateSpaceModel) -> Tuple[Tensor, Tensor, Tensor]:
     """``(E[x_k], E[x_k x_kᵀ], E[x_{k+1} x_kᵀ])`` (reference :31-89)."""
     mu0, l0, a, b, lq, bsz, t, d = ssm._flat()
@@ -76,6 +77,7 @@ def ssm_to_expectations(ssm: StateSpaceModel) -> Tuple[Tensor, Tensor, Tensor]:
     return lin.reshape(bs + (t, d)), diag.reshape(bs + (t, d, d)), sub.reshape(bs + (t - 1, d, d))
 
 
+@boundary
 def expectations_to_ssm_params(eta_linear, eta_diag, eta_subdiag):
     """Returns ``(As, offsets, chol_P0, chol_Qs, mu0)`` (reference :92-178)."""
     return _ssm_outputs("mf_expectations_to_ssm", eta_linear, eta_diag, eta_subdiag)
@@ -96,21 +98,25 @@ def _to_naturals(ssm: StateSpaceModel, smoothing: bool):
     return lin.reshape(bs + (t, d)), diag.reshape(bs + (t, d, d)), sub.reshape(bs + (t - 1, d, d))
 
 
+@boundary
 def ssm_to_naturals(ssm: StateSpaceModel) -> Tuple[Tensor, Tensor, Tensor]:
     """``(θ_lin, θ_diag, θ_sub)`` (reference :181-253)."""
     return _to_naturals(ssm, True)
 
 
+@boundary
 def ssm_to_naturals_no_smoothing(ssm: StateSpaceModel) -> Tuple[Tensor, Tensor, Tensor]:
     """Reference :256-329."""
     return _to_naturals(ssm, False)
 
 
+@boundary
 def naturals_to_ssm_params(theta_linear, theta_diag, theta_subdiag):
     """Returns ``(As, offsets, chol_P0, chol_Qs, mu0)`` (reference :332-511)."""
     return _ssm_outputs("mf_nat_to_ssm", theta_linear, theta_diag, theta_subdiag, 1)
 
 
+@boundary
 def naturals_to_ssm_params_no_smoothing(theta_linear, theta_diag, theta_subdiag):
     """Reference :514-593."""
     return _ssm_outputs("mf_nat_to_ssm", theta_linear, theta_diag, theta_subdiag, 0)

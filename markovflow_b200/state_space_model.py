@@ -20,7 +20,7 @@ from ._lib import CholeskyError, check, current_stream, dtype_code, i64, ptr
 from .config import check_numerics
 from .block_tri_diag import LowerTriangularBlockTriDiagonal, SymmetricBlockTriDiagonal, _prod
 from .gauss_markov import GaussMarkovDistribution, check_compatible
-from .interop import as_torch, require_cuda
+from .interop import framework_of, as_torch, boundary, require_cuda
 
 
 class StateSpaceModel(GaussMarkovDistribution):
@@ -28,6 +28,8 @@ class StateSpaceModel(GaussMarkovDistribution):
 
     def __init__(self, initial_mean, chol_initial_covariance, state_transitions, state_offsets,
                  chol_process_covariances) -> None:
+        self._fw = framework_of(initial_mean, chol_initial_covariance, state_transitions, state_offsets,
+                                chol_process_covariances)
         mu0 = as_torch(initial_mean)
         dev = mu0.device
         l0 = as_torch(chol_initial_covariance, dev)
@@ -54,6 +56,10 @@ class StateSpaceModel(GaussMarkovDistribution):
             raise ValueError("a StateSpaceModel needs at least one transition")
         self._mu_0, self._chol_P_0, self._A_s, self._b_s, self._chol_Q_s = mu0, l0, a, b, lq
 
+    @property
+    def _dev(self) -> torch.device:
+        return self._A_s.device
+
     # -- shapes / accessors (reference :126-229) -------------------------------------------------
     @property
     def event_shape(self) -> torch.Size:
@@ -72,34 +78,42 @@ class StateSpaceModel(GaussMarkovDistribution):
         return int(self._A_s.shape[-3])
 
     @property
+    @boundary
     def cholesky_process_covariances(self) -> torch.Tensor:
         return self._chol_Q_s
 
     @property
+    @boundary
     def cholesky_initial_covariance(self) -> torch.Tensor:
         return self._chol_P_0
 
     @property
+    @boundary
     def initial_covariance(self) -> torch.Tensor:
         return self._chol_P_0 @ self._chol_P_0.transpose(-1, -2)
 
     @property
+    @boundary
     def concatenated_cholesky_process_covariance(self) -> torch.Tensor:
         return torch.cat([self._chol_P_0[..., None, :, :], self._chol_Q_s], dim=-3)
 
     @property
+    @boundary
     def state_offsets(self) -> torch.Tensor:
         return self._b_s
 
     @property
+    @boundary
     def initial_mean(self) -> torch.Tensor:
         return self._mu_0
 
     @property
+    @boundary
     def concatenated_state_offsets(self) -> torch.Tensor:
         return torch.cat([self._mu_0[..., None, :], self._b_s], dim=-2)
 
     @property
+    @boundary
     def state_transitions(self) -> torch.Tensor:
         return self._A_s
 
@@ -145,28 +159,34 @@ class StateSpaceModel(GaussMarkovDistribution):
 
     # -- moments (reference :231-275, :326-341) ----------------------------------------------------
     @property
+    @boundary
     def marginal_means(self) -> torch.Tensor:
         return self._affine(None, ())
 
     @property
+    @boundary
     def marginal_covariances(self) -> torch.Tensor:
         return self._marginals(False, True, False)[1]
 
     @property
+    @boundary
     def marginals(self) -> Tuple[torch.Tensor, torch.Tensor]:
         mean, cov, _ = self._marginals(True, True, False)
         return mean, cov
 
+    @boundary
     def covariance_blocks(self) -> Tuple[torch.Tensor, torch.Tensor]:
         _, cov, sub = self._marginals(False, True, True)
         return cov, sub
 
+    @boundary
     def subsequent_covariances(self, marginal_covariances) -> torch.Tensor:
         """``Σ_{k+1,k} = A_k Σ_kk`` (reference :326-341)."""
         cov = as_torch(marginal_covariances, self._A_s.device)
         return self._A_s @ cov[..., :-1, :, :]
 
     @property
+    @boundary
     def a_inv_block(self) -> LowerTriangularBlockTriDiagonal:
         """``A⁻¹``: identity diagonal, ``-A_k`` sub-diagonal (reference :277-296)."""
         d, t = self.state_dim, self.num_transitions + 1
@@ -188,6 +208,7 @@ class StateSpaceModel(GaussMarkovDistribution):
         )
         return out.reshape(tuple(sample_shape) + tuple(self.batch_shape) + (t, d))
 
+    @boundary
     def sample(self, sample_shape, generator: Optional[torch.Generator] = None) -> torch.Tensor:
         """Trajectories ``sample_shape + batch_shape + [T, D]`` (reference :298-324)."""
         if isinstance(sample_shape, int):
@@ -199,6 +220,7 @@ class StateSpaceModel(GaussMarkovDistribution):
             return eps
         return self._affine(eps, sample_shape)
 
+    @boundary
     def sample_from_epsilons(self, epsilons) -> torch.Tensor:
         """:meth:`sample` with the standard-normal draw supplied (``[..., batch, T, D]``)."""
         eps = as_torch(epsilons, self._A_s.device)
@@ -206,22 +228,26 @@ class StateSpaceModel(GaussMarkovDistribution):
         sample_shape = tuple(eps.shape[: eps.dim() - nb])
         return self._affine(eps, sample_shape)
 
+    @boundary
     def log_det_precision(self) -> torch.Tensor:
         """``-log|P₀| - Σ log|Q_k|`` (reference :343-373)."""
         l0 = LowerTriangularBlockTriDiagonal(self._chol_P_0[..., None, :, :])
         lq = LowerTriangularBlockTriDiagonal(self._chol_Q_s)
         return -2.0 * (l0.abs_log_det() + lq.abs_log_det())
 
+    @boundary
     def create_non_trainable_copy(self) -> "StateSpaceModel":
         return StateSpaceModel(*(t.detach() for t in (
             self._mu_0, self._chol_P_0, self._A_s, self._b_s, self._chol_Q_s)))
 
+    @boundary
     def create_trainable_copy(self) -> "StateSpaceModel":
         """Copy whose parameters are fresh leaf tensors (reference :396-429; the reference wraps
         them in ``gpflow.Parameter`` with a triangular bijector, which is optimiser plumbing)."""
         return StateSpaceModel(*(t.detach().clone() for t in (
             self._mu_0, self._chol_P_0, self._A_s, self._b_s, self._chol_Q_s)))
 
+    @boundary
     def _build_precision(self) -> SymmetricBlockTriDiagonal:
         """``K⁻¹`` blocks (reference :431-483)."""
         diag, sub = self._precision_blocks(None, None)
@@ -235,11 +261,21 @@ class StateSpaceModel(GaussMarkovDistribution):
         sub = torch.empty(bsz, t - 1, d, d, dtype=a.dtype, device=a.device)
         m, hb, rs = 0, 1, 1
         if h is not None:
+            # same operand handling as kalman_log_likelihood: dtype of the model, emission batch
+            # expanded to the model's batch, shapes checked before any pointer is handed over
+            h = as_torch(h, a.device)
+            r_inv = as_torch(r_inv, a.device)
             m = int(h.shape[-2])
+            if tuple(h.shape[-3:]) != (t, m, d):
+                raise ValueError(f"emission matrix must be [..., {t}, m, {d}], got {tuple(h.shape)}")
+            if tuple(r_inv.shape) not in ((m, m), (t, m, m)):
+                raise ValueError("observation precision must be [m, m] or [T, m, m]")
             hb = 1 if h.dim() == 3 else bsz
-            h = h.reshape(hb, t, m, d).contiguous()
+            if h.dim() > 3 and tuple(h.shape[:-3]) != tuple(self.batch_shape):
+                h = h.expand(tuple(self.batch_shape) + (t, m, d))
+            h = h.reshape(hb, t, m, d).contiguous().to(a.dtype)
             rs = 1 if r_inv.dim() == 2 else t
-            r_inv = r_inv.reshape(rs, m, m).contiguous()
+            r_inv = r_inv.reshape(rs, m, m).contiguous().to(a.dtype)
         check(
             _lib.lib().mf_ssm_build_precision(
                 dtype_code(a.dtype), ptr(l0), ptr(a), ptr(lq), ptr(h), ptr(r_inv), ptr(diag),
@@ -249,6 +285,7 @@ class StateSpaceModel(GaussMarkovDistribution):
         bs = tuple(self.batch_shape)
         return diag.reshape(bs + (t, d, d)), sub.reshape(bs + (t - 1, d, d))
 
+    @boundary
     def log_pdf(self, states) -> torch.Tensor:
         """``log p(states)``: ``[..., batch, T, D] -> [..., batch]`` (reference :485-526)."""
         mu0, l0, a, b, lq, bsz, t, d = self._flat()
@@ -269,6 +306,7 @@ class StateSpaceModel(GaussMarkovDistribution):
         )
         return out.reshape(lead + tuple(self.batch_shape))
 
+    @boundary
     def kl_divergence(self, dist: GaussMarkovDistribution) -> torch.Tensor:
         """``KL(self ‖ dist)`` with shape ``batch_shape`` (reference :528-593)."""
         check_compatible(self, dist)
@@ -284,6 +322,7 @@ class StateSpaceModel(GaussMarkovDistribution):
         )
         return out.reshape(tuple(self.batch_shape))
 
+    @boundary
     def normalizer(self) -> torch.Tensor:
         """Reference :595-609."""
         dim = (self.num_transitions + 1) * self.state_dim
@@ -293,6 +332,7 @@ class StateSpaceModel(GaussMarkovDistribution):
         return 0.5 * (dim * math.log(2.0 * math.pi) - self.log_det_precision() + mahalanobis)
 
 
+@boundary
 def cholesky_or_zero(covariance) -> torch.Tensor:
     """Cholesky factor of every ``[D,D]`` block, an all-zero block mapping to zero (reference
     ``state_space_model.py:634-656``)."""
@@ -313,6 +353,7 @@ def cholesky_or_zero(covariance) -> torch.Tensor:
     return out.reshape(cov.shape)
 
 
+@boundary
 def state_space_model_from_covariances(initial_mean, initial_covariance, state_transitions,
                                        state_offsets, process_covariances) -> StateSpaceModel:
     """Reference ``state_space_model.py:613-664``."""
