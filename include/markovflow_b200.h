@@ -295,6 +295,28 @@ int mf_conditional_predict(int dtype, const void* proj, const void* tcov, const 
                            void* out_cov, int64_t B, int64_t N, int64_t M, int64_t D, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Reverse mode (vector-Jacobian products) -- SURVEY.md 8f-3.  The reference differentiates through
+ * every banded op with TensorFlow's tape (gradients registered by banded-matrices; callers
+ * ssm_natgrad.py:142-172, tests/integration/models/test_gaussian_process_regression.py:117-130).
+ * Each recurrence has an adjoint sweep that walks the chain in the opposite direction.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Adjoint of mf_btd_cholesky: factor ld [B,T,D,D], ls [B,T-1,D,D] (or NULL) and the adjoints of its
+ * blocks g_ld (lower triangles read; NULL = 0), g_ls (NULL = 0)  ->  g_diag [B,T,D,D], the gradient
+ * with respect to the entries the forward pass READS (lower triangles; an off-diagonal entry stands
+ * for both symmetric positions; upper triangles are written as 0), and g_sub [B,T-1,D,D]. */
+int mf_btd_cholesky_bwd(int dtype, const void* ld, const void* ls, const void* g_ld, const void* g_ls,
+                        void* g_diag, void* g_sub, int64_t B, int64_t T, int64_t D, void* stream);
+
+/* Adjoint of mf_ssm_marginals: SSM parameters, the forward results mean [B,T,D], cov [B,T,D,D] and
+ * the adjoints g_mean, g_cov, g_sub (each may be NULL)  ->  g_mu0 [B,D], g_chol_p0 [B,D,D],
+ * g_a [B,T-1,D,D], g_b [B,T-1,D], g_chol_q [B,T-1,D,D] (lower triangles). */
+int mf_ssm_marginals_bwd(int dtype, const void* chol_p0, const void* a, const void* chol_q,
+                         const void* mean, const void* cov, const void* g_mean, const void* g_cov,
+                         const void* g_sub, void* g_mu0, void* g_chol_p0, void* g_a, void* g_b,
+                         void* g_chol_q, int64_t B, int64_t T, int64_t D, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host-buffer variants: same operators, arrays in HOST memory (pinned for asynchronous copies;
  * pageable memory works, synchronously).  The library stages chunks through per-device slots it
  * keeps between calls (freed by mf_host_release), overlapping host->device copies, the sweeps and

@@ -34,6 +34,7 @@ from .ssm_gaussian_transformations import (
     ssm_to_naturals,
     ssm_to_naturals_no_smoothing,
 )
+from .ssm_natgrad import SSMNaturalGradient
 from .kernels import Matern12, Matern32, Matern52, matern_kalman_log_likelihood
 from .state_space_model import (
     StateSpaceModel,
@@ -43,6 +44,7 @@ from .state_space_model import (
 
 __all__ = [
     "Graphed",
+    "SSMNaturalGradient",
     "base_conditional_predict",
     "conditional_predict_from_transitions",
     "conditional_statistics_from_transitions",

@@ -22,6 +22,7 @@ import torch
 from . import _lib
 from ._lib import CholeskyError, check, current_stream, dtype_code, i64, ptr
 from .config import check_numerics
+from .autograd import CholeskyFn, SolveFn, needs_grad
 from .interop import framework_of, as_torch, boundary, require_cuda
 
 
@@ -186,6 +187,8 @@ class BlockTriDiagonal(abc.ABC):
         """``L x``, ``Lᵀ x`` or (symmetric) ``M x`` (reference :175-199)."""
         diag, sub, rhs, fb, bm = self._prepare_right(right)
         t, d = self.outer_dim, self.inner_dim
+        if needs_grad(diag, sub, rhs):
+            return self._dense_mult_torch(diag, sub, rhs, bm, transpose_left).reshape(fb + (t, d))
         out = torch.empty_like(rhs)
         check(
             _lib.lib().mf_btd_dense_mult(
@@ -196,6 +199,27 @@ class BlockTriDiagonal(abc.ABC):
             "mf_btd_dense_mult",
         )
         return out.reshape(fb + (t, d))
+
+    def _dense_mult_torch(self, diag, sub, rhs, bm: int, transpose_left: bool) -> torch.Tensor:
+        """The product in differentiable torch ops (a per-step map: no recursion), used when an operand
+        requires a gradient."""
+        n, t, d = rhs.shape
+        x = rhs.reshape(n // bm, bm, t, d, 1)
+        low = torch.tril(diag)
+        if self._symmetric:
+            low = low + torch.tril(diag, -1).transpose(-1, -2)
+        elif transpose_left:
+            low = low.transpose(-1, -2)
+        y = low @ x
+        if sub is not None:
+            zero = torch.zeros_like(y[:, :, :1])
+            down = torch.cat([zero, sub @ x[:, :, :-1]], dim=2)              # (L x)_k += sub_{k-1} x_{k-1}
+            up = torch.cat([sub.transpose(-1, -2) @ x[:, :, 1:], zero], dim=2)  # (L^T x)_k += sub_k^T x_{k+1}
+            if self._symmetric:
+                y = y + down + up
+            else:
+                y = y + (up if transpose_left else down)
+        return y[..., 0].reshape(n, t, d)
 
     @abc.abstractmethod
     def __add__(self, other):
@@ -259,6 +283,8 @@ class LowerTriangularBlockTriDiagonal(BlockTriDiagonal):
         """``L⁻¹ x`` or ``L⁻ᵀ x`` (reference :339-351)."""
         diag, sub, rhs, fb, bm = self._prepare_right(right, skip_diag=self._unit_diagonal)
         t, d = self.outer_dim, self.inner_dim
+        if needs_grad(diag, sub, rhs):
+            return SolveFn.apply(diag, sub, rhs, bool(transpose_left)).reshape(fb + (t, d))
         out = torch.empty_like(rhs)
         check(
             _lib.lib().mf_btd_solve(
@@ -273,6 +299,9 @@ class LowerTriangularBlockTriDiagonal(BlockTriDiagonal):
     def abs_log_det(self) -> torch.Tensor:
         """``Σ log|L_nn|`` with shape ``batch_shape`` (reference :353-366)."""
         diag, _, b, t, d = self._flat()
+        if needs_grad(diag):  # elementwise + reduction: differentiable torch ops
+            ld = torch.log(torch.diagonal(diag, dim1=-2, dim2=-1).abs()).sum((-1, -2))
+            return ld.reshape(tuple(self.batch_shape))
         out = torch.empty(b, dtype=diag.dtype, device=diag.device)
         check(
             _lib.lib().mf_btd_abs_log_det(
@@ -318,6 +347,8 @@ class SymmetricBlockTriDiagonal(BlockTriDiagonal):
             if tuple(rhs.shape) != tuple(self.batch_shape) + (t, d) or rhs.dtype != diag.dtype:
                 raise ValueError("right must have shape batch_shape + [outer_dim, inner_dim]")
             rhs = rhs.reshape(b, t, d).contiguous()
+        if needs_grad(diag, sub, rhs):
+            return self._cholesky_and_solve_diff(diag, sub, rhs, want_log_det)
         out_d = torch.empty_like(diag)
         out_s = torch.empty_like(sub) if sub is not None else None
         out_x = torch.empty_like(rhs) if rhs is not None else None
@@ -340,6 +371,18 @@ class SymmetricBlockTriDiagonal(BlockTriDiagonal):
         return chol, x, ld
 
     @boundary
+    def _cholesky_and_solve_diff(self, diag, sub, rhs, want_log_det: bool):
+        """The same three results from the differentiable primitives (adjoint sweeps, autograd.py)."""
+        t, d = self.outer_dim, self.inner_dim
+        ld, ls, info = CholeskyFn.apply(diag, sub)
+        _raise_if_failed(info, "SymmetricBlockTriDiagonal.cholesky")
+        bs = tuple(self.batch_shape)
+        chol = LowerTriangularBlockTriDiagonal(
+            ld.reshape(bs + (t, d, d)), None if ls is None else ls.reshape(bs + (t - 1, d, d)))
+        x = None if rhs is None else SolveFn.apply(ld, ls, rhs, False).reshape(bs + (t, d))
+        logdet = chol.abs_log_det() if want_log_det else None
+        return chol, x, logdet
+
     def upper_diagonal_lower(
         self,
     ) -> Tuple[LowerTriangularBlockTriDiagonal, LowerTriangularBlockTriDiagonal]:

@@ -19,6 +19,7 @@ from . import _lib
 from ._lib import check, current_stream, dtype_code, i64, ptr
 from .block_tri_diag import LowerTriangularBlockTriDiagonal, SymmetricBlockTriDiagonal, _prod
 from .emission_model import EmissionModel
+from .autograd import needs_grad
 from .interop import framework_of, as_torch, boundary, require_cuda
 from .state_space_model import StateSpaceModel, cholesky_or_zero
 
@@ -61,6 +62,13 @@ def kalman_log_likelihood(ssm: StateSpaceModel, emission_matrix: torch.Tensor,
     y = y.reshape(bsz, t, m).contiguous().to(a.dtype)
     rs = 1 if lr.dim() == 2 else t
     lr = lr.reshape(rs, m, m).contiguous().to(a.dtype)
+    if needs_grad(mu0, l0, a, b, lq, h, y, lr):
+        from .autograd import kalman_log_likelihood_diff
+        from .block_tri_diag import _raise_if_failed
+
+        ll, info = kalman_log_likelihood_diff(mu0, l0, a, b, lq, h, y, lr if lr.shape[0] > 1 else lr[0])
+        _raise_if_failed(info, "KalmanFilter.log_likelihood")
+        return ll.reshape(tuple(ssm.batch_shape))
     out = torch.empty(bsz, dtype=a.dtype, device=a.device)
     lib = _lib.lib()
     lib.mf_kalman_workspace_bytes.restype = _lib.ctypes.c_size_t

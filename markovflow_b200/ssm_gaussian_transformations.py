@@ -15,6 +15,7 @@ import torch
 from . import _lib
 from ._lib import check, current_stream, dtype_code, i64, ptr
 from .block_tri_diag import _prod, _raise_if_failed
+from .autograd import needs_grad
 from .interop import as_torch, boundary, require_cuda
 from .state_space_model import StateSpaceModel
 
@@ -42,6 +43,8 @@ def _flat_params(lin, diag, sub):
 
 def _ssm_outputs(entry: str, lin, diag, sub, *extra) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
     lin, diag, sub, batch, bsz, t, d = _flat_params(lin, diag, sub)
+    if needs_grad(lin, diag, sub):
+        return _ssm_outputs_diff(entry, lin, diag, sub, batch, t, d, *extra)
     a = torch.empty_like(sub)
     off = torch.empty_like(lin)
     chol = torch.empty_like(diag)
@@ -61,9 +64,44 @@ def _ssm_outputs(entry: str, lin, diag, sub, *extra) -> Tuple[Tensor, Tensor, Te
 
 
 @boundary
+def _ssm_outputs_diff(entry: str, lin, diag, sub, batch, t, d, *extra):
+    """The same outputs with reverse mode (autograd.py): the CUDA kernel runs forward, the torch restatement
+    of the per-step map is differentiated backward.  ``naturals_to_ssm_params`` (a backward recursion) has no
+    adjoint sweep yet."""
+    from .autograd import _RecomputeFn, expectations_to_ssm_torch
+
+    if entry != "mf_expectations_to_ssm":
+        raise NotImplementedError(
+            "naturals_to_ssm_params has no reverse mode yet; expectations_to_ssm_params, ssm_to_expectations, "
+            "ssm_to_naturals, the marginals, kl_divergence and the Kalman log-likelihood are differentiable")
+
+    def cuda_fn(lin_, diag_, sub_):
+        a_ = torch.empty_like(sub_)
+        off_ = torch.empty_like(lin_)
+        chol_ = torch.empty_like(diag_)
+        info = torch.empty(lin_.shape[0], dtype=torch.int32, device=lin_.device)
+        check(getattr(_lib.lib(), entry)(dtype_code(lin_.dtype), ptr(lin_), ptr(diag_), ptr(sub_), ptr(a_),
+                                         ptr(off_), ptr(chol_), ptr(info), i64(lin_.shape[0]), i64(t), i64(d),
+                                         *extra, current_stream()), entry)
+        _raise_if_failed(info, entry)
+        return a_, off_, chol_
+
+    a, off, chol = _RecomputeFn.apply(cuda_fn, expectations_to_ssm_torch, 3, lin, diag, sub)
+    a = a.reshape(batch + (t - 1, d, d))
+    off = off.reshape(batch + (t, d))
+    chol = chol.reshape(batch + (t, d, d))
+    return a, off[..., 1:, :], chol[..., 0, :, :], chol[..., 1:, :, :], off[..., 0, :]
+
+
 def ssm_to_expectations(ssm: StateSpaceModel) -> Tuple[Tensor, Tensor, Tensor]:
     """``(E[x_k], E[x_k x_kᵀ], E[x_{k+1} x_kᵀ])`` (reference :31-89)."""
     mu0, l0, a, b, lq, bsz, t, d = ssm._flat()
+    if needs_grad(mu0, l0, a, b, lq):
+        # the differentiable moment sweep (adjoint: mf_ssm_marginals_bwd) + the outer products of :79-87
+        mean, cov, sub = ssm._marginals(True, True, True)
+        mu = mean[..., None]
+        return (mean, cov + mu @ mu.transpose(-1, -2),
+                sub + mu[..., 1:, :, :] @ mu[..., :-1, :, :].transpose(-1, -2))
     lin = torch.empty(bsz, t, d, dtype=a.dtype, device=a.device)
     diag = torch.empty(bsz, t, d, d, dtype=a.dtype, device=a.device)
     sub = torch.empty(bsz, t - 1, d, d, dtype=a.dtype, device=a.device)
@@ -83,8 +121,29 @@ def expectations_to_ssm_params(eta_linear, eta_diag, eta_subdiag):
     return _ssm_outputs("mf_expectations_to_ssm", eta_linear, eta_diag, eta_subdiag)
 
 
+def _to_naturals_torch(ssm: StateSpaceModel, smoothing: bool):
+    """``ssm_to_naturals`` / ``ssm_to_naturals_no_smoothing`` in differentiable torch ops (per-step maps,
+    reference :181-329), used when a parameter requires a gradient."""
+    a = ssm._A_s
+    d = ssm.state_dim
+    offsets = torch.cat([ssm._mu_0[..., None, :], ssm._b_s], dim=-2)[..., None]
+    chols = torch.tril(torch.cat([ssm._chol_P_0[..., None, :, :], ssm._chol_Q_s], dim=-3))
+    eye = torch.eye(d, dtype=a.dtype, device=a.device).expand(chols.shape)
+    prec = torch.cholesky_solve(eye, chols)
+    tmp = torch.cholesky_solve(offsets, chols)
+    inv_q_a = torch.cholesky_solve(a, chols[..., 1:, :, :])
+    if not smoothing:
+        return tmp[..., 0], -0.5 * prec, inv_q_a
+    lin = torch.cat([tmp[..., :-1, :, :] - a.transpose(-1, -2) @ tmp[..., 1:, :, :], tmp[..., -1:, :, :]], dim=-3)
+    aqa = a.transpose(-1, -2) @ inv_q_a
+    aqa = torch.cat([aqa, torch.zeros_like(aqa[..., :1, :, :])], dim=-3)
+    return lin[..., 0], -0.5 * (prec + aqa), inv_q_a
+
+
 def _to_naturals(ssm: StateSpaceModel, smoothing: bool):
     mu0, l0, a, b, lq, bsz, t, d = ssm._flat()
+    if needs_grad(mu0, l0, a, b, lq):
+        return _to_naturals_torch(ssm, smoothing)
     lin = torch.empty(bsz, t, d, dtype=a.dtype, device=a.device)
     diag = torch.empty(bsz, t, d, d, dtype=a.dtype, device=a.device)
     sub = torch.empty(bsz, t - 1, d, d, dtype=a.dtype, device=a.device)

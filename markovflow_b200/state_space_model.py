@@ -20,6 +20,7 @@ from ._lib import CholeskyError, check, current_stream, dtype_code, i64, ptr
 from .config import check_numerics
 from .block_tri_diag import LowerTriangularBlockTriDiagonal, SymmetricBlockTriDiagonal, _prod
 from .gauss_markov import GaussMarkovDistribution, check_compatible
+from .autograd import MarginalsFn, needs_grad
 from .interop import framework_of, as_torch, boundary, require_cuda
 
 
@@ -141,6 +142,11 @@ class StateSpaceModel(GaussMarkovDistribution):
 
     def _marginals(self, mean: bool, cov: bool, sub: bool):
         mu0, l0, a, b, lq, bsz, t, d = self._flat()
+        if needs_grad(mu0, l0, a, b, lq):
+            bs = tuple(self.batch_shape)
+            o_mean, o_cov, o_sub = MarginalsFn.apply(mu0, l0, a, b, lq)
+            return (o_mean.reshape(bs + (t, d)) if mean else None, o_cov.reshape(bs + (t, d, d)) if cov else None,
+                    o_sub.reshape(bs + (t - 1, d, d)) if sub else None)
         o_mean = torch.empty(bsz, t, d, dtype=a.dtype, device=a.device) if mean else None
         o_cov = torch.empty(bsz, t, d, d, dtype=a.dtype, device=a.device) if cov else None
         o_sub = torch.empty(bsz, t - 1, d, d, dtype=a.dtype, device=a.device) if sub else None
@@ -161,6 +167,8 @@ class StateSpaceModel(GaussMarkovDistribution):
     @property
     @boundary
     def marginal_means(self) -> torch.Tensor:
+        if needs_grad(*self._flat()[:5]):
+            return self._marginals(True, False, False)[0]
         return self._affine(None, ())
 
     @property
@@ -196,6 +204,10 @@ class StateSpaceModel(GaussMarkovDistribution):
 
     def _affine(self, eps: Optional[torch.Tensor], sample_shape) -> torch.Tensor:
         mu0, l0, a, b, lq, bsz, t, d = self._flat()
+        if eps is not None and needs_grad(mu0, l0, a, b, lq, eps):
+            raise NotImplementedError(
+                "StateSpaceModel.sample has no reverse mode yet (draw with torch.no_grad(), or detach the "
+                "parameters); marginals, log_pdf, kl_divergence and the Kalman log-likelihood are differentiable")
         n = _prod(sample_shape) * bsz
         out = torch.empty(n, t, d, dtype=a.dtype, device=a.device)
         if eps is not None:
@@ -244,8 +256,13 @@ class StateSpaceModel(GaussMarkovDistribution):
     def create_trainable_copy(self) -> "StateSpaceModel":
         """Copy whose parameters are fresh leaf tensors (reference :396-429; the reference wraps
         them in ``gpflow.Parameter`` with a triangular bijector, which is optimiser plumbing)."""
-        return StateSpaceModel(*(t.detach().clone() for t in (
+        return StateSpaceModel(*(t.detach().clone().requires_grad_(True) for t in (
             self._mu_0, self._chol_P_0, self._A_s, self._b_s, self._chol_Q_s)))
+
+    @property
+    def trainable_variables(self):
+        """``(A_s, b_s, chol_P_0, chol_Q_s, mu_0)`` -- the order ``ssm_natgrad.py:159-166`` unpacks."""
+        return (self._A_s, self._b_s, self._chol_P_0, self._chol_Q_s, self._mu_0)
 
     @boundary
     def _build_precision(self) -> SymmetricBlockTriDiagonal:
@@ -257,8 +274,6 @@ class StateSpaceModel(GaussMarkovDistribution):
         """Precision blocks, optionally fused with ``+ HᵀR⁻¹H`` (``kalman_filter.py:85-101``).
         ``h``: ``[T,m,D]`` or ``batch + [T,m,D]``; ``r_inv``: ``[m,m]`` or ``[T,m,m]``."""
         mu0, l0, a, b, lq, bsz, t, d = self._flat()
-        diag = torch.empty(bsz, t, d, d, dtype=a.dtype, device=a.device)
-        sub = torch.empty(bsz, t - 1, d, d, dtype=a.dtype, device=a.device)
         m, hb, rs = 0, 1, 1
         if h is not None:
             # same operand handling as kalman_log_likelihood: dtype of the model, emission batch
@@ -276,12 +291,12 @@ class StateSpaceModel(GaussMarkovDistribution):
             h = h.reshape(hb, t, m, d).contiguous().to(a.dtype)
             rs = 1 if r_inv.dim() == 2 else t
             r_inv = r_inv.reshape(rs, m, m).contiguous().to(a.dtype)
-        check(
-            _lib.lib().mf_ssm_build_precision(
-                dtype_code(a.dtype), ptr(l0), ptr(a), ptr(lq), ptr(h), ptr(r_inv), ptr(diag),
-                ptr(sub), i64(bsz), i64(t), i64(d), i64(m), i64(hb), i64(rs), current_stream()),
-            "mf_ssm_build_precision",
-        )
+        if needs_grad(l0, a, lq, h, r_inv):
+            from .autograd import _precision
+
+            diag, sub = _precision(l0, a, lq, h, r_inv)
+        else:
+            diag, sub = _precision_blocks_cuda(l0, a, lq, h, r_inv)
         bs = tuple(self.batch_shape)
         return diag.reshape(bs + (t, d, d)), sub.reshape(bs + (t - 1, d, d))
 
@@ -290,6 +305,8 @@ class StateSpaceModel(GaussMarkovDistribution):
         """``log p(states)``: ``[..., batch, T, D] -> [..., batch]`` (reference :485-526)."""
         mu0, l0, a, b, lq, bsz, t, d = self._flat()
         x = as_torch(states, a.device)
+        if needs_grad(mu0, l0, a, b, lq, x):
+            return self._log_pdf_torch(x)
         nb = len(self.batch_shape)
         if x.dim() < nb + 2 or tuple(x.shape[x.dim() - nb - 2:]) != tuple(self.batch_shape) + (t, d):
             raise ValueError(
@@ -307,12 +324,29 @@ class StateSpaceModel(GaussMarkovDistribution):
         return out.reshape(lead + tuple(self.batch_shape))
 
     @boundary
+    def _log_pdf_torch(self, x: torch.Tensor) -> torch.Tensor:
+        """``log_pdf`` in differentiable torch ops (per-step Gaussian factors, no recursion), used when an
+        operand requires a gradient (reference ``_log_pdf_factors`` :485-526)."""
+        def mvn(res, chol):
+            z = torch.linalg.solve_triangular(chol, res[..., None], upper=False)[..., 0]
+            half_log_det = torch.log(torch.diagonal(chol, dim1=-2, dim2=-1).abs()).sum(-1)
+            return -0.5 * torch.sum(z * z, dim=-1) - half_log_det - 0.5 * res.shape[-1] * math.log(2.0 * math.pi)
+
+        init = mvn(x[..., 0, :] - self._mu_0, torch.tril(self._chol_P_0))
+        cond = (self._A_s @ x[..., :-1, :, None])[..., 0] + self._b_s
+        rest = mvn(x[..., 1:, :] - cond, torch.tril(self._chol_Q_s))
+        return init + rest.sum(-1)
+
     def kl_divergence(self, dist: GaussMarkovDistribution) -> torch.Tensor:
         """``KL(self ‖ dist)`` with shape ``batch_shape`` (reference :528-593)."""
         check_compatible(self, dist)
         q = self._flat()
         p = dist._flat()
         bsz, t, d = q[5], q[6], q[7]
+        if needs_grad(*q[:5], *p[:5]):
+            from .autograd import kl_divergence_diff
+
+            return kl_divergence_diff(q[:5], p[:5]).reshape(tuple(self.batch_shape))
         out = torch.empty(bsz, dtype=q[2].dtype, device=q[2].device)
         check(
             _lib.lib().mf_ssm_kl_divergence(
@@ -333,6 +367,25 @@ class StateSpaceModel(GaussMarkovDistribution):
 
 
 @boundary
+def _precision_blocks_cuda(l0, a, lq, h=None, r_inv=None):
+    """``mf_ssm_build_precision`` on flat operands: ``l0 [B,D,D]``, ``a / lq [B,T-1,D,D]``, optional
+    ``h [1|B,T,m,D]``, ``r_inv [1|T,m,m]``  ->  ``(diag [B,T,D,D], sub [B,T-1,D,D])``."""
+    bsz, n, d, _ = a.shape
+    t = n + 1
+    diag = torch.empty(bsz, t, d, d, dtype=a.dtype, device=a.device)
+    sub = torch.empty(bsz, n, d, d, dtype=a.dtype, device=a.device)
+    m, hb, rs = 0, 1, 1
+    if h is not None:
+        m, hb, rs = int(h.shape[-2]), int(h.shape[0]), int(r_inv.shape[0])
+    check(
+        _lib.lib().mf_ssm_build_precision(
+            dtype_code(a.dtype), ptr(l0), ptr(a), ptr(lq), ptr(h), ptr(r_inv), ptr(diag),
+            ptr(sub), i64(bsz), i64(t), i64(d), i64(m), i64(hb), i64(rs), current_stream()),
+        "mf_ssm_build_precision",
+    )
+    return diag, sub
+
+
 def cholesky_or_zero(covariance) -> torch.Tensor:
     """Cholesky factor of every ``[D,D]`` block, an all-zero block mapping to zero (reference
     ``state_space_model.py:634-656``)."""
