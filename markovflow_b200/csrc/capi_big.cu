@@ -5,6 +5,10 @@
 
 namespace mf {
 
+int big2_cholesky(int dtype, const void* diag, const void* sub, const void* rhs, void* out_diag, void* out_sub,
+                  void* out_x, void* out_logdet, int32_t* info, int64_t B, int64_t T, int64_t D,
+                  cudaStream_t s);  // capi_big2.cu
+
 namespace {
 
 template <typename F>
@@ -37,6 +41,10 @@ int set_smem(K kern, size_t bytes) {  // set on every launch: per-device attribu
 int big_cholesky(int dtype, const void* diag, const void* sub, const void* rhs, void* out_diag,
                  void* out_sub, void* out_x, void* out_logdet, int32_t* info, int64_t B, int64_t T,
                  int64_t D, cudaStream_t s) {
+  // 9 <= D <= 17: half a warp per chain, parallel in time for few long chains (btd_big2.cuh);
+  // tuning knob 7 = 2 keeps the one-warp-per-chain kernel below (A/B measurements)
+  if (D <= 17 && tuning(7) != 2)
+    return big2_cholesky(dtype, diag, sub, rhs, out_diag, out_sub, out_x, out_logdet, info, B, T, D, s);
   return dispatch_big(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;

@@ -142,3 +142,66 @@ def test_config4_sum_kernel_d17_posterior_precision():
     rec_d[:, 1:] += gs @ np.swapaxes(gs, -1, -2)
     assert max_rel_err(np.tril(rec_d), np.tril(diag)) < 1e-12
     assert max_rel_err(gs @ np.swapaxes(gd[:, :-1], -1, -2), sub) < 1e-12
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("d", [9, 12, 16, 17])
+@pytest.mark.parametrize("b,t,segments", [(1, 200, 5), (3, 97, 3), (4, 160, 4), (5, 403, 12), (2, 65, 2)])
+def test_parallel_in_time_large_blocks(b, t, segments, d, dtype):
+    """Few long chains of large blocks (config 4's regime) are cut into time segments (btd_big2.cuh): the
+    first segment is factorised directly, the inner ones are reduced to linear-fractional elements, a fold
+    seeds every segment, and every segment is factorised from its seed.  Tuning knob 7 = number of segments
+    (ragged last segment, odd batches, in-place aliasing, failure report); knob 7 = 1 is the uncut sweep."""
+    from markovflow_b200 import _lib
+    from markovflow_b200._lib import check, current_stream, i64, ptr
+
+    diag, sub, _, _ = random_well_conditioned_spd_btd((b,), t, d, rng=d * 1000 + t)
+    rhs = np.random.default_rng(t).standard_normal((b, t, d))
+    if dtype == torch.float32:
+        diag, sub, rhs = (x.astype(np.float32).astype(np.float64) for x in (diag, sub, rhs))
+    o_ld, o_ls = O.btd_cholesky(diag, sub)
+    o_x = O.btd_solve(o_ld, o_ls, rhs)
+    o_logdet = O.btd_abs_log_det(o_ld)
+    lib = _lib.lib()
+    code = _lib.MF_F64 if dtype == torch.float64 else _lib.MF_F32
+    tol = TOL[dtype]
+    results = {}
+    for knob, inplace in ((segments, False), (segments, True), (1, False)):
+        gd, gs, gr = tt(diag, dtype), tt(sub, dtype), tt(rhs, dtype)
+        od, os_, ox = (gd, gs, gr) if inplace else (torch.full_like(gd, float("nan")), torch.full_like(gs, float("nan")),
+                                                    torch.full_like(gr, float("nan")))
+        logdet = torch.empty(b, dtype=dtype, device=dev())
+        info = torch.full((b,), 7, dtype=torch.int32, device=dev())
+        lib.mf_set_tuning(7, knob)
+        try:
+            check(lib.mf_btd_cholesky(code, ptr(gd), ptr(gs), ptr(gr), ptr(od), ptr(os_), ptr(ox), ptr(logdet),
+                                      ptr(info), i64(b), i64(t), i64(d), current_stream()), "mf_btd_cholesky")
+            torch.cuda.synchronize()
+        finally:
+            lib.mf_set_tuning(7, 0)
+        assert int(info.abs().max()) == 0
+        assert max_rel_err(npy(od), o_ld) < tol and max_rel_err(npy(os_), o_ls) < tol
+        assert max_rel_err(npy(ox), o_x) < tol
+        assert max_rel_err(npy(logdet), o_logdet) < tol
+        assert np.all(np.triu(npy(od), 1) == 0.0)
+        results[(knob, inplace)] = npy(od)
+    # in place == out of place, bit for bit
+    assert np.array_equal(results[(segments, False)], results[(segments, True)])
+
+
+def test_parallel_in_time_large_blocks_failure_is_reported():
+    from markovflow_b200 import CholeskyError, SymmetricBlockTriDiagonal, _lib
+
+    d, t, b = 17, 120, 3
+    diag, sub, _, _ = random_well_conditioned_spd_btd((b,), t, d, rng=11)
+    bad = diag.copy()
+    bad[1, 70] = -bad[1, 70]
+    lib = _lib.lib()
+    lib.mf_set_tuning(7, 4)
+    try:
+        with pytest.raises(CholeskyError):
+            SymmetricBlockTriDiagonal(tt(bad), tt(sub)).cholesky
+        chol = SymmetricBlockTriDiagonal(tt(diag), tt(sub)).cholesky  # the clean batch still factorises
+        assert max_rel_err(npy(chol.block_diagonal), O.btd_cholesky(diag, sub)[0]) < 1e-10
+    finally:
+        lib.mf_set_tuning(7, 0)
