@@ -132,6 +132,16 @@ int mf_ssm_affine_scan(int dtype, const void* mu0, const void* chol_p0, const vo
                        const void* b, const void* chol_q, const void* eps, void* out, int64_t n,
                        int64_t Bm, int64_t T, int64_t D, void* stream);
 
+/* StateSpaceModel.sample (state_space_model.py:298-324) with the standard normals drawn INSIDE the sweep
+ * (SURVEY.md 8f-4): Philox4x32-10 keyed by (seed, trajectory, step), so the n*T*D draws are never written to
+ * or read from memory and do not depend on how the launch is cut.  out [n,T,D]; trajectory c uses SSM chain
+ * c % Bm.  mf_philox_normal writes the same stream out, eps [n,T,D]: mf_ssm_affine_scan on it reproduces the
+ * sample (the reference's tf.random.normal stream cannot be pinned by any port). */
+int mf_ssm_sample(int dtype, const void* mu0, const void* chol_p0, const void* a, const void* b,
+                  const void* chol_q, uint64_t seed, void* out, int64_t n, int64_t Bm, int64_t T,
+                  int64_t D, void* stream);
+int mf_philox_normal(int dtype, uint64_t seed, void* out, int64_t n, int64_t T, int64_t D, void* stream);
+
 /* marginal_means / marginal_covariances / covariance_blocks / subsequent_covariances
  * (state_space_model.py:231-275,326-341) in one forward sweep:  any of out_mean [B,T,D],
  * out_cov [B,T,D,D], out_sub [B,T-1,D,D] (= a_k Sigma_kk) may be NULL. */

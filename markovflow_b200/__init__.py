@@ -8,6 +8,8 @@ from .block_tri_diag import (
 )
 from .conditionals import (
     base_conditional_predict,
+    conditional_predict,
+    conditional_statistics,
     conditional_predict_from_transitions,
     conditional_statistics_from_transitions,
     insertion_indices,
@@ -35,7 +37,13 @@ from .ssm_gaussian_transformations import (
     ssm_to_naturals_no_smoothing,
 )
 from .ssm_natgrad import SSMNaturalGradient
-from .kernels import Matern12, Matern32, Matern52, matern_kalman_log_likelihood
+from .kernels import HarmonicOscillator, Matern12, Matern32, Matern52, SDEKernel, Sum, matern_kalman_log_likelihood
+from .posterior import (
+    AnalyticPosteriorProcess,
+    ConditionalProcess,
+    ImportanceWeightedPosteriorProcess,
+    PosteriorProcess,
+)
 from .state_space_model import (
     StateSpaceModel,
     cholesky_or_zero,
@@ -44,6 +52,15 @@ from .state_space_model import (
 
 __all__ = [
     "Graphed",
+    "AnalyticPosteriorProcess",
+    "ConditionalProcess",
+    "ImportanceWeightedPosteriorProcess",
+    "PosteriorProcess",
+    "HarmonicOscillator",
+    "SDEKernel",
+    "Sum",
+    "conditional_predict",
+    "conditional_statistics",
     "SSMNaturalGradient",
     "base_conditional_predict",
     "conditional_predict_from_transitions",

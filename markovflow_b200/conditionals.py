@@ -134,3 +134,41 @@ def conditional_predict_from_transitions(
         state_transitions_to_t, process_covariances_to_t, state_transitions_from_t, process_covariances_from_t)
     proj = torch.cat([d_t, e_t], dim=-1)
     return _predict(proj, t_t, training_pairwise_means, training_pairwise_covariances, indices)
+
+
+APPROX_INF = 1e10  # reference markovflow/base.py:46: the "time" of the phantom states before / after the data
+
+
+def _conditional_statistics(new_time_points, training_time_points, kernel):
+    """``(P_t, T_t, indices)`` for every new time point (reference ``conditionals.py:207-254``): the two
+    gaps around it go through ``kernel.transition_statistics`` (closed forms, per point), the conditional
+    statistics through ``mf_conditional_statistics``."""
+    new = as_torch(new_time_points)
+    train = as_torch(training_time_points, new.device).to(new.dtype)
+    idx = torch.searchsorted(train.contiguous(), new.contiguous())
+    inf = APPROX_INF * torch.ones_like(train[..., -1:])
+    aug = torch.cat([-inf, train, inf], dim=-1)
+    minus = torch.gather(aug, -1, idx)
+    plus = torch.gather(aug, -1, idx + 1)
+    a_mt, q_mt = kernel.transition_statistics(minus, new - minus)
+    a_tp, q_tp = kernel.transition_statistics(new, plus - new)
+    d_t, e_t, t_t = conditional_statistics_from_transitions(a_mt, q_mt, a_tp, q_tp)
+    return torch.cat([d_t, e_t], dim=-1), t_t, idx
+
+
+@boundary
+def conditional_statistics(new_time_points, training_time_points, kernel) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``(P_t, T_t)`` of ``p(x_t | x_-, x_+) = N(P_t [x_-, x_+], T_t)`` (reference ``conditionals.py:86-125``)."""
+    p, t, _ = _conditional_statistics(new_time_points, training_time_points, kernel)
+    return p, t
+
+
+@boundary
+def conditional_predict(new_time_points, training_time_points, kernel, training_pairwise_means,
+                        training_pairwise_covariances=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The reference's ``conditional_predict`` (``conditionals.py:29-83``), same signature: marginals
+    ``N(P_t m_t, T_t + P_t S_t P_t^T)`` at the (sorted) ``new_time_points`` given the pairwise marginals of the
+    states at the (sorted) ``training_time_points``; without covariances, the conditional density.  The gather
+    of the pairs by insertion index is fused into the prediction kernel."""
+    proj, tcov, idx = _conditional_statistics(new_time_points, training_time_points, kernel)
+    return _predict(proj, tcov, training_pairwise_means, training_pairwise_covariances, idx)

@@ -45,7 +45,41 @@ int mf_ssm_affine_scan(int dtype, const void* mu0, const void* chol_p0, const vo
     constexpr int kD = decltype(dd)::value;
     ssm_affine_scan_kernel<Tp, kD><<<grid_for(n, 32), 32, 0, s>>>(
         (const Tp*)mu0, (const Tp*)chol_p0, (const Tp*)a, (const Tp*)b, (const Tp*)chol_q,
-        (const Tp*)eps, (Tp*)out, n, Bm, T);
+        (const Tp*)eps, (Tp*)out, n, Bm, T, 0, 0ull);
+    return check_launch();
+  });
+}
+
+int mf_ssm_sample(int dtype, const void* mu0, const void* chol_p0, const void* a, const void* b,
+                  const void* chol_q, uint64_t seed, void* out, int64_t n, int64_t Bm, int64_t T, int64_t D,
+                  void* stream) {
+  if (n < 0 || Bm < 1 || T < 1 || D < 1) return MF_ERR_BAD_ARG;
+  if (n == 0) return MF_OK;
+  if (!mu0 || !chol_p0 || !out || (T > 1 && (!a || !b || !chol_q))) return MF_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (D <= kSsmSweepMaxD && T > 1 && tuning(4) != 1) {
+    const int rc = ssm_sweep_affine(dtype, D, mu0, chol_p0, a, b, chol_q, nullptr, out, n, Bm, T, s, 1, seed);
+    if (rc != MF_ERR_UNSUPPORTED) return rc;
+  }
+  return dispatch_small(dtype, D, [&](auto tt, auto dd) {
+    using Tp = typename decltype(tt)::type;
+    constexpr int kD = decltype(dd)::value;
+    ssm_affine_scan_kernel<Tp, kD><<<grid_for(n, 32), 32, 0, s>>>(
+        (const Tp*)mu0, (const Tp*)chol_p0, (const Tp*)a, (const Tp*)b, (const Tp*)chol_q, nullptr, (Tp*)out, n,
+        Bm, T, 1, (unsigned long long)seed);
+    return check_launch();
+  });
+}
+
+int mf_philox_normal(int dtype, uint64_t seed, void* out, int64_t n, int64_t T, int64_t D, void* stream) {
+  if (n < 0 || T < 1 || D < 1) return MF_ERR_BAD_ARG;
+  if (n == 0) return MF_OK;
+  if (!out) return MF_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  return dispatch_small(dtype, D, [&](auto tt, auto dd) {
+    using Tp = typename decltype(tt)::type;
+    constexpr int kD = decltype(dd)::value;
+    philox_normal_kernel<Tp, kD><<<grid_for(n * T, 128), 128, 0, s>>>((Tp*)out, n, T, (unsigned long long)seed);
     return check_launch();
   });
 }

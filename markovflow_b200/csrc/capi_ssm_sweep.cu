@@ -81,30 +81,32 @@ int ssm_sweep_moments(int dtype, int64_t D, int expectations, const void* mu0, c
 
 int ssm_sweep_affine(int dtype, int64_t D, const void* mu0, const void* chol_p0, const void* a,
                      const void* b, const void* chol_q, const void* eps, void* out, int64_t n,
-                     int64_t Bm, int64_t T, cudaStream_t s) {
+                     int64_t Bm, int64_t T, cudaStream_t s, int use_rng, unsigned long long seed) {
   return dispatch_ssm_sweep(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
     SsmAffineParams<Tp> p{(const Tp*)mu0, (const Tp*)chol_p0, (const Tp*)a, (const Tp*)b,
-                          (const Tp*)chol_q, (const Tp*)eps, (Tp*)out, n, Bm, T, 1, T};
+                          (const Tp*)chol_q, (const Tp*)eps, (Tp*)out, n, Bm, T, 1, T, seed};
     if (tuning(2) != 1 && T >= 128 && out != eps) {
       plan_segments(n, T, &p.P, &p.L);
       if (p.L < kD + 2) { p.P = 1; p.L = T; }
     }
-    auto go = [&](auto noise) -> int {
+    auto go = [&](auto noise, auto rng) -> int {
       constexpr bool kN = decltype(noise)::value;
+      constexpr bool kR = decltype(rng)::value;
       if (p.P > 1) {
-        int rc = run<SsmAffineCore<Tp, kD, kN, true>>(p, n * p.P, s);
+        int rc = run<SsmAffineCore<Tp, kD, kN, true, kR>>(p, n * p.P, s);
         if (rc != MF_OK) return rc;
         if (warp_fold(p.P)) ssm_affine_seed_kernel<Tp, kD, true><<<grid_for(n * 32, 128), 128, 0, s>>>(p);
         else ssm_affine_seed_kernel<Tp, kD, false><<<grid_for(n, 128), 128, 0, s>>>(p);
         rc = check_launch();
         if (rc != MF_OK) return rc;
       }
-      return run<SsmAffineCore<Tp, kD, kN, false>>(p, n * p.P, s);
+      return run<SsmAffineCore<Tp, kD, kN, false, kR>>(p, n * p.P, s);
     };
-    if (eps) return go(std::true_type{});
-    return go(std::false_type{});
+    if (use_rng) return go(std::true_type{}, std::true_type{});
+    if (eps) return go(std::true_type{}, std::false_type{});
+    return go(std::false_type{}, std::false_type{});
   });
 }
 

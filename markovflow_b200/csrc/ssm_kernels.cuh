@@ -9,6 +9,7 @@
 #include <cstdint>
 
 #include "smallmat.cuh"
+#include "smallrng.cuh"
 
 namespace mf {
 
@@ -130,12 +131,26 @@ ssm_build_precision_kernel(const T* __restrict__ chol_p0, const T* __restrict__ 
 // = a_inv_block.solve(...) of marginal_means (state_space_model.py:231-251) and sample (:298-324).
 // Output chain c uses SSM chain c % Bm (leading sample dims).  eps may be NULL (means).
 // ---------------------------------------------------------------------------------------------
+// the standard-normal stream of ChainRng written out: eps [n,T,D] (thread per (trajectory, step))
+template <typename T, int D>
+__global__ void __launch_bounds__(128)
+philox_normal_kernel(T* __restrict__ out, int64_t n, int64_t Tn, unsigned long long seed) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= n * Tn) return;
+  ChainRng rng;
+  rng.init(seed, idx / Tn, idx % Tn, D);
+  T e[D];
+  rng.template draw<T, D>(e);
+  store_vec<T, D>(out + idx * D, e);
+}
+
 template <typename T, int D>
 __global__ void __launch_bounds__(32)
 ssm_affine_scan_kernel(const T* __restrict__ mu0, const T* __restrict__ chol_p0,
                        const T* __restrict__ a, const T* __restrict__ b,
                        const T* __restrict__ chol_q, const T* __restrict__ eps,
-                       T* __restrict__ out, int64_t n, int64_t Bm, int64_t Tn) {
+                       T* __restrict__ out, int64_t n, int64_t Bm, int64_t Tn, int use_rng,
+                       unsigned long long seed) {
   const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (c >= n) return;
   constexpr int DD = D * D;
@@ -146,21 +161,25 @@ ssm_affine_scan_kernel(const T* __restrict__ mu0, const T* __restrict__ chol_p0,
   const T* ep = eps ? eps + c * Tn * D : nullptr;
   T* op = out + c * Tn * D;
   T x[D], A[DD], L[DD], off[D], e[D];
+  ChainRng rng;
+  if (use_rng) rng.init(seed, c, 0, D);
   load_vec<T, D>(x, mu0 + cm * D);
-  if (ep) {
+  if (ep || use_rng) {
     load_vec<T, DD>(L, chol_p0 + cm * DD);
     zero_upper<T, D>(L);
-    load_vec<T, D>(e, ep);
+    if (use_rng) rng.template draw<T, D>(e);
+    else load_vec<T, D>(e, ep);
     gemv_add<T, D>(x, L, e);
   }
   store_vec<T, D>(op, x);
   for (int64_t k = 1; k < Tn; ++k) {
     load_vec<T, DD>(A, ap + (k - 1) * DD);
     load_vec<T, D>(off, bp + (k - 1) * D);
-    if (ep) {
+    if (ep || use_rng) {
       load_vec<T, DD>(L, qp + (k - 1) * DD);
       zero_upper<T, D>(L);
-      load_vec<T, D>(e, ep + k * D);
+      if (use_rng) rng.template draw<T, D>(e);
+      else load_vec<T, D>(e, ep + k * D);
       gemv_add<T, D>(off, L, e);
     }
     gemv_add<T, D>(off, A, x);

@@ -11,6 +11,7 @@
 #pragma once
 #include "dispatch.cuh"
 #include "nat_kernels.cuh"
+#include "smallrng.cuh"
 #include "sweep.cuh"
 
 namespace mf {
@@ -552,14 +553,16 @@ struct SsmAffineParams {
   T* out;
   int64_t n, Bm, Tn;
   int64_t P, L;
+  unsigned long long seed;  // RNG cores: the standard normals are drawn in the kernel (smallrng.cuh)
 };
 
-template <typename T_, int D, bool NOISE, bool SUMMARY = false>
+// NOISE: x_k += chol_q eps_k; RNG: eps is drawn in the kernel instead of being streamed in
+template <typename T_, int D, bool NOISE, bool SUMMARY = false, bool RNG = false>
 struct SsmAffineCore {
   using T = T_;
   using Params = SsmAffineParams<T>;
   static constexpr int DD = D * D;
-  static constexpr int NIN = NOISE ? 4 : 2, NOUT = SUMMARY ? 0 : 1;
+  static constexpr int NIN = NOISE ? (RNG ? 3 : 4) : 2, NOUT = SUMMARY ? 0 : 1;
   static constexpr bool BACKWARD = false;
   static constexpr int ein(int i) { return (i == 0 || i == 2) ? DD : D; }
   static constexpr int eout(int) { return D; }
@@ -584,12 +587,14 @@ struct SsmAffineCore {
   T Phi[SUMMARY ? DD : 1];  // column q at Phi[q * D ..]
   int64_t cm, k0_, n_;
   bool live_;
+  ChainRng rng;
   __device__ __forceinline__ void init(const Params& p, int64_t v) {
     const int64_t c = v / p.P;
     cm = c % p.Bm;
     k0_ = (v % p.P) * p.L;
     n_ = seg_steps(p.Tn, k0_, p.L);
     live_ = !SUMMARY || is_live(p, v);
+    if (RNG) rng.init(p.seed, c, k0_, D);
     if (SUMMARY) {
 #pragma unroll
       for (int i = 0; i < DD; ++i) Phi[SUMMARY ? i : 0] = (i / D == i % D) ? T(1) : T(0);
@@ -616,7 +621,8 @@ struct SsmAffineCore {
           T L[DD], e[D];
           ld_s<T, DD>(L, in[2] + j * DD);
           zero_upper<T, D>(L);
-          ld_s<T, D>(e, in[3] + j * D);
+          if (RNG) rng.template draw<T, D>(e);
+          else ld_s<T, D>(e, in[RNG ? 0 : 3] + j * D);
           gemv_add<T, D>(off, L, e);
         }
         gemv_add<T, D>(off, A, x);
@@ -642,7 +648,8 @@ struct SsmAffineCore {
           T L[DD], e[D];
           load_vec<T, DD>(L, p.chol_p0 + cm * DD);
           zero_upper<T, D>(L);
-          ld_s<T, D>(e, in[3] + j * D);
+          if (RNG) rng.template draw<T, D>(e);
+          else ld_s<T, D>(e, in[RNG ? 0 : 3] + j * D);
           gemv_add<T, D>(x, L, e);
         }
       }

@@ -15,7 +15,7 @@ int ssm_sweep_moments(int dtype, int64_t D, int expectations, const void* mu0, c
                       void* o_sub, int64_t B, int64_t T, cudaStream_t s);
 int ssm_sweep_affine(int dtype, int64_t D, const void* mu0, const void* chol_p0, const void* a,
                      const void* b, const void* chol_q, const void* eps, void* out, int64_t n,
-                     int64_t Bm, int64_t T, cudaStream_t s);
+                     int64_t Bm, int64_t T, cudaStream_t s, int use_rng = 0, unsigned long long seed = 0);
 int ssm_sweep_kl(int dtype, int64_t D, const void* q_mu0, const void* q_chol_p0, const void* q_a,
                  const void* q_b, const void* q_chol_q, const void* p_mu0, const void* p_chol_p0,
                  const void* p_a, const void* p_b, const void* p_chol_q, void* out, int64_t B,

@@ -9,11 +9,13 @@ and ``KalmanFilter.log_likelihood`` (``kalman_filter.py:184-255``) reads them ba
 ``kernels/matern.py:80-86,299-324,434-460`` and ``Q_k = P∞ − A_k P∞ A_kᵀ + jitter·I``,
 ``sde_kernel.py:421-446``): a step reads two values instead of ``2D²+2D+1``.
 
-Only what that path needs is mirrored: ``Matern12/32/52(lengthscale, variance, jitter)`` with
-``state_dim`` and ``kalman_log_likelihood``; the kernels' other methods stay with the caller.
+The kernels are mirrored as far as the operator API consumes them (the ``SDEKernel`` protocol below:
+``state_space_model``, ``transition_statistics``, ``generate_emission_model``, initial moments) for
+``Matern12/32/52``, ``HarmonicOscillator`` and ``Sum`` -- per-step closed forms, no recursion.
 """
 from __future__ import annotations
 
+import math
 from typing import Optional
 
 import torch
@@ -107,8 +109,110 @@ def matern_kalman_log_likelihood(state_dim: int, lengthscale, variance, observat
     return ll
 
 
-class _Matern:
-    """Common part of the mirrored Matern kernels (reference ``kernels/matern.py``)."""
+class SDEKernel:
+    """The part of ``markovflow.kernels.SDEKernel`` / ``StationaryKernel`` (``kernels/sde_kernel.py:38-520``)
+    that the operator API consumes: the kernel as a linear SDE ``dx = F x dt + L dB`` observed through
+    ``H = [1, 0, ...]``, i.e. a recipe for state-space models on arbitrary time points.  Closed forms
+    are per-step elementwise maps (no recursion) and stay in torch; everything downstream
+    (``state_space_model(...)``, ``ConditionalProcess``, Kalman filters) runs on the CUDA operators.
+
+    Subclasses provide ``state_dim``, ``steady_state_covariance`` ``[D,D]`` and
+    ``state_transitions(transition_times, time_deltas)``; hyper-parameters may be tensors that
+    require gradients (the closed forms are differentiable)."""
+
+    output_dim: int = 1
+    jitter: float = 0.0
+
+    # -- to be provided ------------------------------------------------------------------------
+    state_dim: int = 0
+
+    def _like(self, ref=None):
+        for v in getattr(self, "_hyper", ()):
+            if isinstance(v, torch.Tensor):
+                return dict(dtype=v.dtype, device=v.device)
+        if isinstance(ref, torch.Tensor):
+            return dict(dtype=ref.dtype if ref.is_floating_point() else torch.float64, device=ref.device)
+        dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        return dict(dtype=torch.float64, device=dev)
+
+    def _pinf(self, ref=None) -> torch.Tensor:
+        """``steady_state_covariance`` on the dtype / device of ``ref`` (python-float hyper-parameters)."""
+        raise NotImplementedError
+
+    @property
+    def steady_state_covariance(self) -> torch.Tensor:
+        return self._pinf(None)
+
+    def state_transitions(self, transition_times, time_deltas) -> torch.Tensor:
+        raise NotImplementedError
+
+    # -- reference API (sde_kernel.py:153-520) ---------------------------------------------------
+    def _jitter(self, ref) -> torch.Tensor:
+        return self.jitter * torch.eye(self.state_dim, dtype=ref.dtype, device=ref.device)
+
+    @property
+    def jitter_matrix(self) -> torch.Tensor:
+        return self._jitter(self.steady_state_covariance)
+
+    def initial_mean(self, batch_shape, ref=None) -> torch.Tensor:
+        kw = self._like(ref)
+        return torch.zeros(tuple(batch_shape) + (self.state_dim,), **kw)
+
+    def initial_covariance(self, initial_time_point) -> torch.Tensor:
+        t0 = as_torch(initial_time_point)
+        pinf = self._pinf(t0)
+        pinf = pinf + self._jitter(pinf)
+        return pinf.expand(tuple(t0.shape[:-1]) + (self.state_dim, self.state_dim))
+
+    def state_offsets(self, transition_times, time_deltas) -> torch.Tensor:
+        dt = as_torch(time_deltas)
+        return torch.zeros(tuple(dt.shape) + (self.state_dim,), dtype=dt.dtype, device=dt.device)
+
+    def transition_statistics(self, transition_times, time_deltas):
+        """``(A_k, Q_k)`` with ``Q_k = Pinf - A_k Pinf A_k^T + jitter I`` (``sde_kernel.py:421-446``)."""
+        a = self.state_transitions(transition_times, time_deltas)
+        pinf = self._pinf(a).to(a.dtype)
+        q = pinf - a @ pinf @ a.transpose(-1, -2)
+        return a, q + self._jitter(a)
+
+    def transition_statistics_from_time_points(self, time_points):
+        tp = as_torch(time_points)
+        return self.transition_statistics(tp[..., :-1], tp[..., 1:] - tp[..., :-1])
+
+    def state_space_model(self, time_points):
+        """``sde_kernel.py:153-171``: the prior on ``time_points`` as a :class:`StateSpaceModel`."""
+        from .state_space_model import state_space_model_from_covariances
+
+        tp = as_torch(time_points)
+        a, q = self.transition_statistics_from_time_points(tp)
+        batch = tuple(tp.shape[:-1])
+        return state_space_model_from_covariances(
+            initial_mean=self.initial_mean(batch, a).to(a.dtype),
+            initial_covariance=self.initial_covariance(tp[..., :1]).to(a.dtype).contiguous(),
+            state_transitions=a,
+            state_offsets=self.state_offsets(tp[..., :-1], tp[..., 1:] - tp[..., :-1]).to(a.dtype),
+            process_covariances=q)
+
+    def build_finite_distribution(self, time_points):
+        return self.state_space_model(time_points)
+
+    def generate_emission_model(self, time_points):
+        """``H = [1, 0, ...]`` tiled over the time points (``sde_kernel.py:173-211``)."""
+        from .emission_model import EmissionModel
+
+        tp = as_torch(time_points)
+        row = self._emission_row().to(tp.dtype if tp.is_floating_point() else torch.float64).to(tp.device)
+        return EmissionModel(row.expand(tuple(tp.shape) + (self.output_dim, self.state_dim)).contiguous())
+
+    def _emission_row(self) -> torch.Tensor:
+        h = torch.zeros(self.output_dim, self.state_dim, dtype=torch.float64)
+        h[:, 0] = 1.0
+        return h
+
+
+class _Matern(SDEKernel):
+    """Common part of the mirrored Matern kernels (reference ``kernels/matern.py``): hyper-parameters,
+    the closed-form SDE statistics and the fused Kalman log-likelihood."""
 
     state_dim: int = 0
 
@@ -119,6 +223,56 @@ class _Matern:
         self.variance = variance
         self.jitter = float(jitter)
         self.output_dim = output_dim
+        self._hyper = (lengthscale, variance)
+
+    def _lam(self, ref=None) -> torch.Tensor:
+        kw = self._like(ref)
+        ls = torch.as_tensor(self.lengthscale, **kw) if not isinstance(self.lengthscale, torch.Tensor) else self.lengthscale
+        return math.sqrt(2.0 * self.state_dim - 1.0) / ls
+
+    def _var(self, ref=None) -> torch.Tensor:
+        kw = self._like(ref)
+        return torch.as_tensor(self.variance, **kw) if not isinstance(self.variance, torch.Tensor) else self.variance
+
+    @property
+    def feedback_matrix(self) -> torch.Tensor:
+        return self._feedback(None)
+
+    def _feedback(self, ref) -> torch.Tensor:
+        """Companion matrix of ``(s + lam)^D`` (``kernels/matern.py:60-78,271-297,407-432``)."""
+        lam, d = self._lam(ref), self.state_dim
+        f = torch.zeros(d, d, dtype=lam.dtype, device=lam.device)
+        for i in range(d - 1):
+            f[i, i + 1] = 1.0
+        coef = [math.comb(d, i) for i in range(d)]
+        row = torch.stack([-coef[i] * lam ** (d - i) for i in range(d)])
+        return torch.cat([f[:-1], row[None]], dim=0)
+
+    def _pinf(self, ref=None) -> torch.Tensor:
+        lam, var = self._lam(ref), self._var(ref)
+        one, zero = torch.ones_like(lam), torch.zeros_like(lam)
+        if self.state_dim == 1:
+            rows = [[one]]
+        elif self.state_dim == 2:
+            rows = [[one, zero], [zero, lam * lam]]
+        else:
+            l2 = lam * lam
+            rows = [[one, zero, -l2 / 3.0], [zero, l2 / 3.0, zero], [-l2 / 3.0, zero, l2 * l2]]
+        return var * torch.stack([torch.stack(r) for r in rows])
+
+    def state_transitions(self, transition_times, time_deltas) -> torch.Tensor:
+        """``A = exp(-lam dt) (I + N dt + N^2 dt^2 / 2)`` with ``N = F + lam I`` nilpotent
+        (``kernels/matern.py:80-86,299-324,434-460``)."""
+        dt = as_torch(time_deltas)
+        lam = self._lam(dt).to(dt.dtype)
+        d = self.state_dim
+        eye = torch.eye(d, dtype=dt.dtype, device=dt.device)
+        n_mat = self._feedback(dt).to(dt.dtype) + lam * eye
+        x = n_mat * dt[..., None, None]
+        poly = eye + x
+        if d == 3:
+            poly = poly + x @ x / 2.0
+        return torch.exp(-lam * dt)[..., None, None] * poly
 
     @boundary
     def kalman_log_likelihood_per_chain(self, time_points, observations, chol_obs_covariance):
@@ -147,3 +301,72 @@ class Matern32(_Matern):
 class Matern52(_Matern):
     """``kernels/matern.py:376-501``."""
     state_dim = 3
+
+
+class HarmonicOscillator(SDEKernel):
+    """``kernels/periodic.py:27-187``: ``k(r) = variance cos(2 pi r / period)``; the state rotates,
+    ``Pinf = variance I`` and ``Q_k = jitter I``."""
+
+    state_dim = 2
+
+    def __init__(self, variance, period, output_dim: int = 1, jitter: float = 0.0) -> None:
+        self.variance, self.period = variance, period
+        self.jitter, self.output_dim = float(jitter), output_dim
+        self._hyper = (variance, period)
+
+    def _pinf(self, ref=None) -> torch.Tensor:
+        kw = self._like(ref)
+        var = self.variance if isinstance(self.variance, torch.Tensor) else torch.as_tensor(self.variance, **kw)
+        return var * torch.eye(2, dtype=var.dtype, device=var.device)
+
+    def state_transitions(self, transition_times, time_deltas) -> torch.Tensor:
+        dt = as_torch(time_deltas)
+        per = self.period if isinstance(self.period, torch.Tensor) else torch.as_tensor(self.period, dtype=dt.dtype, device=dt.device)
+        ang = dt * (2.0 * math.pi / per)
+        c, s = torch.cos(ang), torch.sin(ang)
+        return torch.stack([torch.stack([c, -s], dim=-1), torch.stack([s, c], dim=-1)], dim=-2)
+
+
+class Sum(SDEKernel):
+    """``kernels/sde_kernel.py:540-687``: independent components, block-diagonal state, summed outputs."""
+
+    def __init__(self, kernels, jitter: float = 0.0) -> None:
+        self.kernels = list(kernels)
+        self.jitter = float(jitter)
+        self.output_dim = self.kernels[0].output_dim
+        self.state_dim = sum(k.state_dim for k in self.kernels)
+        self._hyper = tuple(h for k in self.kernels for h in getattr(k, "_hyper", ()))
+
+    def _pinf(self, ref=None) -> torch.Tensor:
+        return torch.block_diag(*(k._pinf(ref) for k in self.kernels))
+
+    def state_transitions(self, transition_times, time_deltas) -> torch.Tensor:
+        dt = as_torch(time_deltas)
+        blocks = [k.state_transitions(transition_times, dt) for k in self.kernels]
+        out = torch.zeros(tuple(dt.shape) + (self.state_dim, self.state_dim), dtype=blocks[0].dtype, device=dt.device)
+        o = 0
+        for k, blk in zip(self.kernels, blocks):
+            out[..., o:o + k.state_dim, o:o + k.state_dim] = blk
+            o += k.state_dim
+        return out
+
+    def transition_statistics(self, transition_times, time_deltas):
+        """Block-diagonal of the components' statistics plus this kernel's jitter (``:592-640``)."""
+        dt = as_torch(time_deltas)
+        parts = [k.transition_statistics(transition_times, dt) for k in self.kernels]
+        a = torch.zeros(tuple(dt.shape) + (self.state_dim, self.state_dim), dtype=parts[0][0].dtype, device=dt.device)
+        q = torch.zeros_like(a)
+        o = 0
+        for k, (ak, qk) in zip(self.kernels, parts):
+            a[..., o:o + k.state_dim, o:o + k.state_dim] = ak
+            q[..., o:o + k.state_dim, o:o + k.state_dim] = qk
+            o += k.state_dim
+        return a, q + self._jitter(a)
+
+    def _emission_row(self) -> torch.Tensor:
+        h = torch.zeros(self.output_dim, self.state_dim, dtype=torch.float64)
+        o = 0
+        for k in self.kernels:
+            h[:, o] = 1.0
+            o += k.state_dim
+        return h

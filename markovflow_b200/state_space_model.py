@@ -221,16 +221,57 @@ class StateSpaceModel(GaussMarkovDistribution):
         return out.reshape(tuple(sample_shape) + tuple(self.batch_shape) + (t, d))
 
     @boundary
-    def sample(self, sample_shape, generator: Optional[torch.Generator] = None) -> torch.Tensor:
-        """Trajectories ``sample_shape + batch_shape + [T, D]`` (reference :298-324)."""
+    def sample(self, sample_shape, generator: Optional[torch.Generator] = None,
+               seed: Optional[int] = None) -> torch.Tensor:
+        """Trajectories ``sample_shape + batch_shape + [T, D]`` (reference :298-324).
+
+        By default the standard normals are drawn INSIDE the sweep (``mf_ssm_sample``: Philox4x32-10 keyed by
+        ``seed``, trajectory and step -- nothing is written or read for them); ``seed`` defaults to a draw from
+        torch's global CPU generator, so ``torch.manual_seed`` makes samples reproducible.
+        :meth:`sample_epsilons` returns the same stream.  With a ``generator`` the draws come from
+        ``torch.randn`` and are streamed through ``mf_ssm_affine_scan``."""
         if isinstance(sample_shape, int):
             sample_shape = (sample_shape,)
         sample_shape = tuple(int(s) for s in sample_shape)
         full = sample_shape + tuple(self.batch_shape) + tuple(self.event_shape)
-        eps = torch.randn(full, dtype=self._A_s.dtype, device=self._A_s.device, generator=generator)
-        if eps.numel() == 0:
-            return eps
-        return self._affine(eps, sample_shape)
+        if generator is not None:
+            eps = torch.randn(full, dtype=self._A_s.dtype, device=self._A_s.device, generator=generator)
+            if eps.numel() == 0:
+                return eps
+            return self._affine(eps, sample_shape)
+        mu0, l0, a, b, lq, bsz, t, d = self._flat()
+        if needs_grad(mu0, l0, a, b, lq):
+            raise NotImplementedError(
+                "StateSpaceModel.sample has no reverse mode yet (draw with torch.no_grad(), or detach the parameters)")
+        n = _prod(sample_shape) * bsz
+        out = torch.empty(n, t, d, dtype=a.dtype, device=a.device)
+        if n == 0:
+            return out.reshape(full)
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (), dtype=torch.int64).item())
+        check(
+            _lib.lib().mf_ssm_sample(
+                dtype_code(a.dtype), ptr(mu0), ptr(l0), ptr(a), ptr(b), ptr(lq), _lib.ctypes.c_uint64(int(seed)),
+                ptr(out), i64(n), i64(bsz), i64(t), i64(d), current_stream()),
+            "mf_ssm_sample",
+        )
+        return out.reshape(full)
+
+    def sample_epsilons(self, sample_shape, seed: int) -> torch.Tensor:
+        """The standard normals :meth:`sample` draws in its kernel for ``seed``, written out
+        (``mf_philox_normal``): ``sample_from_epsilons(sample_epsilons(shape, seed)) == sample(shape, seed=seed)``."""
+        if isinstance(sample_shape, int):
+            sample_shape = (sample_shape,)
+        sample_shape = tuple(int(s) for s in sample_shape)
+        t, d = self.num_transitions + 1, self.state_dim
+        n = _prod(sample_shape) * _prod(self.batch_shape)
+        out = torch.empty(n, t, d, dtype=self._A_s.dtype, device=self._A_s.device)
+        check(
+            _lib.lib().mf_philox_normal(dtype_code(out.dtype), _lib.ctypes.c_uint64(int(seed)), ptr(out), i64(n),
+                                        i64(t), i64(d), current_stream()),
+            "mf_philox_normal",
+        )
+        return out.reshape(sample_shape + tuple(self.batch_shape) + (t, d))
 
     @boundary
     def sample_from_epsilons(self, epsilons) -> torch.Tensor:
