@@ -291,29 +291,44 @@ def other_configs(dev, rank, world, dist, peak, args):
     t3 = 10_000_000
     ssm, h, y, lr = bench_inputs.kalman_inputs_config3(t3, dev)
     mu0, l0, a, b, lq, _, _, d = ssm._flat()
+    ring = None
     if world == 1:
         ms = _timed(lambda: mf.kalman_log_likelihood(ssm, h, y, lr))
         ll = float(mf.kalman_log_likelihood(ssm, h, y, lr))
         e3 = entry(t3, 104, ms, workload="Matern32 D=2, ONE series T=1e7, f64 (parallel in time, one pass)",
                    loglik=ll, scaling="single GPU")
     else:
+        from markovflow_b200.parallel import PeerRing, time_sharded_log_likelihood
+
         seg = time_segment(mu0, l0, a, b, lq, h.reshape(1, t3, 1, d), y.reshape(1, t3, 1),
                            lr.reshape(1, 1, 1), rank, world)
         eng = CudaKalmanEngine()
+        ring = PeerRing(torch.float64, 1, d)  # peer-mapped regions (cudaIpc over NVLink), set up once
 
-        def sharded():
+        def via_nccl():
             elem = eng.segment_summary(seg)
             gathered = [torch.empty_like(elem) for _ in range(world)]
             dist.all_gather(gathered, elem)
             return eng.fold(torch.stack(gathered), d)[:, -1]
 
-        ms = _timed(sharded)
-        tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ll = float(sharded()[0])
-        e3 = entry(t3, 104, float(tms.item()), workload=f"Matern32 D=2, ONE series T=1e7, f64, time-sharded over "
-                   f"{world} GPUs (segment element, NCCL all-gather of {world} x 136 B, ordered fold)",
-                   loglik=ll, scaling="strong", frac_note="of ONE GPU's peak; / n_gpus for the aggregate")
+        def via_peers():
+            return time_sharded_log_likelihood(seg, engine=eng, ring=ring)
+
+        def timed_max(fn):
+            dist.barrier()
+            ms_ = _timed(fn)
+            t_ = torch.tensor([ms_], dtype=torch.float64, device=dev)
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            return float(t_.item())
+
+        ms_nccl = timed_max(via_nccl)
+        ms = timed_max(via_peers)
+        ll = float(via_peers()[0])
+        e3 = entry(t3, 104, ms, workload=f"Matern32 D=2, ONE series T=1e7, f64, time-sharded over {world} GPUs: "
+                   "segment element + exchange over peer memory + ordered join in ONE reduction kernel "
+                   "(mf_kalman_time_sharded_log_likelihood)", loglik=ll, scaling="strong",
+                   ms_nccl_all_gather_plus_fold=ms_nccl, rel_diff_peers_vs_nccl=abs(ll - float(via_nccl()[0])) / abs(ll),
+                   frac_note="of ONE GPU's peak; / n_gpus for the aggregate")
     if rank == 0:
         # parity at the named size: the C port of the reference's SpInGP route over the WHOLE series, and
         # end to end from host memory (mf_host_kalman_log_likelihood: 104 B per step in, one value out)
@@ -354,7 +369,8 @@ def other_configs(dev, rank, world, dist, peak, args):
         kw = dict(scaling="single GPU", ms_cuda_graph_replay=_timed(mf.Graphed(fused), warm=2, reps=10))
     else:
         first, seg_dt, seg_y = matern_time_segment(dts, y2, rank, world)
-        fused = lambda: time_sharded_matern_log_likelihood(2, one, one, seg_dt, seg_y, lr, first)
+        fused = lambda: ring.matern(2, one, one, seg_dt, seg_y, lr, first)[0]
+        dist.barrier()
         ms = _timed(fused)
         tms = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -371,6 +387,36 @@ def other_configs(dev, rank, world, dist, peak, args):
     out["config3_kalman_loglik_from_time_deltas"] = e
     del dts, y2, ssm, h, y, mu0, l0, a, b, lq
     torch.cuda.empty_cache()
+    # ---- the same job ten times longer (T = 1e8): per-GPU work that outweighs the exchange latency --------
+    try:
+        t8 = 100_000_000
+        ssm8, h8, y8, lr8 = bench_inputs.kalman_inputs_config3(t8, dev)
+        if world == 1:
+            ms8 = _timed(lambda: mf.kalman_log_likelihood(ssm8, h8, y8, lr8), warm=2, reps=5)
+            ll8 = float(mf.kalman_log_likelihood(ssm8, h8, y8, lr8))
+            out["config3_kalman_loglik_T1e8"] = entry(t8, 104, ms8, loglik=ll8, scaling="single GPU",
+                                                      workload="Matern32 D=2, ONE series T=1e8, f64")
+        else:
+            f8 = ssm8._flat()
+            seg8 = time_segment(*f8[:5], h8.reshape(1, t8, 1, 2), y8.reshape(1, t8, 1), lr8.reshape(1, 1, 1), rank, world)
+            del ssm8, h8, y8, f8
+            torch.cuda.empty_cache()
+            eng8 = CudaKalmanEngine()
+            dist.barrier()
+            ms8 = _timed(lambda: time_sharded_log_likelihood(seg8, engine=eng8, ring=ring), warm=2, reps=5)
+            t_ = torch.tensor([ms8], dtype=torch.float64, device=dev)
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            ll8 = float(time_sharded_log_likelihood(seg8, engine=eng8, ring=ring)[0])
+            out["config3_kalman_loglik_T1e8"] = entry(
+                t8, 104, float(t_.item()), loglik=ll8, scaling="strong",
+                workload=f"Matern32 D=2, ONE series T=1e8, f64, time-sharded over {world} GPUs (peer-memory exchange)")
+            del seg8
+        torch.cuda.empty_cache()
+    except Exception as exc:  # noqa: BLE001
+        out["config3_kalman_loglik_T1e8"] = {"skipped": f"{type(exc).__name__}: {exc}"}
+    if ring is not None:
+        dist.barrier()
+        ring.close()
     if rank != 0:
         return out, kalman_e2e
 

@@ -219,6 +219,27 @@ int mf_kalman_log_likelihood_seeded(int dtype, const void* mu0, const void* chol
                                     int summaries_valid, void* workspace, size_t workspace_bytes,
                                     void* stream);
 
+/* The same protocol in ONE call per rank with the exchange inside the reduction kernel: every rank owns a
+ * peer-mapped region (mf_peer_alloc / mf_peer_open: cudaIpc, NVLink peer-to-peer) of
+ * mf_kalman_peer_region_bytes; the thread that holds a series' local element stores it into EVERY rank's
+ * region, raises a flag, waits for the flags of all ranks and joins the `world` elements in rank (= time) order.
+ * No NCCL collective, no extra launch.  peer_regions[r] = rank r's region as mapped in this process
+ * (peer_regions[rank] = the own allocation); epoch = call counter (> 0, the same on every rank; regions are
+ * double-buffered on its parity).  out [B]: log-likelihood of the WHOLE series (the same on every rank),
+ * out_elem [B, 3D^2+2D+1]: its joined element.  m = 1 and D <= 4 (MF_ERR_UNSUPPORTED otherwise); world <= 8. */
+size_t mf_kalman_peer_region_bytes(int dtype, int64_t B, int64_t D, int world);
+int mf_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);  /* zeroed device memory + its IPC handle */
+int mf_peer_open(const unsigned char* handle64, void** ptr);           /* map a peer's region */
+int mf_peer_close(void* ptr);
+int mf_peer_free(void* ptr);
+int mf_kalman_time_sharded_log_likelihood(int dtype, const void* mu0, const void* chol_p0, const void* a,
+                                          const void* b, const void* chol_q, const void* h,
+                                          const void* obs, const void* chol_r, void* out, void* out_elem,
+                                          int64_t B, int64_t T, int64_t D, int64_t m, int64_t h_batch,
+                                          int64_t r_steps, int first_is_initial, void* const* peer_regions,
+                                          int rank, int world, uint64_t epoch, void* workspace,
+                                          size_t workspace_bytes, void* stream);
+
 /* KalmanFilter.log_likelihood of a stationary Matern prior with the state-space
  * model built INSIDE the kernel from the time deltas.  Replaces, in one launch (+ one reduction),
  *   SDEKernel.state_space_model (kernels/sde_kernel.py:153-171)
@@ -242,6 +263,16 @@ int mf_kalman_matern_log_likelihood(int dtype, const void* lengthscale, const vo
                                     const void* chol_r, void* out, void* out_elem, int64_t B,
                                     int64_t T, int64_t D, int first_is_initial, void* workspace,
                                     size_t workspace_bytes, void* stream);
+
+/* mf_kalman_matern_log_likelihood of ONE time segment per rank with the exchange of the segment elements inside
+ * the reduction kernel (see mf_kalman_time_sharded_log_likelihood): out [B] = log-likelihood of the whole series. */
+int mf_kalman_matern_time_sharded_log_likelihood(int dtype, const void* lengthscale, const void* variance,
+                                                 double jitter, const void* time_deltas, const void* obs,
+                                                 const void* chol_r, void* out, void* out_elem, int64_t B,
+                                                 int64_t T, int64_t D, int first_is_initial,
+                                                 void* const* peer_regions, int rank, int world,
+                                                 uint64_t epoch, void* workspace, size_t workspace_bytes,
+                                                 void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Natural / expectation parameter transforms (markovflow/ssm_gaussian_transformations.py)

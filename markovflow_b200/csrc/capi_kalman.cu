@@ -1,4 +1,6 @@
 // C-ABI entry points for the Kalman log-likelihood (include/markovflow_b200.h).
+#include <cstring>
+
 #include "dispatch.cuh"
 #include "kalman_kernels.cuh"
 #include "kalman_sweep_api.h"
@@ -182,11 +184,103 @@ size_t mf_kalman_workspace_bytes(int dtype, int64_t B, int64_t T, int64_t D) {
   return legacy;
 }
 
+}  // extern "C"
+
+namespace {
+
+int fill_peers(KalmanPeerArgs& pa, void* const* regions, int rank, int world, uint64_t epoch) {
+  if (world < 1 || world > 8 || rank < 0 || rank >= world || epoch == 0 || !regions) return MF_ERR_BAD_ARG;
+  pa.rank = rank; pa.world = world; pa.epoch = epoch;
+  for (int r = 0; r < 8; ++r) pa.region[r] = r < world ? regions[r] : nullptr;
+  for (int r = 0; r < world; ++r)
+    if (!pa.region[r]) return MF_ERR_BAD_ARG;
+  return MF_OK;
+}
+
+int segment_summary_impl(int dtype, const void* mu0, const void* chol_p0, const void* a,
+                         const void* b, const void* chol_q, const void* h, const void* obs,
+                         const void* chol_r, void* out_elem, int64_t B, int64_t T, int64_t D,
+                         int64_t m, int64_t h_batch, int64_t r_steps, int first_is_initial,
+                         void* workspace, size_t workspace_bytes, void* stream, const KalmanPeerArgs* peers,
+                         void* out_ell);
+
+}  // namespace
+
+extern "C" {
+
 int mf_kalman_segment_summary(int dtype, const void* mu0, const void* chol_p0, const void* a,
                               const void* b, const void* chol_q, const void* h, const void* obs,
                               const void* chol_r, void* out_elem, int64_t B, int64_t T, int64_t D,
                               int64_t m, int64_t h_batch, int64_t r_steps, int first_is_initial,
                               void* workspace, size_t workspace_bytes, void* stream) {
+  return segment_summary_impl(dtype, mu0, chol_p0, a, b, chol_q, h, obs, chol_r, out_elem, B, T, D, m, h_batch,
+                              r_steps, first_is_initial, workspace, workspace_bytes, stream, nullptr, nullptr);
+}
+
+int mf_kalman_time_sharded_log_likelihood(int dtype, const void* mu0, const void* chol_p0, const void* a,
+                                          const void* b, const void* chol_q, const void* h, const void* obs,
+                                          const void* chol_r, void* out, void* out_elem, int64_t B, int64_t T,
+                                          int64_t D, int64_t m, int64_t h_batch, int64_t r_steps,
+                                          int first_is_initial, void* const* peer_regions, int rank, int world,
+                                          uint64_t epoch, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!out || !out_elem) return MF_ERR_BAD_ARG;
+  KalmanPeerArgs pa;
+  const int rc = fill_peers(pa, peer_regions, rank, world, epoch);
+  if (rc != MF_OK) return rc;
+  return segment_summary_impl(dtype, mu0, chol_p0, a, b, chol_q, h, obs, chol_r, out_elem, B, T, D, m, h_batch,
+                              r_steps, first_is_initial, workspace, workspace_bytes, stream, &pa, out);
+}
+
+size_t mf_kalman_peer_region_bytes(int dtype, int64_t B, int64_t D, int world) {
+  if (B < 1 || D < 1 || world < 1) return 0;
+  const size_t es = dtype == MF_F64 ? 8 : 4;
+  const size_t N = 3 * D * D + 2 * D + 1;
+  return es * 2 * (size_t)world * B * N + 8 * 2 * (size_t)world * B;
+}
+
+int mf_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64) {
+  if (!bytes || !ptr || !handle64) return MF_ERR_BAD_ARG;
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) return check_launch();
+  if (cudaMemset(p, 0, bytes) != cudaSuccess) return check_launch();
+  cudaIpcMemHandle_t hd;
+  if (cudaIpcGetMemHandle(&hd, p) != cudaSuccess) { cudaFree(p); return check_launch(); }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &hd, 64);
+  *ptr = p;
+  return MF_OK;
+}
+
+int mf_peer_open(const unsigned char* handle64, void** ptr) {
+  if (!handle64 || !ptr) return MF_ERR_BAD_ARG;
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle64, 64);
+  if (cudaIpcOpenMemHandle(ptr, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) return check_launch();
+  return MF_OK;
+}
+
+int mf_peer_close(void* ptr) {
+  if (!ptr) return MF_ERR_BAD_ARG;
+  if (cudaIpcCloseMemHandle(ptr) != cudaSuccess) return check_launch();
+  return MF_OK;
+}
+
+int mf_peer_free(void* ptr) {
+  if (!ptr) return MF_ERR_BAD_ARG;
+  if (cudaFree(ptr) != cudaSuccess) return check_launch();
+  return MF_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+int segment_summary_impl(int dtype, const void* mu0, const void* chol_p0, const void* a,
+                         const void* b, const void* chol_q, const void* h, const void* obs,
+                         const void* chol_r, void* out_elem, int64_t B, int64_t T, int64_t D,
+                         int64_t m, int64_t h_batch, int64_t r_steps, int first_is_initial,
+                         void* workspace, size_t workspace_bytes, void* stream, const KalmanPeerArgs* peers,
+                         void* out_ell) {
   int st = check_args(mu0, chol_p0, a, b, chol_q, h, obs, chol_r, B, T, D, m, h_batch, r_steps,
                       first_is_initial);
   if (st != MF_OK) return st;
@@ -203,12 +297,15 @@ int mf_kalman_segment_summary(int dtype, const void* mu0, const void* chol_p0, c
                                      h_batch, r_steps, first_is_initial);
     // one pass: per-warp joins of the segment elements, then an ordered reduction
     if (sp.P == 1) {
-      return kalman_sweep_launch(1, r, 1, T, nullptr, nullptr, 1, 0, out_elem, s, 0);
+      int rc = kalman_sweep_launch(1, r, 1, T, nullptr, nullptr, 1, 0, out_elem, s, 0);
+      if (rc != MF_OK || !peers) return rc;
+      return kalman_sweep_reduce(dtype, D, out_elem, out_elem, out_ell, B, 1, s, peers);
     }
     int rc = kalman_sweep_launch(1, r, sp.P, sp.L, nullptr, nullptr, sp.nblk, 0, ws + w.elems, s, 1);
     if (rc != MF_OK) return rc;
-    return kalman_sweep_reduce(dtype, D, ws + w.elems, out_elem, nullptr, B, sp.P / 32, s);
+    return kalman_sweep_reduce(dtype, D, ws + w.elems, out_elem, out_ell, B, sp.P / 32, s, peers);
   }
+  if (peers) return MF_ERR_UNSUPPORTED;  // the fused exchange lives in the sweep path (m = 1, D <= 4)
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
@@ -226,6 +323,10 @@ int mf_kalman_segment_summary(int dtype, const void* mu0, const void* chol_p0, c
     return check_launch();
   });
 }
+
+}  // namespace
+
+extern "C" {
 
 int mf_kalman_fold_elements(int dtype, const void* elems, void* out, int64_t n, int64_t B,
                             int64_t D, void* stream) {

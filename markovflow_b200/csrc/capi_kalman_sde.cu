@@ -104,11 +104,41 @@ size_t mf_kalman_matern_workspace_bytes(int dtype, int64_t B, int64_t T, int64_t
   return align_up(es * (size_t)B * slots * N) + 256;
 }
 
+static int matern_impl(int dtype, const void* lengthscale, const void* variance, double jitter,
+                       const void* time_deltas, const void* obs, const void* chol_r, void* out, void* out_elem,
+                       int64_t B, int64_t T, int64_t D, int first_is_initial, void* workspace,
+                       size_t workspace_bytes, void* stream, const KalmanPeerArgs* peers);
+
 int mf_kalman_matern_log_likelihood(int dtype, const void* lengthscale, const void* variance,
                                     double jitter, const void* time_deltas, const void* obs,
                                     const void* chol_r, void* out, void* out_elem, int64_t B,
                                     int64_t T, int64_t D, int first_is_initial, void* workspace,
                                     size_t workspace_bytes, void* stream) {
+  return matern_impl(dtype, lengthscale, variance, jitter, time_deltas, obs, chol_r, out, out_elem, B, T, D,
+                     first_is_initial, workspace, workspace_bytes, stream, nullptr);
+}
+
+int mf_kalman_matern_time_sharded_log_likelihood(int dtype, const void* lengthscale, const void* variance,
+                                                 double jitter, const void* time_deltas, const void* obs,
+                                                 const void* chol_r, void* out, void* out_elem, int64_t B,
+                                                 int64_t T, int64_t D, int first_is_initial,
+                                                 void* const* peer_regions, int rank, int world, uint64_t epoch,
+                                                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (!out || !out_elem || !peer_regions || world < 1 || world > 8 || rank < 0 || rank >= world || epoch == 0)
+    return MF_ERR_BAD_ARG;
+  KalmanPeerArgs pa;
+  pa.rank = rank; pa.world = world; pa.epoch = epoch;
+  for (int r = 0; r < 8; ++r) pa.region[r] = r < world ? peer_regions[r] : nullptr;
+  for (int r = 0; r < world; ++r)
+    if (!pa.region[r]) return MF_ERR_BAD_ARG;
+  return matern_impl(dtype, lengthscale, variance, jitter, time_deltas, obs, chol_r, out, out_elem, B, T, D,
+                     first_is_initial, workspace, workspace_bytes, stream, &pa);
+}
+
+static int matern_impl(int dtype, const void* lengthscale, const void* variance, double jitter,
+                       const void* time_deltas, const void* obs, const void* chol_r, void* out, void* out_elem,
+                       int64_t B, int64_t T, int64_t D, int first_is_initial, void* workspace,
+                       size_t workspace_bytes, void* stream, const KalmanPeerArgs* peers) {
   if (B < 0 || T < 1 || D < 1) return MF_ERR_BAD_ARG;
   if (D > 3) return MF_ERR_UNSUPPORTED;
   if (B == 0) return MF_OK;
@@ -116,6 +146,7 @@ int mf_kalman_matern_log_likelihood(int dtype, const void* lengthscale, const vo
   if ((T - (first_is_initial ? 1 : 0)) > 0 && !time_deltas) return MF_ERR_BAD_ARG;
   if (!out && !out_elem) return MF_ERR_BAD_ARG;
   if (!first_is_initial && !out_elem) return MF_ERR_BAD_ARG;  // a later time segment has no ell of its own
+  if (peers) first_is_initial = first_is_initial ? 1 : 0;
   cudaStream_t s = (cudaStream_t)stream;
   SdePlan pl = make_sde_plan(B, T);
   const size_t need = mf_kalman_matern_workspace_bytes(dtype, B, T, D);
@@ -139,6 +170,7 @@ int mf_kalman_matern_log_likelihood(int dtype, const void* lengthscale, const vo
       }
       p.out = (Tp*)out_elem;
       int rc = launch_core<Tp, kD, true>(p, B, s);
+      if (rc == MF_OK && peers) return kalman_sweep_reduce(dtype, kD, out_elem, out_elem, out, B, 1, s, peers);
       if (rc != MF_OK || !out) return rc;
       // ell is the last of the N values of an element
       constexpr int N = ScanElem<Tp, kD>::N;
@@ -154,7 +186,7 @@ int mf_kalman_matern_log_likelihood(int dtype, const void* lengthscale, const vo
     p.out = (Tp*)workspace;
     int rc = launch_core<Tp, kD, true>(p, B * pl.P, s);
     if (rc != MF_OK) return rc;
-    return kalman_sweep_reduce(dtype, kD, workspace, out_elem, out, B, pl.P / 32, s);
+    return kalman_sweep_reduce(dtype, kD, workspace, out_elem, out, B, pl.P / 32, s, peers);
   });
 }
 

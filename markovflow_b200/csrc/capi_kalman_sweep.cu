@@ -162,13 +162,20 @@ int kalman_sweep_top_scan(int dtype, int64_t D, const void* block_agg, const voi
 }
 
 int kalman_sweep_reduce(int dtype, int64_t D, const void* elems, void* total_out, void* ell_out,
-                        int64_t B, int64_t P, cudaStream_t s) {
+                        int64_t B, int64_t P, cudaStream_t s, const KalmanPeerArgs* peers) {
   return dispatch_sweep(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
     constexpr int NT = kD <= 2 ? 512 : 256;
+    PeerExchange px;
+    px.world = 1; px.rank = 0; px.epoch = 0; px.B = B;
+    for (int r = 0; r < 8; ++r) px.region[r] = nullptr;
+    if (peers && peers->world > 1) {
+      px.world = peers->world; px.rank = peers->rank; px.epoch = peers->epoch;
+      for (int r = 0; r < peers->world; ++r) px.region[r] = peers->region[r];
+    }
     kalman_reduce_kernel<Tp, kD, NT><<<(unsigned)B, NT, 0, s>>>((const Tp*)elems, (Tp*)total_out,
-                                                               (Tp*)ell_out, P);
+                                                               (Tp*)ell_out, P, px);
     return check_launch();
   });
 }

@@ -352,10 +352,64 @@ kalman_top_scan_kernel(const T* __restrict__ block_agg, const T* __restrict__ pr
 // join = the marginal log-likelihood when the first element starts at the prior.  total_out [B,N]
 // optional.  Thread t folds the run [t*r, (t+1)*r) sequentially, then warp-shuffle scans join the
 // NT partial results in time order.
+// Time-sharded series over several GPUs: the exchange of the per-rank elements happens INSIDE
+// the reduction's tail.  Every rank owns a peer-mapped region (cudaIpc / NVLink P2P, mf_peer_*) laid out as
+//   elements [2][world][B][N]  |  flags (uint64) [2][world][B]          (2 = call parity: double buffer)
+// The thread that holds a chain's local total stores it into slot `rank` of EVERY rank's region, fences, raises
+// the flags, then waits for the flags of all ranks in its own region and joins the `world` elements in rank
+// (= time) order: no NCCL call, no extra launch, no host glue.  world == 1: plain reduction.
+struct PeerExchange {
+  void* region[8];        // region[r]: rank r's region as mapped into this process
+  unsigned long long epoch;  // call counter, > 0, the same on every rank
+  int rank, world;
+  int64_t B;
+};
+
+template <typename T, int D>
+__device__ __forceinline__ void peer_exchange_join(ScanElem<T, D>& acc, const PeerExchange& px, int64_t c) {
+  constexpr int N = ScanElem<T, D>::N;
+  const int par = (int)(px.epoch & 1ull);
+  const size_t flag_off = sizeof(T) * (size_t)2 * px.world * px.B * N;
+  T tmp[N];
+  elem_store<T, D>(tmp, acc);
+  const size_t slot = ((size_t)(par * px.world + px.rank) * px.B + c);
+  for (int r = 0; r < px.world; ++r) {
+    volatile T* dst = reinterpret_cast<volatile T*>(px.region[r]) + slot * N;
+#pragma unroll
+    for (int i = 0; i < N; ++i) dst[i] = tmp[i];
+  }
+  __threadfence_system();
+  for (int r = 0; r < px.world; ++r) {
+    volatile unsigned long long* f =
+        reinterpret_cast<volatile unsigned long long*>(reinterpret_cast<char*>(px.region[r]) + flag_off) + slot;
+    *f = px.epoch;
+  }
+  char* own = reinterpret_cast<char*>(px.region[px.rank]);
+  ScanElem<T, D> tot, nxt, cmb;
+  for (int r = 0; r < px.world; ++r) {
+    const size_t s = ((size_t)(par * px.world + r) * px.B + c);
+    volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(own + flag_off) + s;
+    while (*f < px.epoch) {
+    }
+    __threadfence_system();
+    const volatile T* src = reinterpret_cast<const volatile T*>(own) + s * N;
+#pragma unroll
+    for (int i = 0; i < N; ++i) tmp[i] = src[i];
+    elem_load<T, D>(nxt, tmp);
+    if (r == 0) {
+      tot = nxt;
+    } else {
+      elem_combine<T, D>(cmb, tot, nxt);
+      tot = cmb;
+    }
+  }
+  acc = tot;
+}
+
 template <typename T, int D, int NT>
 __global__ void __launch_bounds__(NT)
 kalman_reduce_kernel(const T* __restrict__ elems, T* __restrict__ total_out,
-                     T* __restrict__ ell_out, int64_t P) {
+                     T* __restrict__ ell_out, int64_t P, const PeerExchange px) {
   constexpr int N = ScanElem<T, D>::N, NW = NT / 32;
   __shared__ T smem[NW * N];
   const int64_t c = blockIdx.x;
@@ -364,6 +418,7 @@ kalman_reduce_kernel(const T* __restrict__ elems, T* __restrict__ total_out,
     if (threadIdx.x == 0) {
       ScanElem<T, D> e;
       elem_load<T, D>(e, elems + c * N);
+      if (px.world > 1) peer_exchange_join<T, D>(e, px, c);
       if (total_out) elem_store<T, D>(total_out + c * N, e);
       if (ell_out) ell_out[c] = e.ell;
     }
@@ -405,6 +460,7 @@ kalman_reduce_kernel(const T* __restrict__ elems, T* __restrict__ total_out,
       }
     }
     if (lane == NW - 1) {
+      if (px.world > 1) peer_exchange_join<T, D>(acc, px, c);
       if (total_out) elem_store<T, D>(total_out + c * N, acc);
       if (ell_out) ell_out[c] = acc.ell;
     }

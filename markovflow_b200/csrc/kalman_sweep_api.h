@@ -39,8 +39,16 @@ int kalman_sweep_top_scan(int dtype, int64_t D, const void* block_agg, const voi
                           void* block_prefix, void* total_out, void* ell_out, int64_t B,
                           int64_t nblk, cudaStream_t s);
 
-// ordered reduction of elems [B,P,N]: total_out [B,N] or NULL, ell_out [B] or NULL
+// peer-mapped exchange regions of a time-sharded evaluation (kalman_sweep.cuh: PeerExchange)
+struct KalmanPeerArgs {
+  void* region[8];
+  unsigned long long epoch;
+  int rank, world;
+};
+
+// ordered reduction of elems [B,P,N]: total_out [B,N] or NULL, ell_out [B] or NULL; with `peers` the chain
+// totals are exchanged with the other ranks and joined in rank order in the same launch
 int kalman_sweep_reduce(int dtype, int64_t D, const void* elems, void* total_out, void* ell_out,
-                        int64_t B, int64_t P, cudaStream_t s);
+                        int64_t B, int64_t P, cudaStream_t s, const KalmanPeerArgs* peers = nullptr);
 
 }  // namespace mf

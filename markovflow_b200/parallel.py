@@ -147,12 +147,123 @@ class CudaKalmanEngine:
         return out
 
 
-def time_sharded_log_likelihood(seg: TimeSegment, group=None, engine=None) -> torch.Tensor:
+class PeerRing:
+    """The peer-mapped exchange regions of a time-sharded evaluation (``mf_peer_*``, ``include/markovflow_b200.h``).
+
+    Every rank allocates one region (plain ``cudaMalloc``), exports its CUDA IPC handle, and maps the regions of
+    all other ranks of the node (NVLink / NVSwitch peer-to-peer).  The handles travel once through
+    ``all_gather_object``; afterwards a time-sharded log-likelihood is ONE library call per rank
+    (:meth:`kalman` / :meth:`matern`): the kernel that reduces the rank's segment writes its element into every
+    rank's region, raises flags, waits for the others' and joins the elements in rank order -- no collective."""
+
+    def __init__(self, dtype: torch.dtype, batch: int, state_dim: int, group=None, regions=None, rank=None,
+                 world=None) -> None:
+        import torch.distributed as dist
+
+        self.lib = _lib.lib()
+        self.dtype, self.batch, self.state_dim = dtype, int(batch), int(state_dim)
+        self.lib.mf_kalman_peer_region_bytes.restype = _lib.ctypes.c_size_t
+        self._own = self._opened = None
+        if regions is not None:  # regions supplied by the caller (tests: virtual ranks on one device)
+            self.rank, self.world = int(rank), int(world)
+            self._ptrs = [int(p) for p in regions]
+        else:
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+            nbytes = self.region_bytes(dtype, batch, state_dim, self.world)
+            own = _lib.ctypes.c_void_p()
+            handle = (_lib.ctypes.c_ubyte * 64)()
+            check(self.lib.mf_peer_alloc(_lib.ctypes.c_size_t(nbytes), _lib.ctypes.byref(own), handle), "mf_peer_alloc")
+            self._own = own
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            self._ptrs, self._opened = [], []
+            for r, hb in enumerate(handles):
+                if r == self.rank:
+                    self._ptrs.append(int(own.value))
+                    continue
+                p = _lib.ctypes.c_void_p()
+                check(self.lib.mf_peer_open((_lib.ctypes.c_ubyte * 64).from_buffer_copy(hb), _lib.ctypes.byref(p)),
+                      "mf_peer_open")
+                self._opened.append(p)
+                self._ptrs.append(int(p.value))
+            dist.barrier(group=group)
+        self._arr = (_lib.ctypes.c_void_p * self.world)(*self._ptrs)
+        self.epoch = 0
+
+    @staticmethod
+    def region_bytes(dtype, batch: int, state_dim: int, world: int) -> int:
+        lib = _lib.lib()
+        lib.mf_kalman_peer_region_bytes.restype = _lib.ctypes.c_size_t
+        return int(lib.mf_kalman_peer_region_bytes(dtype_code(dtype), i64(batch), i64(state_dim), int(world)))
+
+    def close(self) -> None:
+        for p in self._opened or []:
+            self.lib.mf_peer_close(p)
+        if self._own is not None:
+            self.lib.mf_peer_free(self._own)
+        self._opened, self._own = None, None
+
+    def _next(self) -> int:
+        self.epoch += 1
+        return self.epoch
+
+    def kalman(self, seg: TimeSegment, engine: Optional["CudaKalmanEngine"] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``(log-likelihood [B] of the whole series, its joined scan element [B,N])`` -- collective: every rank
+        calls it with its own segment (rank order == time order)."""
+        engine = engine or CudaKalmanEngine()
+        bsz, tl, m, d, hb, rs = engine._dims(seg)
+        ws, n = engine._workspace(seg)
+        out = torch.empty(bsz, dtype=seg.obs.dtype, device=seg.obs.device)
+        elem = torch.empty(bsz, engine.elem_size(d), dtype=seg.obs.dtype, device=seg.obs.device)
+        check(
+            self.lib.mf_kalman_time_sharded_log_likelihood(
+                dtype_code(seg.obs.dtype), ptr(seg.mu0), ptr(seg.chol_p0), ptr(seg.a), ptr(seg.b), ptr(seg.chol_q),
+                ptr(seg.h), ptr(seg.obs), ptr(seg.chol_r), ptr(out), ptr(elem), i64(bsz), i64(tl), i64(d), i64(m),
+                i64(hb), i64(rs), int(seg.first), self._arr, int(self.rank), int(self.world),
+                _lib.ctypes.c_uint64(self._next()), ptr(ws), _lib.ctypes.c_size_t(n), current_stream()),
+            "mf_kalman_time_sharded_log_likelihood",
+        )
+        return out, elem
+
+    def matern(self, state_dim: int, lengthscale, variance, seg_deltas, seg_obs, chol_obs_covariance, first: bool,
+               jitter: float = 0.0) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The same for a Matern prior with the state-space model built in the kernel from the time deltas."""
+        y = seg_obs.contiguous()
+        bsz, t = y.shape
+        dt = seg_deltas.contiguous()
+        dtype, dev = y.dtype, y.device
+        ls = torch.as_tensor(lengthscale, dtype=dtype, device=dev).expand(bsz).contiguous()
+        var = torch.as_tensor(variance, dtype=dtype, device=dev).expand(bsz).contiguous()
+        lr = torch.as_tensor(chol_obs_covariance, dtype=dtype, device=dev).reshape(-1)[:1].contiguous()
+        self.lib.mf_kalman_matern_workspace_bytes.restype = _lib.ctypes.c_size_t
+        nbytes = int(self.lib.mf_kalman_matern_workspace_bytes(dtype_code(dtype), i64(bsz), i64(t), i64(state_dim)))
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        out = torch.empty(bsz, dtype=dtype, device=dev)
+        elem = torch.empty(bsz, 3 * state_dim * state_dim + 2 * state_dim + 1, dtype=dtype, device=dev)
+        check(
+            self.lib.mf_kalman_matern_time_sharded_log_likelihood(
+                dtype_code(dtype), ptr(ls), ptr(var), _lib.ctypes.c_double(float(jitter)), ptr(dt), ptr(y), ptr(lr),
+                ptr(out), ptr(elem), i64(bsz), i64(t), i64(state_dim), int(bool(first)), self._arr, int(self.rank),
+                int(self.world), _lib.ctypes.c_uint64(self._next()), ptr(ws), _lib.ctypes.c_size_t(nbytes),
+                current_stream()),
+            "mf_kalman_matern_time_sharded_log_likelihood",
+        )
+        return out, elem
+
+
+def time_sharded_log_likelihood(seg: TimeSegment, group=None, engine=None, ring: Optional[PeerRing] = None
+                                ) -> torch.Tensor:
     """Per-chain log-likelihood ``[B]`` of the whole series, computed collectively: every rank
-    passes its own :class:`TimeSegment` (rank order == time order) and receives the same value."""
+    passes its own :class:`TimeSegment` (rank order == time order) and receives the same value.
+    With a :class:`PeerRing` the exchange happens inside the reduction kernel over peer memory (one library
+    call, no collective); without one: NCCL all-gather of the elements + a fold launch."""
     import torch.distributed as dist
 
     engine = engine or CudaKalmanEngine()
+    if ring is not None:
+        if seg.first != (ring.rank == 0):
+            raise ValueError("rank 0 (and only rank 0) must hold the segment that starts at the prior")
+        return ring.kalman(seg, engine)[0]
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     if seg.first != (rank == 0):

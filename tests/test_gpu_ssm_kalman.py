@@ -596,3 +596,54 @@ def test_mid_size_batch_log_likelihood_is_cut_in_time():
     sub = O.SSM(ssm.mu0[pick], ssm.chol_p0[pick], ssm.a_s[pick], ssm.b_s[pick], ssm.chol_q_s[pick])
     want = O.kalman_log_likelihood(sub, h[pick], y[pick], O._r_inv_from_chol(lr), per_chain=True)
     assert max_rel_err(cut[pick], want) < 1e-10
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_time_sharded_exchange_inside_the_kernel_virtual_ranks(world):
+    """mf_kalman_time_sharded_log_likelihood / mf_kalman_matern_time_sharded_log_likelihood: the per-rank
+    elements are exchanged through peer-mapped regions and joined INSIDE the reduction kernel.  Here the `world`
+    ranks are virtual: one device, one stream per rank, regions = plain device buffers (on several GPUs they are
+    cudaIpc mappings of each other's allocations); every rank must return the log-likelihood of the whole series,
+    call after call (the regions are double-buffered on the call parity)."""
+    import markovflow_b200 as mf
+    from markovflow_b200.parallel import (PeerRing, matern_time_segment, time_sharded_log_likelihood,
+                                          time_sharded_segments)
+
+    rng = np.random.default_rng(world)
+    t, bsz = 40_000, 2
+    k = O.Matern32(1.0, 1.0)
+    tps = np.cumsum(rng.uniform(0.05, 0.15, size=(bsz, t)), axis=-1)
+    ssm = k.state_space_model(tps)
+    h = k.emission_matrix(tps[0])
+    y = np.sin(tps)[..., None] + 0.1 * rng.standard_normal((bsz, t, 1))
+    lr = np.array([[0.1]])
+    gssm = to_gpu_ssm(ssm)
+    whole = mf.kalman_log_likelihood(gssm, tt(h), tt(y), tt(lr))
+    segs = time_sharded_segments(gssm, tt(h), tt(y), tt(lr), world)
+    nbytes = PeerRing.region_bytes(torch.float64, bsz, 2, world)
+    regions = [torch.zeros(nbytes, dtype=torch.uint8, device=dev()) for _ in range(world)]
+    rings = [PeerRing(torch.float64, bsz, 2, regions=[r.data_ptr() for r in regions], rank=r, world=world)
+             for r in range(world)]
+    streams = [torch.cuda.Stream(device=dev()) for _ in range(world)]
+    torch.cuda.synchronize()
+    for call in range(3):
+        outs = []
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                outs.append(time_sharded_log_likelihood(segs[r], ring=rings[r]))
+        torch.cuda.synchronize()
+        for o in outs:
+            assert max_rel_err(npy(o), npy(whole)) < 1e-10
+    # Matern prior built in the kernel from the time deltas, same series
+    dts = tt(np.diff(tps, axis=-1))
+    y2 = tt(y[..., 0])
+    one = torch.ones(bsz, dtype=torch.float64, device=dev())
+    for call in range(2):
+        outs = []
+        for r in range(world):
+            first, seg_dt, seg_y = matern_time_segment(dts, y2, r, world)
+            with torch.cuda.stream(streams[r]):
+                outs.append(rings[r].matern(2, one, one, seg_dt, seg_y, tt(lr), first)[0])
+        torch.cuda.synchronize()
+        for o in outs:
+            assert max_rel_err(npy(o), npy(whole)) < 1e-10
