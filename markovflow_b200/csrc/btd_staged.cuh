@@ -40,7 +40,7 @@ template <typename T, int D, bool RHS, int C, int K, int NSI, int NSO>
 __global__ void __launch_bounds__(256, 1)
 btd_chol_staged_kernel(const T* __restrict__ diag, const T* __restrict__ sub,
                        const T* __restrict__ rhs, T* od, T* os, T* ox, T* __restrict__ logdet,
-                       int32_t* __restrict__ info, int64_t B, int64_t Tn) {
+                       int32_t* __restrict__ info, int64_t B, int64_t Tn, const int elem_wait) {
   using Cfg = CholStagedCfg<T, D, RHS, C, K, NSI, NSO>;
   constexpr int DD = Cfg::DD, ETOT = Cfg::ETOT, CP = Cfg::CP, NCW = Cfg::NCW;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -83,7 +83,7 @@ btd_chol_staged_kernel(const T* __restrict__ diag, const T* __restrict__ sub,
       tile_load<T, DD, 0, ETOT, K, C, CP>(st, diag, off_diag, Tn, k0, w, NCW, lane);
       tile_load<T, DD, DD, ETOT, K, C, CP>(st, sub, off_sub, Tn - 1, k0, w, NCW, lane);
       if (RHS) tile_load<T, D, 2 * DD, ETOT, K, C, CP>(st, rhs, off_vec, Tn, k0, w, NCW, lane);
-      cp_async_arrive_noinc(full_in + (tile % NSI));
+      cp_async_arrive(full_in + (tile % NSI), elem_wait);
     };
     for (int64_t t = 0; t < NSI && t < ntiles; ++t) issue_loads(t);
     for (int64_t t = 0; t < ntiles; ++t) {

@@ -103,7 +103,7 @@ template <typename T, int D, bool RHS, int C, int K, int NSI, int NSO>
 __global__ void __launch_bounds__(CholTmaCfg<T, D, RHS, C, K, NSI, NSO>::THREADS, 1)
 btd_chol_tma_kernel(const T* __restrict__ diag, const T* __restrict__ sub,
                     const T* __restrict__ rhs, T* od, T* os, T* ox, T* __restrict__ logdet,
-                    int32_t* __restrict__ info, int64_t B, int64_t Tn) {
+                    int32_t* __restrict__ info, int64_t B, int64_t Tn, const int elem_wait) {
   using Cfg = CholTmaCfg<T, D, RHS, C, K, NSI, NSO>;
   constexpr int DD = Cfg::DD, ES = Cfg::ES;
   static_assert(Cfg::ALIGN_OK, "K * E * sizeof(T) must be a multiple of 16 for every stream");
@@ -170,7 +170,7 @@ btd_chol_tma_kernel(const T* __restrict__ diag, const T* __restrict__ sub,
                                      : seg_interior_bytes<ES, DD, K>(sg, k0, h, b);
         mbar_arrive_expect_tx(bar, tx);
         if (stream == 2) seg_load<ES, D, K>(st, sg, k0, bar); else seg_load<ES, DD, K>(st, sg, k0, bar);
-        cp_async_arrive_noinc(bar);
+        cp_async_arrive(bar, elem_wait);
       };
       for (int64_t t = 0; t < NSI && t < ntiles; ++t) issue_load(t);
       for (int64_t t = 0; t + NSI < ntiles; ++t) {

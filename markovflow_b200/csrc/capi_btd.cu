@@ -35,10 +35,10 @@ namespace {
 // Tuning knobs (mf_set_tuning): 0 = variant of the Cholesky sweep (0 auto = TMA, 1 direct,
 // 2 cp.async-staged),
 // 1 = steps per shared-memory stage for the staged sweep (0 auto).
-int g_tuning[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+int g_tuning[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 }  // namespace
 namespace mf {
-int tuning(int knob) { return (knob >= 0 && knob < 12) ? g_tuning[knob] : 0; }
+int tuning(int knob) { return (knob >= 0 && knob < 16) ? g_tuning[knob] : 0; }
 }  // namespace mf
 namespace {
 
@@ -63,7 +63,7 @@ int launch_chol_staged(const void* diag, const void* sub, const void* rhs, void*
   static SmemOnce once;  // per instantiation, per device
   if (ensure_smem(once, kern, Cfg::SMEM_BYTES) != cudaSuccess) return check_launch();
   kern<<<grid_for(B, C), Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(
-      (const T*)diag, (const T*)sub, (const T*)rhs, (T*)od, (T*)os, (T*)ox, (T*)logdet, info, B, Tn);
+      (const T*)diag, (const T*)sub, (const T*)rhs, (T*)od, (T*)os, (T*)ox, (T*)logdet, info, B, Tn, tuning(12));
   return check_launch();
 }
 
@@ -102,7 +102,7 @@ int launch_chol_tma(const void* diag, const void* sub, const void* rhs, void* od
   static SmemOnce once;  // per instantiation, per device
   if (ensure_smem(once, kern, Cfg::SMEM_BYTES) != cudaSuccess) return check_launch();
   kern<<<grid_for(B, C), Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(
-      (const T*)diag, (const T*)sub, (const T*)rhs, (T*)od, (T*)os, (T*)ox, (T*)logdet, info, B, Tn);
+      (const T*)diag, (const T*)sub, (const T*)rhs, (T*)od, (T*)os, (T*)ox, (T*)logdet, info, B, Tn, tuning(12));
   return check_launch();
 }
 
@@ -122,7 +122,7 @@ int launch_chol_fast(const void* diag, const void* sub, const void* rhs, void* o
 extern "C" {
 
 int mf_set_tuning(int knob, int value) {
-  if (knob < 0 || knob >= 12) return MF_ERR_BAD_ARG;
+  if (knob < 0 || knob >= 16) return MF_ERR_BAD_ARG;
   g_tuning[knob] = value;
   return MF_OK;
 }

@@ -51,6 +51,20 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
                : "memory");
 }
 
+// Completion of this thread's element cp.async on `bar`.  Default: cp.async.mbarrier.arrive.noinc -- the arrival
+// is triggered by the hardware when the copies land (the documented cp.async + mbarrier pattern; the thread does
+// not wait).  wait_all != 0 (tuning knob 12, for compute-sanitizer racecheck, which does not model that
+// completion path and reports the consumers' reads as hazards): the thread waits for its copies itself and then
+// arrives with an ordinary release arrive.  Both make the copies visible to the waiting threads.
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar, int wait_all) {
+  if (wait_all) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    mbar_arrive(bar);
+  } else {
+    cp_async_arrive_noinc(bar);
+  }
+}
+
 template <int BYTES>
 __device__ __forceinline__ void cp_async_elem(void* smem, const void* gmem) {
   static_assert(BYTES == 4 || BYTES == 8, "element copies are 4 or 8 bytes");

@@ -135,7 +135,7 @@ __device__ __forceinline__ uint32_t sweep_ranges(const SweepSeg& sg, int E, int6
 
 template <class Core, int C, int K, int NSI, int NSO>
 __global__ void __launch_bounds__(SweepCfg<Core, C, K, NSI, NSO>::THREADS)
-chain_sweep_kernel(const typename Core::Params prm, const int cpb) {
+chain_sweep_kernel(const typename Core::Params prm, const int cpb, const int elem_wait) {
   using Cfg = SweepCfg<Core, C, K, NSI, NSO>;
   using T = typename Core::T;
   constexpr int ES = Cfg::ES, NIN = Cfg::NIN, NOUT = Cfg::NOUT, NSOE = Cfg::NSO_EFF;
@@ -201,7 +201,7 @@ chain_sweep_kernel(const typename Core::Params prm, const int cpb) {
           for (int o = lo; o < lo + head; o += ES) cp_async_elem<ES>(sd + o, g0 + o);
           for (int o = lo + head + (int)tx; o < hi; o += ES) cp_async_elem<ES>(sd + o, g0 + o);
         }
-        cp_async_arrive_noinc(bar);
+        cp_async_arrive(bar, elem_wait);
       };
       for (int64_t t = 0; t < NSI && t < ntiles; ++t) issue_load(t);
       for (int64_t t = 0; t + NSI < ntiles; ++t) {
@@ -319,7 +319,7 @@ inline cudaError_t launch_chain_sweep(const typename Core::Params& prm, int64_t 
     if (cpb < 1) cpb = 1;
   }
   const unsigned grid = (unsigned)((nchains + cpb - 1) / cpb);
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(prm, (int)cpb);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(prm, (int)cpb, tuning(12));
   return cudaGetLastError();
 }
 

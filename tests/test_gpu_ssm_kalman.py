@@ -638,12 +638,15 @@ def test_time_sharded_exchange_inside_the_kernel_virtual_ranks(world):
     dts = tt(np.diff(tps, axis=-1))
     y2 = tt(y[..., 0])
     one = torch.ones(bsz, dtype=torch.float64, device=dev())
+    msegs = [matern_time_segment(dts, y2, r, world) for r in range(world)]
+    glr = tt(lr)
+    torch.cuda.synchronize()  # the slices were cut on the default stream: the ranks' streams must see them
     for call in range(2):
         outs = []
         for r in range(world):
-            first, seg_dt, seg_y = matern_time_segment(dts, y2, r, world)
+            first, seg_dt, seg_y = msegs[r]
             with torch.cuda.stream(streams[r]):
-                outs.append(rings[r].matern(2, one, one, seg_dt, seg_y, tt(lr), first)[0])
+                outs.append(rings[r].matern(2, one, one, seg_dt, seg_y, glr, first)[0])
         torch.cuda.synchronize()
         for o in outs:
             assert max_rel_err(npy(o), npy(whole)) < 1e-10
