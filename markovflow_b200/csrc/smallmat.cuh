@@ -10,11 +10,31 @@ namespace mf {
 
 template <typename T> struct Num;
 template <> struct Num<double> {
-  static __device__ __forceinline__ double rsqrt(double x) { return ::rsqrt(x); }
+  // Branch-free 1/sqrt(x) for positive normal x: MUFU.RSQ64H seed (rel. error <= 2^-20 with the low word it
+  // ignores) + one third-order step y(1 + e/2 + 3e^2/8), e = 1 - x y^2, error O(e^3) < 2^-60 before rounding.
+  // ::rsqrt() wraps the same seed in a slow-path BRANCH (denormals, 0, inf) that ends the basic block, so
+  // independent rsqrt's of one step could not overlap (ncu: 3 x ~70 cycles serialised in the D=3 Cholesky
+  // step).  x <= 0 or NaN gives NaN/inf here as well; callers test the pivot's sign themselves.
+  static __device__ __forceinline__ double rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = x * y;
+    const double e = ::fma(-h, y, 1.0);
+    const double t = ::fma(0.375, e, 0.5);
+    // x = 0, inf (seed inf, 0: h is NaN) and NaN seeds fall through as the seed itself -- a select, not a branch
+    return ::fabs(e) < 0.5 ? ::fma(y * e, t, y) : y;
+  }
   static __device__ __forceinline__ double log(double x) { return ::log(x); }
   static __device__ __forceinline__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
   static __device__ __forceinline__ double abs(double x) { return ::fabs(x); }
-  static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+  // Branch-free 1/x for normal x (no division subroutine): MUFU.RCP64H seed + y(1 + e + e^2), e = 1 - x y.
+  static __device__ __forceinline__ double rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = ::fma(-x, y, 1.0);
+    const double t = ::fma(e, e, e);
+    return ::fabs(e) < 0.5 ? ::fma(y, t, y) : y;  // 1/inf = 0, 1/0 = inf (an "infinite" noise variance = missing observation)
+  }
 };
 template <> struct Num<float> {
   static __device__ __forceinline__ float rsqrt(float x) { return ::rsqrtf(x); }
