@@ -55,8 +55,17 @@ const char* mf_last_cuda_error(void);
  * 1..4 TMA chain-sweep geometries, 5/6 register-capped variants); knob 9: its virtual chains per SM, in warps (0 auto); knob 10: segments per chain from which
  * the parallel-in-time seed folds run as warp scans (0 auto = 8); knob 11: 1 = the default
  * 8-step tiles everywhere (no 16-step tiles for output-less float32 sweeps, no 4-step tiles for the
- * float64 D = 2 naturals -> SSM sweep). */
+ * float64 D = 2 naturals -> SSM sweep); knob 7 (current meaning): large-block Cholesky for D <= 17 -- 0 auto
+ * (half-warp-per-chain kernels, parallel in time for few chains), 1 never cut chains into segments, n >= 3
+ * that many segments, 2 the round-1 warp-per-chain kernel; knob 12: 1 = ring producers wait for their element
+ * cp.async themselves and arrive with a plain mbarrier arrive (the completion path compute-sanitizer's
+ * racecheck models; default: cp.async.mbarrier.arrive.noinc); knob 13: 1 = no tensor-map (cp.async.bulk.tensor)
+ * sweeps, always one 1-D bulk copy per chain; knob 14: tensor-map tile geometry (0 auto: 4-step tiles, 1: 8-step,
+ * 2: 4-step with one output stage, 3: 2-step). */
 int mf_set_tuning(int knob, int value);
+/* Number of sweeps launched on the tensor-map engine (csrc/sweep_tm.cuh) since the library was loaded; the tests
+ * use it to check which engine served a call. */
+int64_t mf_tm_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Block-tridiagonal operators (markovflow/block_tri_diag.py)

@@ -51,6 +51,9 @@ static void plan_segments(int64_t B, int64_t T, int64_t* P, int64_t* L) {
   if (p < 1) p = 1;
   if (tuning(3) > 0 && tuning(3) < T) p = (T + tuning(3) - 1) / tuning(3);
   int64_t l = (T + p - 1) / p;
+  // segments of a multiple of 4 steps start 16-byte aligned in every stream of either dtype (what the tensor-map
+  // engine needs, sweep_tm.cuh); an explicit segment length (knob 3) is taken as given
+  if (!(tuning(3) > 0 && tuning(3) < T) && l >= 16) l = (l + 3) / 4 * 4;
   if (l < 2) l = 2;
   *L = l;
   *P = (T + l - 1) / l;

@@ -9,10 +9,12 @@
 //   SsmKlCore        forward : KL(q || p), chain-rule form                    (mf_ssm_kl_divergence)
 //   NatToSsmCore     backward: naturals -> SSM parameters, U D U^T sweep      (mf_nat_to_ssm)
 #pragma once
+#include <type_traits>
+
 #include "dispatch.cuh"
 #include "nat_kernels.cuh"
 #include "smallrng.cuh"
-#include "sweep.cuh"
+#include "sweep_tm.cuh"
 
 namespace mf {
 
@@ -137,6 +139,18 @@ struct SsmMomentsCore {
     if (i == 2) return vgeom_incoming<T>(p.o_sub, c, p.Tn, DD, k0, n);
     return vgeom_states<T>(i == 0 ? p.o_vec : p.o_diag, c, p.Tn, eout(i), k0, n);
   }
+  // host-side description of the same streams for the tensor-map engine (sweep_tm.cuh)
+  static void tm_describe(const Params& p, TmStream* in, TmStream* out) {
+    in[0] = TmStream{p.a, p.Tn - 1, -1};
+    in[1] = TmStream{p.b, p.Tn - 1, -1};
+    in[2] = TmStream{p.chol_q, p.Tn - 1, -1};
+    out[0] = TmStream{p.o_vec, p.Tn, 0};
+    out[1] = TmStream{p.o_diag, p.Tn, 0};
+    out[2] = TmStream{p.o_sub, p.Tn - 1, -1};
+  }
+  static int64_t tm_segments(const Params& p) { return p.P; }
+  static int64_t tm_seg_len(const Params& p) { return p.L; }
+  static int64_t tm_chains(const Params& p) { return p.B; }
   T mu[D], P[DD];
   int64_t k0_, n_;
   __device__ __forceinline__ void init(const Params& p, int64_t v) {
@@ -230,6 +244,14 @@ struct SsmMomSummaryCore {
   static __device__ __forceinline__ StreamGeom out_geom(const Params&, int, int64_t) {
     return StreamGeom{nullptr, 0, 0};
   }
+  static void tm_describe(const Params& p, TmStream* in, TmStream*) {
+    in[0] = TmStream{p.a, p.Tn - 1, -1};
+    in[1] = TmStream{p.b, p.Tn - 1, -1};
+    in[2] = TmStream{p.chol_q, p.Tn - 1, -1};
+  }
+  static int64_t tm_segments(const Params& p) { return p.P; }
+  static int64_t tm_seg_len(const Params& p) { return p.L; }
+  static int64_t tm_chains(const Params& p) { return p.B; }
   T Phi[DD], cv[D], Qt[DD];
   int64_t k0_;
   bool live_;
@@ -947,6 +969,20 @@ struct NatGeomBase {
     if (i == 2) return vgeom_outgoing<T>(p.th_sub, c, p.Tn, DD, k0, n);
     return vgeom_states<T>(i == 0 ? p.th_lin : p.th_diag, c, p.Tn, ein(i), k0, n);
   }
+  // host-side description for the tensor-map engine: inputs here, outputs (NatToSsmCore only) below
+  static void tm_describe(const Params& p, TmStream* in, TmStream* out) {
+    in[0] = TmStream{p.th_lin, p.Tn, 0};
+    in[1] = TmStream{p.th_diag, p.Tn, 0};
+    in[2] = TmStream{p.th_sub, p.Tn - 1, 0};
+    if (out) {
+      out[0] = TmStream{p.out_a, p.Tn - 1, 0};
+      out[1] = TmStream{p.out_off, p.Tn, 0};
+      out[2] = TmStream{p.out_chol, p.Tn, 0};
+    }
+  }
+  static int64_t tm_segments(const Params& p) { return p.P; }
+  static int64_t tm_seg_len(const Params& p) { return p.L; }
+  static int64_t tm_chains(const Params& p) { return p.B; }
 };
 
 // Backward U D U^T sweep of one segment, seeded with the state entering it.
@@ -1077,6 +1113,9 @@ struct NatSummaryCore : NatGeomBase<T_, D> {
     StreamGeom g = NatGeomBase<T_, D>::in_geom(p, i, v);
     if (v % p.P == 0) g.end = 0;  // the first segment feeds nobody: nothing to load
     return g;
+  }
+  static void tm_describe(const Params& p, TmStream* in, TmStream*) {
+    NatGeomBase<T_, D>::tm_describe(p, in, nullptr);
   }
   static __device__ __forceinline__ StreamGeom out_geom(const Params&, int, int64_t) {
     return StreamGeom{nullptr, 0, 0};
@@ -1289,6 +1328,46 @@ nat_seed_kernel(const NatToSsmParams<T> p) {
 template <class Core> struct PrefersShortTiles { static constexpr bool value = false; };
 template <> struct PrefersShortTiles<NatToSsmCore<double, 2>> { static constexpr bool value = true; };
 
+// Cores that describe their streams for the tensor-map engine (sweep_tm.cuh) try it first; it declines
+// (cudaErrorNotSupported) geometries it cannot map and the 1-D engine below takes over.  Records of up to
+// 4 elements (D <= 2) only: those are the sweeps bound by bulk-copy issue.  Knob 13 = 1: off;
+// knob 14: tile geometry (0 default, 1: K=8, 2: K=4 with one output stage, 3: K=2).
+template <class Core, class = void>
+struct HasTm : std::false_type {};
+template <class Core>
+struct HasTm<Core, std::void_t<decltype(&Core::tm_describe)>> : std::true_type {};
+
+template <class Core>
+struct TmAuto {
+  static constexpr int max_e() {
+    int m = 0;
+    for (int i = 0; i < Core::NIN; ++i) m = Core::ein(i) > m ? Core::ein(i) : m;
+    for (int i = 0; i < Core::NOUT; ++i) m = Core::eout(i) > m ? Core::eout(i) : m;
+    return m;
+  }
+  static constexpr bool small = max_e() <= 4;
+  template <int K, int NSI, int NSO>
+  static constexpr bool fits() { return SweepTmCfg<Core, 64, K, NSI, NSO, 4>::FITS; }
+  static constexpr bool ok = small && fits<4, 2, 2>();
+  static cudaError_t launch(const typename Core::Params& prm, cudaStream_t s) {
+    if constexpr (ok) {
+      const int g = tuning(14);
+      if constexpr (fits<8, 2, 2>()) {
+        if (g == 1) return launch_chain_sweep_tm<Core, 64, 8, 2, 2, 4>(prm, s);
+      }
+      if constexpr (fits<4, 2, 1>()) {
+        if (g == 2) return launch_chain_sweep_tm<Core, 64, 4, 2, 1, 4>(prm, s);
+      }
+      if constexpr (fits<2, 2, 2>()) {
+        if (g == 3) return launch_chain_sweep_tm<Core, 64, 2, 2, 2, 4>(prm, s);
+      }
+      return launch_chain_sweep_tm<Core, 64, 4, 2, 2, 4>(prm, s);
+    } else {
+      return cudaErrorNotSupported;
+    }
+  }
+};
+
 // Compile-time choice of a ring geometry that fits (chains per CTA, steps per tile, stages).
 template <class Core>
 struct SweepAuto {
@@ -1303,6 +1382,12 @@ struct SweepAuto {
   // float64 summary passes lose a resident CTA per SM to the longer tiles (config 5: 290 -> 426 us).
   static constexpr bool long_tiles = fits<64, 16, 2, 2>() && Core::NOUT == 0 && sizeof(typename Core::T) == 4;
   static cudaError_t launch(const typename Core::Params& prm, int64_t nchains, cudaStream_t s) {
+    if constexpr (HasTm<Core>::value) {
+      if (tuning(13) != 1) {
+        const cudaError_t e = TmAuto<Core>::launch(prm, s);
+        if (e != cudaErrorNotSupported) return e;
+      }
+    }
     if constexpr (long_tiles) {
       if (nchains > (int64_t)148 * 48 && tuning(11) != 1) return launch_chain_sweep<Core, 64, 16, 2, 2>(prm, nchains, s, true);
     }
