@@ -1,0 +1,139 @@
+// Host side of the mid-size (8 < D <= 32) kernels (mid_kernels.cuh): one warp per chain or per (chain, step),
+// blocks in shared memory.  Called from the C-ABI entry points of capi_nat.cu / capi_ssm.cu when the state
+// dimension exceeds what one thread's registers hold.
+#include "dispatch.cuh"
+#include "mid_api.h"
+#include "mid_kernels.cuh"
+
+namespace mf {
+
+namespace {
+
+template <class K>
+int mid_prepare(SmemOnce& once, K kern, size_t bytes) {
+  const cudaError_t e = ensure_smem(once, kern, bytes);
+  if (e != cudaSuccess) {
+    set_last_error(cudaGetErrorString(e));
+    return MF_ERR_CUDA;
+  }
+  return MF_OK;
+}
+
+}  // namespace
+
+int mid_nat_to_ssm(int dtype, const void* th_lin, const void* th_diag, const void* th_sub, void* out_a,
+                   void* out_off, void* out_chol, int32_t* info, int64_t B, int64_t T, int64_t D, int smoothing,
+                   cudaStream_t s) {
+  if (!mid_dim(D)) return MF_ERR_UNSUPPORTED;
+  return dispatch_dtype(dtype, [&](auto tt) {
+    using Tp = typename decltype(tt)::type;
+    if (smoothing) {
+      auto kern = mid_nat_to_ssm_kernel<Tp>;
+      static SmemOnce once;
+      const size_t bytes = mid_smem_bytes(6, 2, sizeof(Tp));
+      if (int rc = mid_prepare(once, kern, bytes)) return rc;
+      kern<<<(unsigned)B, 32, bytes, s>>>((const Tp*)th_lin, (const Tp*)th_diag, (const Tp*)th_sub, (Tp*)out_a,
+                                           (Tp*)out_off, (Tp*)out_chol, info, B, T, (int)D);
+    } else {
+      if (info && cudaMemsetAsync(info, 0, sizeof(int32_t) * B, s) != cudaSuccess) return check_launch();
+      if (B * T > 0x7fffffffLL) return MF_ERR_UNSUPPORTED;
+      auto kern = mid_nat_to_ssm_no_smoothing_kernel<Tp>;
+      static SmemOnce once;
+      const size_t bytes = mid_smem_bytes(4, 2, sizeof(Tp));
+      if (int rc = mid_prepare(once, kern, bytes)) return rc;
+      kern<<<(unsigned)(B * T), 32, bytes, s>>>((const Tp*)th_lin, (const Tp*)th_diag, (const Tp*)th_sub,
+                                                 (Tp*)out_a, (Tp*)out_off, (Tp*)out_chol, info, B, T, (int)D);
+    }
+    return check_launch();
+  });
+}
+
+int mid_ssm_to_naturals(int dtype, const void* mu0, const void* chol_p0, const void* a, const void* b,
+                        const void* chol_q, void* th_lin, void* th_diag, void* th_sub, int64_t B, int64_t T,
+                        int64_t D, int smoothing, cudaStream_t s) {
+  if (!mid_dim(D)) return MF_ERR_UNSUPPORTED;
+  if (B * T > 0x7fffffffLL) return MF_ERR_UNSUPPORTED;
+  return dispatch_dtype(dtype, [&](auto tt) {
+    using Tp = typename decltype(tt)::type;
+    auto kern = mid_ssm_to_naturals_kernel<Tp>;
+    static SmemOnce once;
+    const size_t bytes = mid_smem_bytes(5, 1, sizeof(Tp));
+    if (int rc = mid_prepare(once, kern, bytes)) return rc;
+    kern<<<(unsigned)(B * T), 32, bytes, s>>>((const Tp*)mu0, (const Tp*)chol_p0, (const Tp*)a, (const Tp*)b,
+                                               (const Tp*)chol_q, (Tp*)th_lin, (Tp*)th_diag, (Tp*)th_sub, B, T,
+                                               (int)D, smoothing);
+    return check_launch();
+  });
+}
+
+int mid_ssm_moments(int dtype, int expectations, const void* mu0, const void* chol_p0, const void* a,
+                    const void* b, const void* chol_q, void* o_vec, void* o_diag, void* o_sub, int64_t B,
+                    int64_t T, int64_t D, cudaStream_t s) {
+  if (!mid_dim(D)) return MF_ERR_UNSUPPORTED;
+  return dispatch_dtype(dtype, [&](auto tt) {
+    using Tp = typename decltype(tt)::type;
+    const size_t bytes = mid_smem_bytes(5, 0, sizeof(Tp));
+    if (expectations) {
+      auto kern = mid_ssm_moments_kernel<Tp, true>;
+      static SmemOnce once;
+      if (int rc = mid_prepare(once, kern, bytes)) return rc;
+      kern<<<(unsigned)B, 32, bytes, s>>>((const Tp*)mu0, (const Tp*)chol_p0, (const Tp*)a, (const Tp*)b,
+                                           (const Tp*)chol_q, (Tp*)o_vec, (Tp*)o_diag, (Tp*)o_sub, B, T, (int)D);
+    } else {
+      auto kern = mid_ssm_moments_kernel<Tp, false>;
+      static SmemOnce once;
+      if (int rc = mid_prepare(once, kern, bytes)) return rc;
+      kern<<<(unsigned)B, 32, bytes, s>>>((const Tp*)mu0, (const Tp*)chol_p0, (const Tp*)a, (const Tp*)b,
+                                           (const Tp*)chol_q, (Tp*)o_vec, (Tp*)o_diag, (Tp*)o_sub, B, T, (int)D);
+    }
+    return check_launch();
+  });
+}
+
+int mid_expectations_to_ssm(int dtype, const void* eta_lin, const void* eta_diag, const void* eta_sub,
+                            void* out_a, void* out_off, void* out_chol, int32_t* info, int64_t B, int64_t T,
+                            int64_t D, cudaStream_t s) {
+  if (!mid_dim(D)) return MF_ERR_UNSUPPORTED;
+  if (B * T > 0x7fffffffLL) return MF_ERR_UNSUPPORTED;
+  return dispatch_dtype(dtype, [&](auto tt) {
+    using Tp = typename decltype(tt)::type;
+    auto kern = mid_expectations_to_ssm_kernel<Tp>;
+    static SmemOnce once;
+    const size_t bytes = mid_smem_bytes(6, 1, sizeof(Tp));
+    if (int rc = mid_prepare(once, kern, bytes)) return rc;
+    kern<<<(unsigned)(B * T), 32, bytes, s>>>((const Tp*)eta_lin, (const Tp*)eta_diag, (const Tp*)eta_sub,
+                                               (Tp*)out_a, (Tp*)out_off, (Tp*)out_chol, info, B, T, (int)D);
+    return check_launch();
+  });
+}
+
+int mid_block_cholesky_or_zero(int dtype, const void* cov, void* out, int32_t* info, int64_t n, int64_t D,
+                               cudaStream_t s) {
+  if (!mid_dim(D)) return MF_ERR_UNSUPPORTED;
+  if (n > 0x7fffffffLL) return MF_ERR_UNSUPPORTED;
+  return dispatch_dtype(dtype, [&](auto tt) {
+    using Tp = typename decltype(tt)::type;
+    auto kern = mid_block_cholesky_or_zero_kernel<Tp>;
+    static SmemOnce once;
+    const size_t bytes = mid_smem_bytes(1, 1, sizeof(Tp));
+    if (int rc = mid_prepare(once, kern, bytes)) return rc;
+    kern<<<(unsigned)n, 32, bytes, s>>>((const Tp*)cov, (Tp*)out, info, n, (int)D);
+    return check_launch();
+  });
+}
+
+int mid_block_chol_of_inverse(int dtype, const void* chol, void* out, int64_t n, int64_t D, cudaStream_t s) {
+  if (!mid_dim(D)) return MF_ERR_UNSUPPORTED;
+  if (n > 0x7fffffffLL) return MF_ERR_UNSUPPORTED;
+  return dispatch_dtype(dtype, [&](auto tt) {
+    using Tp = typename decltype(tt)::type;
+    auto kern = mid_block_chol_of_inverse_kernel<Tp>;
+    static SmemOnce once;
+    const size_t bytes = mid_smem_bytes(3, 1, sizeof(Tp));
+    if (int rc = mid_prepare(once, kern, bytes)) return rc;
+    kern<<<(unsigned)n, 32, bytes, s>>>((const Tp*)chol, (Tp*)out, n, (int)D);
+    return check_launch();
+  });
+}
+
+}  // namespace mf

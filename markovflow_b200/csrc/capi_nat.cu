@@ -1,6 +1,7 @@
 // C-ABI entry points for the natural / expectation parameter transforms
 // (include/markovflow_b200.h; reference markovflow/ssm_gaussian_transformations.py).
 #include "dispatch.cuh"
+#include "mid_api.h"
 #include "nat_kernels.cuh"
 #include "ssm_sweep_api.h"
 
@@ -16,6 +17,9 @@ int mf_nat_to_ssm(int dtype, const void* theta_lin, const void* theta_diag, cons
   if (!theta_lin || !theta_diag || !out_offsets || !out_chols) return MF_ERR_BAD_ARG;
   if (T > 1 && (!theta_sub || !out_a)) return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (mid_dim(D))
+    return mid_nat_to_ssm(dtype, theta_lin, theta_diag, theta_sub, out_a, out_offsets, out_chols, info, B, T, D,
+                          smoothing, s);
   if (smoothing && D <= kSsmSweepMaxD && T > 1 && tuning(4) != 1) {
     const int rc = nat_sweep_to_ssm(dtype, D, theta_lin, theta_diag, theta_sub, out_a, out_offsets,
                                     out_chols, info, B, T, s);
@@ -48,6 +52,9 @@ int mf_ssm_to_naturals(int dtype, const void* mu0, const void* chol_p0, const vo
   if (!mu0 || !chol_p0 || !theta_lin || !theta_diag) return MF_ERR_BAD_ARG;
   if (T > 1 && (!a || !b || !chol_q || !theta_sub)) return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (mid_dim(D))
+    return mid_ssm_to_naturals(dtype, mu0, chol_p0, a, b, chol_q, theta_lin, theta_diag, theta_sub, B, T, D,
+                               smoothing, s);
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
@@ -66,6 +73,7 @@ int mf_ssm_to_expectations(int dtype, const void* mu0, const void* chol_p0, cons
   if (!mu0 || !chol_p0 || !eta_lin || !eta_diag) return MF_ERR_BAD_ARG;
   if (T > 1 && (!a || !b || !chol_q || !eta_sub)) return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (mid_dim(D)) return mid_ssm_moments(dtype, 1, mu0, chol_p0, a, b, chol_q, eta_lin, eta_diag, eta_sub, B, T, D, s);
   if (D <= kSsmSweepMaxD && T > 1 && tuning(4) != 1) {
     const int rc = ssm_sweep_moments(dtype, D, 1, mu0, chol_p0, a, b, chol_q, eta_lin, eta_diag,
                                      eta_sub, B, T, s);
@@ -90,6 +98,8 @@ int mf_expectations_to_ssm(int dtype, const void* eta_lin, const void* eta_diag,
   if (T > 1 && (!eta_sub || !out_a)) return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   if (info && cudaMemsetAsync(info, 0, sizeof(int32_t) * B, s) != cudaSuccess) return check_launch();
+  if (mid_dim(D))
+    return mid_expectations_to_ssm(dtype, eta_lin, eta_diag, eta_sub, out_a, out_offsets, out_chols, info, B, T, D, s);
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;

@@ -1,5 +1,6 @@
 // C-ABI entry points for the StateSpaceModel operators (include/markovflow_b200.h).
 #include "dispatch.cuh"
+#include "mid_api.h"
 #include "ssm_kernels.cuh"
 #include "ssm_sweep_api.h"
 
@@ -91,6 +92,7 @@ int mf_ssm_marginals(int dtype, const void* mu0, const void* chol_p0, const void
   if (B == 0) return MF_OK;
   if (!mu0 || !chol_p0 || (T > 1 && (!a || !b || !chol_q))) return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (mid_dim(D)) return mid_ssm_moments(dtype, 0, mu0, chol_p0, a, b, chol_q, out_mean, out_cov, out_sub, B, T, D, s);
   if (D <= kSsmSweepMaxD && T > 1 && tuning(4) != 1) {
     const int rc = ssm_sweep_moments(dtype, D, 0, mu0, chol_p0, a, b, chol_q, out_mean, out_cov,
                                      out_sub, B, T, s);
@@ -165,6 +167,7 @@ int mf_block_cholesky_or_zero(int dtype, const void* cov, void* out, int32_t* in
   if (!cov || !out) return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   if (info && cudaMemsetAsync(info, 0, sizeof(int32_t), s) != cudaSuccess) return check_launch();
+  if (mid_dim(D)) return mid_block_cholesky_or_zero(dtype, cov, out, info, n, D, s);
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
@@ -180,6 +183,7 @@ int mf_block_chol_of_inverse(int dtype, const void* chol, void* out, int64_t n, 
   if (n == 0) return MF_OK;
   if (!chol || !out) return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (mid_dim(D)) return mid_block_chol_of_inverse(dtype, chol, out, n, D, s);
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;

@@ -1,0 +1,29 @@
+// Internal (C++) interface to the mid-size (8 < D <= 32) warp-per-chain implementations (capi_mid.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace mf {
+
+constexpr int kMidMaxD = 32;
+inline bool mid_dim(int64_t D) { return D > 8 && D <= kMidMaxD; }
+
+int mid_nat_to_ssm(int dtype, const void* th_lin, const void* th_diag, const void* th_sub, void* out_a,
+                   void* out_off, void* out_chol, int32_t* info, int64_t B, int64_t T, int64_t D, int smoothing,
+                   cudaStream_t s);
+int mid_ssm_to_naturals(int dtype, const void* mu0, const void* chol_p0, const void* a, const void* b,
+                        const void* chol_q, void* th_lin, void* th_diag, void* th_sub, int64_t B, int64_t T,
+                        int64_t D, int smoothing, cudaStream_t s);
+int mid_ssm_moments(int dtype, int expectations, const void* mu0, const void* chol_p0, const void* a,
+                    const void* b, const void* chol_q, void* o_vec, void* o_diag, void* o_sub, int64_t B,
+                    int64_t T, int64_t D, cudaStream_t s);
+int mid_expectations_to_ssm(int dtype, const void* eta_lin, const void* eta_diag, const void* eta_sub,
+                            void* out_a, void* out_off, void* out_chol, int32_t* info, int64_t B, int64_t T,
+                            int64_t D, cudaStream_t s);
+
+int mid_block_cholesky_or_zero(int dtype, const void* cov, void* out, int32_t* info, int64_t n, int64_t D,
+                               cudaStream_t s);
+int mid_block_chol_of_inverse(int dtype, const void* chol, void* out, int64_t n, int64_t D, cudaStream_t s);
+
+}  // namespace mf

@@ -1,0 +1,308 @@
+// Mid-size state dimensions, 8 < D <= 32: the natural / expectation parameter transforms and the moment recursion
+// with ONE WARP per chain (sequential recursions) or per (chain, step) (per-step maps), blocks in shared memory
+// (midmat.cuh).  Same algorithms, in the same order, as the one-thread-per-chain kernels of nat_kernels.cuh /
+// ssm_kernels.cuh, which hold a block in registers and stop at D = 8.  Reference:
+// markovflow/ssm_gaussian_transformations.py:31-593, state_space_model.py:202-275.
+#pragma once
+#include "midmat.cuh"
+
+namespace mf {
+
+// M += alpha * u v^T for vectors held one element per lane
+template <typename T>
+__device__ __forceinline__ void mid_rank1(T* __restrict__ m, T alpha, T u, T v, int d, int lane) {
+  __syncwarp();
+  const T au = alpha * u;
+  for (int j = 0; j < d; ++j) {
+    const T vj = __shfl_sync(0xffffffffu, v, j);
+    if (lane < d) m[lane * MID_LD + j] = Num<T>::fma(au, vj, m[lane * MID_LD + j]);
+  }
+  __syncwarp();
+}
+// upper triangle <- lower triangle
+template <typename T>
+__device__ __forceinline__ void mid_mirror_lower(T* m, int d, int lane) {
+  __syncwarp();
+  if (lane < d)
+    for (int j = lane + 1; j < d; ++j) m[lane * MID_LD + j] = m[j * MID_LD + lane];
+  __syncwarp();
+}
+
+template <typename T>
+struct MidSmem {
+  T* base;
+  __device__ __forceinline__ T* mat(int i) const { return base + i * MID_MAT; }
+  __device__ __forceinline__ T* vec(int nmat, int i) const { return base + nmat * MID_MAT + i * 32; }
+};
+inline size_t mid_smem_bytes(int nmat, int nvec, size_t es) { return ((size_t)nmat * MID_MAT + (size_t)nvec * 32) * es; }
+
+// ---- naturals_to_ssm_params, smoothing (nat_kernels.cuh::nat_to_ssm_kernel): backward sweep, warp per chain -------
+template <typename T>
+__global__ void __launch_bounds__(32)
+mid_nat_to_ssm_kernel(const T* __restrict__ th_lin, const T* __restrict__ th_diag, const T* __restrict__ th_sub,
+                      T* __restrict__ out_a, T* __restrict__ out_off, T* __restrict__ out_chol,
+                      int32_t* __restrict__ info, int64_t B, int64_t Tn, int d) {
+  extern __shared__ __align__(16) unsigned char mid_raw[];
+  const MidSmem<T> sm{reinterpret_cast<T*>(mid_raw)};
+  constexpr int NM = 6;
+  T *Dk = sm.mat(0), *S = sm.mat(1), *A = sm.mat(2), *Th = sm.mat(3), *Qc = sm.mat(4), *W = sm.mat(5);
+  T *rinv = sm.vec(NM, 0), *rinv2 = sm.vec(NM, 1);
+  const int lane = threadIdx.x;
+  const int64_t c = blockIdx.x;
+  const int dd = d * d;
+  const T* lp = th_lin + c * Tn * d;
+  const T* dp = th_diag + c * Tn * dd;
+  const T* sp = th_sub + c * (Tn - 1) * dd;
+  T* ap = out_a + c * (Tn - 1) * dd;
+  T* op = out_off + c * Tn * d;
+  T* cp = out_chol + c * Tn * dd;
+  int32_t fail = 0;
+  T z = T(0);
+  for (int64_t k = Tn - 1; k >= 0; --k) {
+    mid_load<T>(Dk, dp + k * dd, d, lane);
+    T th = lane < d ? lp[k * d + lane] : T(0);
+    mid_scale<T>(Dk, T(-2), d, lane);
+    if (k + 1 < Tn) {
+      mid_load<T>(A, sp + k * dd, d, lane);
+      mid_copy<T>(Th, A, d, lane);
+      mid_trsm_l<T>(S, rinv, A, d, lane);
+      mid_trsm_lt<T>(S, rinv, A, d, lane);  // A_k = D_{k+1}^{-1} theta_sub_k
+      mid_store<T>(ap + k * dd, A, d, lane);
+      mid_gemm<T, true, false, -1>(Dk, Th, A, d, lane);  // D_k = -2 theta_diag_k - theta_sub_k^T A_k
+      th = mid_gemv<T, true, 1>(A, z, th, d, lane);      // z_k = theta_lin_k + A_k^T z_{k+1}
+    }
+    z = th;
+    mid_copy<T>(S, Dk, d, lane);
+    const bool ok = mid_chol<T>(S, rinv, d, lane);
+    if (!ok && fail == 0) fail = (int32_t)(k + 1);
+    T off = mid_trsv_l<T>(S, rinv, z, d, lane);
+    off = mid_trsv_lt<T>(S, rinv, off, d, lane);  // offset_k = D_k^{-1} z_k
+    if (lane < d) op[k * d + lane] = off;
+    mid_chol_inverse<T>(Qc, S, rinv, W, d, lane);  // Q_k = D_k^{-1}
+    mid_chol<T>(Qc, rinv2, d, lane);
+    mid_store_lower<T>(cp + k * dd, Qc, d, lane);
+  }
+  if (info && lane == 0) info[c] = fail;
+}
+
+// ---- moment recursion (ssm_kernels.cuh::ssm_marginals_kernel, nat_kernels.cuh::ssm_to_expectations_kernel) ------
+// EXPECT = false: (mu_k, Sigma_kk, A_k Sigma_kk);  true: (mu_k, Sigma_kk + mu mu^T, A_k Sigma_kk + mu_{k+1} mu_k^T).
+// Any output may be NULL.
+template <typename T, bool EXPECT>
+__global__ void __launch_bounds__(32)
+mid_ssm_moments_kernel(const T* __restrict__ mu0, const T* __restrict__ chol_p0, const T* __restrict__ a,
+                       const T* __restrict__ b, const T* __restrict__ chol_q, T* __restrict__ o_vec,
+                       T* __restrict__ o_diag, T* __restrict__ o_sub, int64_t B, int64_t Tn, int d) {
+  extern __shared__ __align__(16) unsigned char mid_raw[];
+  const MidSmem<T> sm{reinterpret_cast<T*>(mid_raw)};
+  T *P = sm.mat(0), *A = sm.mat(1), *L = sm.mat(2), *AP = sm.mat(3), *E = sm.mat(4);
+  const int lane = threadIdx.x;
+  const int64_t c = blockIdx.x;
+  const int dd = d * d;
+  const T* ap = a + c * (Tn - 1) * dd;
+  const T* bp = b + c * (Tn - 1) * d;
+  const T* qp = chol_q + c * (Tn - 1) * dd;
+  T mu = lane < d ? mu0[c * d + lane] : T(0);
+  mid_load<T>(L, chol_p0 + c * dd, d, lane);
+  mid_gemm<T, false, true, 0>(P, L, L, d, lane);
+  for (int64_t k = 0; k < Tn; ++k) {
+    if (o_vec && lane < d) o_vec[(c * Tn + k) * d + lane] = mu;
+    if (o_diag) {
+      if (EXPECT) {
+        mid_copy<T>(E, P, d, lane);
+        mid_rank1<T>(E, T(1), mu, mu, d, lane);
+        mid_store<T>(o_diag + (c * Tn + k) * dd, E, d, lane);
+      } else {
+        mid_store<T>(o_diag + (c * Tn + k) * dd, P, d, lane);
+      }
+    }
+    if (k + 1 == Tn) break;
+    mid_load<T>(A, ap + k * dd, d, lane);
+    mid_load<T>(L, qp + k * dd, d, lane);
+    const T bk = lane < d ? bp[k * d + lane] : T(0);
+    const T nmu = mid_gemv<T, false, 1>(A, mu, bk, d, lane);
+    mid_gemm<T, false, false, 0>(AP, A, P, d, lane);
+    if (o_sub) {
+      if (EXPECT) {
+        mid_copy<T>(E, AP, d, lane);
+        mid_rank1<T>(E, T(1), nmu, mu, d, lane);
+        mid_store<T>(o_sub + (c * (Tn - 1) + k) * dd, E, d, lane);
+      } else {
+        mid_store<T>(o_sub + (c * (Tn - 1) + k) * dd, AP, d, lane);
+      }
+    }
+    mid_gemm<T, false, true, 0>(P, L, L, d, lane);   // Q_{k+1}
+    mid_gemm<T, false, true, 1>(P, AP, A, d, lane);  // + A P A^T
+    mid_mirror_lower<T>(P, d, lane);
+    mu = nmu;
+  }
+}
+
+// ---- expectations_to_ssm_params (nat_kernels.cuh::expectations_to_ssm_kernel): warp per (chain, step) ---------------
+template <typename T>
+__global__ void __launch_bounds__(32)
+mid_expectations_to_ssm_kernel(const T* __restrict__ eta_lin, const T* __restrict__ eta_diag,
+                               const T* __restrict__ eta_sub, T* __restrict__ out_a, T* __restrict__ out_off,
+                               T* __restrict__ out_chol, int32_t* __restrict__ info, int64_t B, int64_t Tn, int d) {
+  extern __shared__ __align__(16) unsigned char mid_raw[];
+  const MidSmem<T> sm{reinterpret_cast<T*>(mid_raw)};
+  constexpr int NM = 6;
+  T *Sk = sm.mat(0), *Sp = sm.mat(1), *Lp = sm.mat(2), *X = sm.mat(3), *A = sm.mat(4), *W = sm.mat(5);
+  T* rinv = sm.vec(NM, 0);
+  const int lane = threadIdx.x;
+  const int64_t idx = blockIdx.x;
+  const int64_t c = idx / Tn, k = idx % Tn;
+  const int dd = d * d;
+  const T ek = lane < d ? eta_lin[idx * d + lane] : T(0);
+  mid_load<T>(Sk, eta_diag + idx * dd, d, lane);
+  mid_rank1<T>(Sk, T(-1), ek, ek, d, lane);  // Sigma_k
+  bool ok = true;
+  if (k == 0) {
+    if (lane < d) out_off[idx * d + lane] = ek;
+    ok = mid_chol<T>(Sk, rinv, d, lane);
+    mid_store_lower<T>(out_chol + idx * dd, Sk, d, lane);
+  } else {
+    const T ep = lane < d ? eta_lin[(idx - 1) * d + lane] : T(0);
+    mid_load<T>(Sp, eta_diag + (idx - 1) * dd, d, lane);
+    mid_rank1<T>(Sp, T(-1), ep, ep, d, lane);  // Sigma_{k-1}
+    mid_load<T>(W, eta_sub + (c * (Tn - 1) + k - 1) * dd, d, lane);
+    mid_transpose<T>(X, W, d, lane);
+    mid_rank1<T>(X, T(-1), ep, ek, d, lane);  // Sigma_{k-1,k} = eta_sub^T - eta_{k-1} eta_k^T
+    mid_copy<T>(Lp, Sp, d, lane);
+    ok = mid_chol<T>(Lp, rinv, d, lane);
+    mid_trsm_l<T>(Lp, rinv, X, d, lane);
+    mid_trsm_lt<T>(Lp, rinv, X, d, lane);  // Sigma_{k-1}^{-1} Sigma_{k-1,k} = A^T
+    mid_transpose<T>(A, X, d, lane);
+    mid_store<T>(out_a + (c * (Tn - 1) + k - 1) * dd, A, d, lane);
+    const T off = mid_gemv<T, false, -1>(A, ep, ek, d, lane);  // b = eta_k - A eta_{k-1}
+    if (lane < d) out_off[idx * d + lane] = off;
+    mid_gemm<T, false, false, 0>(W, A, Sp, d, lane);
+    mid_gemm<T, false, true, -1>(Sk, W, A, d, lane);  // Sigma_k - A Sigma_{k-1} A^T
+    ok = mid_chol<T>(Sk, rinv, d, lane) && ok;
+    mid_store_lower<T>(out_chol + idx * dd, Sk, d, lane);
+  }
+  if (info && !ok && lane == 0) atomicMax(info + c, (int32_t)(k + 1));
+}
+
+// ---- ssm_to_naturals (+ no smoothing) (nat_kernels.cuh::ssm_to_naturals_kernel): warp per (chain, step) -------------
+template <typename T>
+__global__ void __launch_bounds__(32)
+mid_ssm_to_naturals_kernel(const T* __restrict__ mu0, const T* __restrict__ chol_p0, const T* __restrict__ a,
+                           const T* __restrict__ b, const T* __restrict__ chol_q, T* __restrict__ th_lin,
+                           T* __restrict__ th_diag, T* __restrict__ th_sub, int64_t B, int64_t Tn, int d,
+                           int smoothing) {
+  extern __shared__ __align__(16) unsigned char mid_raw[];
+  const MidSmem<T> sm{reinterpret_cast<T*>(mid_raw)};
+  constexpr int NM = 5;
+  T *L = sm.mat(0), *Qi = sm.mat(1), *A = sm.mat(2), *X = sm.mat(3), *W = sm.mat(4);
+  T* rinv = sm.vec(NM, 0);
+  const int lane = threadIdx.x;
+  const int64_t idx = blockIdx.x;
+  const int64_t c = idx / Tn, k = idx % Tn;
+  const int64_t tr = c * (Tn - 1);
+  const int dd = d * d;
+  mid_load<T>(L, k == 0 ? chol_p0 + c * dd : chol_q + (tr + k - 1) * dd, d, lane);
+  T lin = lane < d ? (k == 0 ? mu0[c * d + lane] : b[(tr + k - 1) * d + lane]) : T(0);
+  mid_diag_rcp<T>(L, rinv, d, lane);
+  mid_chol_inverse<T>(Qi, L, rinv, W, d, lane);
+  lin = mid_trsv_l<T>(L, rinv, lin, d, lane);
+  lin = mid_trsv_lt<T>(L, rinv, lin, d, lane);  // Q_k^{-1} m_k
+  if (k + 1 < Tn) {
+    mid_load<T>(L, chol_q + (tr + k) * dd, d, lane);
+    mid_load<T>(A, a + (tr + k) * dd, d, lane);
+    const T nm = lane < d ? b[(tr + k) * d + lane] : T(0);
+    mid_diag_rcp<T>(L, rinv, d, lane);
+    mid_copy<T>(X, A, d, lane);
+    mid_trsm_l<T>(L, rinv, X, d, lane);
+    mid_trsm_lt<T>(L, rinv, X, d, lane);  // Q_{k+1}^{-1} A_k
+    mid_store<T>(th_sub + (tr + k) * dd, X, d, lane);
+    if (smoothing) {
+      mid_gemm<T, true, false, 1>(Qi, A, X, d, lane);
+      mid_mirror_lower<T>(Qi, d, lane);
+      lin = mid_gemv<T, true, -1>(X, nm, lin, d, lane);  // - A^T Q^{-1} m_{k+1}
+    }
+  }
+  mid_scale<T>(Qi, T(-0.5), d, lane);
+  mid_store<T>(th_diag + idx * dd, Qi, d, lane);
+  if (lane < d) th_lin[idx * d + lane] = lin;
+}
+
+// ---- naturals_to_ssm_params_no_smoothing (nat_kernels.cuh): warp per (chain, step) ----------------------------------
+template <typename T>
+__global__ void __launch_bounds__(32)
+mid_nat_to_ssm_no_smoothing_kernel(const T* __restrict__ th_lin, const T* __restrict__ th_diag,
+                                   const T* __restrict__ th_sub, T* __restrict__ out_a, T* __restrict__ out_off,
+                                   T* __restrict__ out_chol, int32_t* __restrict__ info, int64_t B, int64_t Tn,
+                                   int d) {
+  extern __shared__ __align__(16) unsigned char mid_raw[];
+  const MidSmem<T> sm{reinterpret_cast<T*>(mid_raw)};
+  constexpr int NM = 4;
+  T *S = sm.mat(0), *A = sm.mat(1), *Qc = sm.mat(2), *W = sm.mat(3);
+  T *rinv = sm.vec(NM, 0), *rinv2 = sm.vec(NM, 1);
+  const int lane = threadIdx.x;
+  const int64_t idx = blockIdx.x;
+  const int64_t c = idx / Tn, k = idx % Tn;
+  const int dd = d * d;
+  mid_load<T>(S, th_diag + idx * dd, d, lane);
+  mid_scale<T>(S, T(-2), d, lane);
+  const bool ok = mid_chol<T>(S, rinv, d, lane);
+  T off = lane < d ? th_lin[idx * d + lane] : T(0);
+  off = mid_trsv_l<T>(S, rinv, off, d, lane);
+  off = mid_trsv_lt<T>(S, rinv, off, d, lane);
+  if (lane < d) out_off[idx * d + lane] = off;
+  if (k > 0) {
+    mid_load<T>(A, th_sub + (c * (Tn - 1) + k - 1) * dd, d, lane);
+    mid_trsm_l<T>(S, rinv, A, d, lane);
+    mid_trsm_lt<T>(S, rinv, A, d, lane);
+    mid_store<T>(out_a + (c * (Tn - 1) + k - 1) * dd, A, d, lane);
+  }
+  mid_chol_inverse<T>(Qc, S, rinv, W, d, lane);
+  mid_chol<T>(Qc, rinv2, d, lane);
+  mid_store_lower<T>(out_chol + idx * dd, Qc, d, lane);
+  if (info && !ok && lane == 0) atomicMax(info + c, (int32_t)(k + 1));
+}
+
+// ---- per-block maps (ssm_kernels.cuh::block_cholesky_or_zero_kernel, block_chol_of_inverse_kernel): warp per block ---
+template <typename T>
+__global__ void __launch_bounds__(32)
+mid_block_cholesky_or_zero_kernel(const T* __restrict__ cov, T* __restrict__ out, int32_t* __restrict__ info,
+                                  int64_t n, int d) {
+  extern __shared__ __align__(16) unsigned char mid_raw[];
+  const MidSmem<T> sm{reinterpret_cast<T*>(mid_raw)};
+  T* S = sm.mat(0);
+  T* rinv = sm.vec(1, 0);
+  const int lane = threadIdx.x;
+  const int64_t i = blockIdx.x;
+  const int dd = d * d;
+  bool nz = false;
+  for (int idx = lane; idx < dd; idx += 32) nz = nz || (cov[i * dd + idx] != T(0));
+  const bool all_zero = !__any_sync(0xffffffffu, nz);
+  mid_load<T>(S, cov + i * dd, d, lane);
+  bool ok = true;
+  if (!all_zero) {
+    ok = mid_chol<T>(S, rinv, d, lane);
+    mid_store_lower<T>(out + i * dd, S, d, lane);
+  } else {
+    mid_store<T>(out + i * dd, S, d, lane);
+  }
+  if (info && !ok && lane == 0) atomicMax(info, (int32_t)(i < 2147483647 ? i + 1 : 2147483647));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32)
+mid_block_chol_of_inverse_kernel(const T* __restrict__ l, T* __restrict__ out, int64_t n, int d) {
+  extern __shared__ __align__(16) unsigned char mid_raw[];
+  const MidSmem<T> sm{reinterpret_cast<T*>(mid_raw)};
+  T *L = sm.mat(0), *S = sm.mat(1), *W = sm.mat(2);
+  T* rinv = sm.vec(3, 0);
+  const int lane = threadIdx.x;
+  const int64_t i = blockIdx.x;
+  const int dd = d * d;
+  mid_load<T>(L, l + i * dd, d, lane);
+  mid_diag_rcp<T>(L, rinv, d, lane);
+  mid_chol_inverse<T>(S, L, rinv, W, d, lane);
+  mid_chol<T>(S, rinv, d, lane);
+  mid_store_lower<T>(out + i * dd, S, d, lane);
+}
+
+}  // namespace mf
