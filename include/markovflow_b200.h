@@ -14,8 +14,8 @@
  *     chain through `info[b]` = 1-based block index of the first failing pivot (0 = success),
  *     LAPACK convention, replacing TF's "Banded Cholesky decomposition failure" error;
  *   - support dtype MF_F32 / MF_F64 and 1 <= D <= MF_SMALL_D_MAX (thread-per-chain register
- *     kernels); mf_btd_cholesky and mf_btd_solve also take MF_SMALL_D_MAX < D <= MF_BIG_D_MAX
- *     (one warp per chain, rows in registers) -- MF_ERR_UNSUPPORTED otherwise.
+ *     kernels); the entry points listed at MF_BIG_D_MAX below also take MF_SMALL_D_MAX < D <=
+ *     MF_BIG_D_MAX (one warp or half-warp per chain) -- MF_ERR_UNSUPPORTED otherwise.
  *
  * The mf_host_* variants (end of this header) take HOST pointers and perform the host<->device
  * copies themselves (chunked and pipelined on internal streams); they are what a host-resident
@@ -40,7 +40,12 @@ extern "C" {
 #define MF_F64 1
 
 #define MF_SMALL_D_MAX 8 /* thread-per-chain register kernels: every entry point */
-#define MF_BIG_D_MAX 32  /* warp-per-chain kernels: mf_btd_cholesky, mf_btd_solve */
+#define MF_BIG_D_MAX 32  /* warp-per-chain kernels (blocks in shared memory / spread over lanes): mf_btd_cholesky,
+                          * mf_btd_solve, mf_btd_inverse_subset, mf_btd_upper_diagonal_lower, mf_btd_dense_mult,
+                          * mf_btd_abs_log_det, mf_ssm_build_precision, mf_ssm_marginals, mf_ssm_affine_scan,
+                          * mf_ssm_log_pdf, mf_nat_to_ssm, mf_ssm_to_naturals, mf_ssm_to_expectations,
+                          * mf_expectations_to_ssm, mf_block_cholesky_or_zero, mf_block_chol_of_inverse,
+                          * mf_kalman_log_likelihood */
 
 /* Library / build information. */
 int mf_version(void);

@@ -206,6 +206,43 @@ def expectations_to_ssm_torch(eta_lin, eta_diag, eta_sub):
     return (a, torch.cat([eta_lin[:, :1], offsets], dim=1), torch.cat([chols[:, :1], chol_q], dim=1))
 
 
+def _sym_lower(m: torch.Tensor) -> torch.Tensor:
+    """The symmetric matrix the kernels see when they read lower triangles."""
+    return torch.tril(m) + torch.tril(m, -1).transpose(-1, -2)
+
+
+def naturals_to_ssm_diff(theta_lin, theta_diag, theta_sub, smoothing: bool = True):
+    """Differentiable ``naturals_to_ssm_params`` (``ssm_gaussian_transformations.py:332-593``) in the concatenated
+    layout of ``mf_nat_to_ssm``: ``(a [B,T-1,D,D], offsets [B,T,D], chols [B,T,D,D])``.
+
+    The backward ``U D U^T`` recursion ``D_k = P_kk - P_{k+1,k}^T D_{k+1}^{-1} P_{k+1,k}``,
+    ``z_k = theta_k + A_k^T z_{k+1}`` IS the block Cholesky + forward substitution of the TIME-REVERSED
+    precision: with ``C_k = chol(D_k)`` the reversed factor has diagonal blocks ``C_k`` and its forward solve
+    gives ``x_k = C_k^{-1} z_k``.  So the sequential part runs on the CUDA sweeps that have adjoint sweeps
+    (``CholeskyFn``, ``SolveFn``); what is left are per-step maps in batched torch ops:
+    ``A_k = D_{k+1}^{-1} theta_sub_k``, ``offset_k = C_k^{-T} x_k``, ``chol_k = chol(D_k^{-1})``."""
+    diag = _sym_lower(-2.0 * theta_diag)
+    if not smoothing:  # per-step map (:514-593)
+        c = torch.linalg.cholesky(diag)
+        off = torch.cholesky_solve(theta_lin[..., None], c)[..., 0]
+        a = torch.cholesky_solve(theta_sub, c[:, 1:])
+        chols = torch.linalg.cholesky(_sym_lower(torch.cholesky_inverse(c)))
+        return a, off, chols
+    t = theta_lin.shape[1]
+    if t == 1:
+        sub_r = None
+    else:
+        sub_r = torch.flip(-theta_sub.transpose(-1, -2), dims=(1,)).contiguous()  # P_{k+1,k}^T, reversed
+    ld_r, ls_r, _ = CholeskyFn.apply(torch.flip(diag, dims=(1,)).contiguous(), sub_r)
+    x_r = SolveFn.apply(ld_r, ls_r, torch.flip(theta_lin, dims=(1,)).contiguous(), False)
+    c = torch.tril(torch.flip(ld_r, dims=(1,)))  # C_k = chol(D_k)
+    x = torch.flip(x_r, dims=(1,))
+    off = torch.linalg.solve_triangular(c.transpose(-1, -2), x[..., None], upper=True)[..., 0]
+    a = torch.cholesky_solve(theta_sub, c[:, 1:]) if t > 1 else theta_sub
+    chols = torch.linalg.cholesky(_sym_lower(torch.cholesky_inverse(c)))
+    return a, off, chols
+
+
 # ---------------------------------------------------------------------------------------------------
 # composites, assembled from the primitives with the reference's formulas
 # ---------------------------------------------------------------------------------------------------

@@ -6,6 +6,7 @@
 #include "btd_staged.cuh"
 #include "btd_tma.cuh"
 #include "dispatch.cuh"
+#include "mid_api.h"
 #include "ssm_sweep_api.h"
 
 namespace mf {
@@ -196,6 +197,7 @@ int mf_btd_inverse_subset(int dtype, const void* ld, const void* ls, void* out_d
   if (T == 1) { ls = nullptr; out_sub = nullptr; }
   if (out_sub && !ls) return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (mid_dim(D)) return mid_inverse_subset(dtype, ld, ls, out_diag, out_sub, B, T, D, s);
   if (D <= kSsmSweepMaxD && T > 1 && tuning(4) != 1) {
     const int rc = btd_sweep_inverse_subset(dtype, D, ld, ls, out_diag, out_sub, B, T, s);
     if (rc != MF_ERR_UNSUPPORTED) return rc;
@@ -216,6 +218,7 @@ int mf_btd_upper_diagonal_lower(int dtype, const void* diag, const void* sub, vo
   if (B == 0) return MF_OK;
   if (!diag || !sub || !out_u || !out_chol_d) return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (mid_dim(D)) return mid_udu(dtype, diag, sub, out_u, out_chol_d, info, B, T, D, s);
   if (D <= kSsmSweepMaxD && tuning(4) != 1) {
     const int rc = btd_sweep_udu(dtype, D, diag, sub, out_u, out_chol_d, info, B, T, s);
     if (rc != MF_ERR_UNSUPPORTED) return rc;
@@ -237,6 +240,7 @@ int mf_btd_dense_mult(int dtype, const void* diag, const void* sub, const void* 
   if (!diag || !right || !out) return MF_ERR_BAD_ARG;
   if (T == 1) sub = nullptr;
   cudaStream_t s = (cudaStream_t)stream;
+  if (mid_dim(D)) return mid_dense_mult(dtype, diag, sub, right, out, n_rhs, Bm, T, D, transpose, symmetric, s);
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;

@@ -2,6 +2,7 @@
 #include <cstring>
 
 #include "dispatch.cuh"
+#include "mid_api.h"
 #include "kalman_kernels.cuh"
 #include "kalman_sweep_api.h"
 
@@ -410,6 +411,9 @@ int mf_kalman_log_likelihood(int dtype, const void* mu0, const void* chol_p0, co
   if (st != MF_OK) return st;
   if (B == 0) return MF_OK;
   if (!out) return MF_ERR_BAD_ARG;
+  if (mid_dim(D))
+    return mid_kalman_log_likelihood(dtype, mu0, chol_p0, a, b, chol_q, h, obs, chol_r, out, B, T, D, m, h_batch,
+                                     r_steps, (cudaStream_t)stream);
   const SweepPlan sp = make_sweep_plan(B, T, D, m);
   if (sp.use) {
     if (dtype != MF_F32 && dtype != MF_F64) return MF_ERR_BAD_ARG;

@@ -136,4 +136,92 @@ int mid_block_chol_of_inverse(int dtype, const void* chol, void* out, int64_t n,
   });
 }
 
+// one launch of a warp-per-block kernel with `nmat` matrix slots and `nvec` vector slots of shared memory
+#define MF_MID_LAUNCH(KERN, NBLOCKS, NMAT, NVEC, ...)                          \
+  do {                                                                         \
+    auto kern = KERN<Tp>;                                                      \
+    static SmemOnce once;                                                      \
+    const size_t bytes = mid_smem_bytes(NMAT, NVEC, sizeof(Tp));               \
+    if (int rc = mid_prepare(once, kern, bytes)) return rc;                    \
+    kern<<<(unsigned)(NBLOCKS), 32, bytes, s>>>(__VA_ARGS__);                  \
+    return check_launch();                                                     \
+  } while (0)
+
+int mid_build_precision(int dtype, const void* chol_p0, const void* a, const void* chol_q, const void* h,
+                        const void* r_inv, void* out_diag, void* out_sub, int64_t B, int64_t T, int64_t D, int64_t m,
+                        int64_t h_batch, int64_t r_steps, cudaStream_t s) {
+  if (!mid_dim(D) || B * T > 0x7fffffffLL) return MF_ERR_UNSUPPORTED;
+  return dispatch_dtype(dtype, [&](auto tt) {
+    using Tp = typename decltype(tt)::type;
+    MF_MID_LAUNCH(mid_build_precision_kernel, B * T, 5, 1, (const Tp*)chol_p0, (const Tp*)a, (const Tp*)chol_q,
+                  (const Tp*)h, (const Tp*)r_inv, (Tp*)out_diag, (Tp*)out_sub, B, T, (int)D, (int)m, h_batch, r_steps);
+  });
+}
+
+int mid_inverse_subset(int dtype, const void* ld, const void* ls, void* out_diag, void* out_sub, int64_t B,
+                       int64_t T, int64_t D, cudaStream_t s) {
+  if (!mid_dim(D)) return MF_ERR_UNSUPPORTED;
+  return dispatch_dtype(dtype, [&](auto tt) {
+    using Tp = typename decltype(tt)::type;
+    MF_MID_LAUNCH(mid_inverse_subset_kernel, B, 6, 1, (const Tp*)ld, (const Tp*)ls, (Tp*)out_diag, (Tp*)out_sub, B, T,
+                  (int)D);
+  });
+}
+
+int mid_udu(int dtype, const void* diag, const void* sub, void* out_u, void* out_chol_d, int32_t* info, int64_t B,
+            int64_t T, int64_t D, cudaStream_t s) {
+  if (!mid_dim(D)) return MF_ERR_UNSUPPORTED;
+  return dispatch_dtype(dtype, [&](auto tt) {
+    using Tp = typename decltype(tt)::type;
+    MF_MID_LAUNCH(mid_udu_kernel, B, 3, 1, (const Tp*)diag, (const Tp*)sub, (Tp*)out_u, (Tp*)out_chol_d, info, B, T,
+                  (int)D);
+  });
+}
+
+int mid_affine_scan(int dtype, const void* mu0, const void* chol_p0, const void* a, const void* b,
+                    const void* chol_q, const void* eps, void* out, int64_t n, int64_t Bm, int64_t T, int64_t D,
+                    cudaStream_t s) {
+  if (!mid_dim(D) || n > 0x7fffffffLL) return MF_ERR_UNSUPPORTED;
+  return dispatch_dtype(dtype, [&](auto tt) {
+    using Tp = typename decltype(tt)::type;
+    MF_MID_LAUNCH(mid_affine_scan_kernel, n, 2, 0, (const Tp*)mu0, (const Tp*)chol_p0, (const Tp*)a, (const Tp*)b,
+                  (const Tp*)chol_q, (const Tp*)eps, (Tp*)out, n, Bm, T, (int)D);
+  });
+}
+
+int mid_kalman_log_likelihood(int dtype, const void* mu0, const void* chol_p0, const void* a, const void* b,
+                              const void* chol_q, const void* h, const void* obs, const void* chol_r, void* out,
+                              int64_t B, int64_t T, int64_t D, int64_t m, int64_t h_batch, int64_t r_steps,
+                              cudaStream_t s) {
+  if (!mid_dim(D) || B > 0x7fffffffLL) return MF_ERR_UNSUPPORTED;
+  return dispatch_dtype(dtype, [&](auto tt) {
+    using Tp = typename decltype(tt)::type;
+    MF_MID_LAUNCH(mid_kalman_loglik_kernel, B, 4, 0, (const Tp*)mu0, (const Tp*)chol_p0, (const Tp*)a, (const Tp*)b,
+                  (const Tp*)chol_q, (const Tp*)h, (const Tp*)obs, (const Tp*)chol_r, (Tp*)out, B, T, (int)D, (int)m,
+                  h_batch, r_steps);
+  });
+}
+
+int mid_dense_mult(int dtype, const void* diag, const void* sub, const void* right, void* out, int64_t n_rhs,
+                   int64_t Bm, int64_t T, int64_t D, int transpose, int symmetric, cudaStream_t s) {
+  if (!mid_dim(D) || n_rhs * T > 0x7fffffffLL) return MF_ERR_UNSUPPORTED;
+  return dispatch_dtype(dtype, [&](auto tt) {
+    using Tp = typename decltype(tt)::type;
+    MF_MID_LAUNCH(mid_dense_mult_kernel, n_rhs * T, 1, 0, (const Tp*)diag, (const Tp*)sub, (const Tp*)right, (Tp*)out,
+                  n_rhs, Bm, T, (int)D, transpose, symmetric);
+  });
+}
+
+int mid_log_pdf(int dtype, const void* mu0, const void* chol_p0, const void* a, const void* b, const void* chol_q,
+                const void* states, void* out, int64_t n, int64_t Bm, int64_t T, int64_t D, cudaStream_t s) {
+  if (!mid_dim(D) || n > 0x7fffffffLL) return MF_ERR_UNSUPPORTED;
+  return dispatch_dtype(dtype, [&](auto tt) {
+    using Tp = typename decltype(tt)::type;
+    MF_MID_LAUNCH(mid_log_pdf_kernel, n, 2, 1, (const Tp*)mu0, (const Tp*)chol_p0, (const Tp*)a, (const Tp*)b,
+                  (const Tp*)chol_q, (const Tp*)states, (Tp*)out, n, Bm, T, (int)D);
+  });
+}
+
+#undef MF_MID_LAUNCH
+
 }  // namespace mf

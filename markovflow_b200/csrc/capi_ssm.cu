@@ -19,6 +19,8 @@ int mf_ssm_build_precision(int dtype, const void* chol_p0, const void* a, const 
   if (h && (!r_inv || m < 1 || (h_batch != 1 && h_batch != B) || (r_steps != 1 && r_steps != T)))
     return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (mid_dim(D))
+    return mid_build_precision(dtype, chol_p0, a, chol_q, h, r_inv, out_diag, out_sub, B, T, D, m, h_batch, r_steps, s);
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
@@ -37,6 +39,7 @@ int mf_ssm_affine_scan(int dtype, const void* mu0, const void* chol_p0, const vo
   if (!mu0 || !out || (T > 1 && (!a || !b))) return MF_ERR_BAD_ARG;
   if (eps && (!chol_p0 || (T > 1 && !chol_q))) return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (mid_dim(D)) return mid_affine_scan(dtype, mu0, chol_p0, a, b, chol_q, eps, out, n, Bm, T, D, s);
   if (D <= kSsmSweepMaxD && T > 1 && tuning(4) != 1) {
     const int rc = ssm_sweep_affine(dtype, D, mu0, chol_p0, a, b, chol_q, eps, out, n, Bm, T, s);
     if (rc != MF_ERR_UNSUPPORTED) return rc;
@@ -116,6 +119,7 @@ int mf_ssm_log_pdf(int dtype, const void* mu0, const void* chol_p0, const void* 
   if (!mu0 || !chol_p0 || !states || !out || (T > 1 && (!a || !b || !chol_q)))
     return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (mid_dim(D)) return mid_log_pdf(dtype, mu0, chol_p0, a, b, chol_q, states, out, n, Bm, T, D, s);
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;

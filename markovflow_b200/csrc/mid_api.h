@@ -26,4 +26,24 @@ int mid_block_cholesky_or_zero(int dtype, const void* cov, void* out, int32_t* i
                                cudaStream_t s);
 int mid_block_chol_of_inverse(int dtype, const void* chol, void* out, int64_t n, int64_t D, cudaStream_t s);
 
+int mid_build_precision(int dtype, const void* chol_p0, const void* a, const void* chol_q, const void* h,
+                        const void* r_inv, void* out_diag, void* out_sub, int64_t B, int64_t T, int64_t D, int64_t m,
+                        int64_t h_batch, int64_t r_steps, cudaStream_t s);
+int mid_inverse_subset(int dtype, const void* ld, const void* ls, void* out_diag, void* out_sub, int64_t B,
+                       int64_t T, int64_t D, cudaStream_t s);
+int mid_udu(int dtype, const void* diag, const void* sub, void* out_u, void* out_chol_d, int32_t* info, int64_t B,
+            int64_t T, int64_t D, cudaStream_t s);
+int mid_affine_scan(int dtype, const void* mu0, const void* chol_p0, const void* a, const void* b,
+                    const void* chol_q, const void* eps, void* out, int64_t n, int64_t Bm, int64_t T, int64_t D,
+                    cudaStream_t s);
+int mid_kalman_log_likelihood(int dtype, const void* mu0, const void* chol_p0, const void* a, const void* b,
+                              const void* chol_q, const void* h, const void* obs, const void* chol_r, void* out,
+                              int64_t B, int64_t T, int64_t D, int64_t m, int64_t h_batch, int64_t r_steps,
+                              cudaStream_t s);
+
+int mid_dense_mult(int dtype, const void* diag, const void* sub, const void* right, void* out, int64_t n_rhs,
+                   int64_t Bm, int64_t T, int64_t D, int transpose, int symmetric, cudaStream_t s);
+int mid_log_pdf(int dtype, const void* mu0, const void* chol_p0, const void* a, const void* b, const void* chol_q,
+                const void* states, void* out, int64_t n, int64_t Bm, int64_t T, int64_t D, cudaStream_t s);
+
 }  // namespace mf

@@ -4,6 +4,7 @@
 // ssm_kernels.cuh, which hold a block in registers and stop at D = 8.  Reference:
 // markovflow/ssm_gaussian_transformations.py:31-593, state_space_model.py:202-275.
 #pragma once
+#include "kalman_core.cuh"
 #include "midmat.cuh"
 
 namespace mf {
@@ -303,6 +304,315 @@ mid_block_chol_of_inverse_kernel(const T* __restrict__ l, T* __restrict__ out, i
   mid_chol_inverse<T>(S, L, rinv, W, d, lane);
   mid_chol<T>(S, rinv, d, lane);
   mid_store_lower<T>(out + i * dd, S, d, lane);
+}
+
+// ---- _build_precision (+ H^T R^-1 H) (ssm_kernels.cuh::ssm_build_precision_kernel): warp per (chain, step) ----------
+template <typename T>
+__global__ void __launch_bounds__(32)
+mid_build_precision_kernel(const T* __restrict__ chol_p0, const T* __restrict__ a, const T* __restrict__ chol_q,
+                           const T* __restrict__ h, const T* __restrict__ r_inv, T* __restrict__ out_diag,
+                           T* __restrict__ out_sub, int64_t B, int64_t Tn, int d, int m, int64_t Bh, int64_t Tr) {
+  extern __shared__ __align__(16) unsigned char mid_raw[];
+  const MidSmem<T> sm{reinterpret_cast<T*>(mid_raw)};
+  constexpr int NM = 5;
+  T *L = sm.mat(0), *Qi = sm.mat(1), *A = sm.mat(2), *X = sm.mat(3), *W = sm.mat(4);
+  T* rinv = sm.vec(NM, 0);
+  const int lane = threadIdx.x;
+  const int64_t idx = blockIdx.x;
+  const int64_t c = idx / Tn, k = idx % Tn;
+  const int dd = d * d;
+  mid_load<T>(L, k == 0 ? chol_p0 + c * dd : chol_q + (c * (Tn - 1) + k - 1) * dd, d, lane);
+  mid_diag_rcp<T>(L, rinv, d, lane);
+  mid_chol_inverse<T>(Qi, L, rinv, W, d, lane);
+  if (k + 1 < Tn) {
+    mid_load<T>(L, chol_q + (c * (Tn - 1) + k) * dd, d, lane);
+    mid_load<T>(A, a + (c * (Tn - 1) + k) * dd, d, lane);
+    mid_diag_rcp<T>(L, rinv, d, lane);
+    mid_copy<T>(X, A, d, lane);
+    mid_trsm_l<T>(L, rinv, X, d, lane);
+    mid_trsm_lt<T>(L, rinv, X, d, lane);  // X = Q_k^{-1} A_k
+    mid_gemm<T, true, false, 1>(Qi, A, X, d, lane);
+    mid_mirror_lower<T>(Qi, d, lane);
+    mid_scale<T>(X, T(-1), d, lane);
+    mid_store<T>(out_sub + (c * (Tn - 1) + k) * dd, X, d, lane);
+  }
+  if (h) {
+    const T* hp = h + (((Bh == 1) ? 0 : c) * Tn + k) * (int64_t)m * d;
+    const T* rp = r_inv + ((Tr == 1) ? 0 : k) * (int64_t)m * m;
+    __syncwarp();
+    for (int i = 0; i < m; ++i)
+      for (int j = 0; j < m; ++j) {
+        const T rij = rp[i * m + j];
+        if (lane < d) {
+          const T hr = hp[i * d + lane] * rij;
+          for (int q = 0; q < d; ++q) Qi[lane * MID_LD + q] = Num<T>::fma(hr, hp[j * d + q], Qi[lane * MID_LD + q]);
+        }
+      }
+    __syncwarp();
+  }
+  mid_store<T>(out_diag + idx * dd, Qi, d, lane);
+}
+
+// ---- sparse inverse subset (btd_direct.cuh::btd_inverse_subset_direct_kernel): backward, warp per chain -----------
+template <typename T>
+__global__ void __launch_bounds__(32)
+mid_inverse_subset_kernel(const T* __restrict__ ld, const T* __restrict__ ls, T* od, T* os, int64_t B, int64_t Tn,
+                          int d) {
+  extern __shared__ __align__(16) unsigned char mid_raw[];
+  const MidSmem<T> sm{reinterpret_cast<T*>(mid_raw)};
+  constexpr int NM = 6;
+  T *L = sm.mat(0), *J = sm.mat(1), *sig = sm.mat(2), *loc = sm.mat(3), *ssub = sm.mat(4), *W = sm.mat(5);
+  T* rinv = sm.vec(NM, 0);
+  const int lane = threadIdx.x;
+  const int64_t c = blockIdx.x;
+  const int dd = d * d;
+  const T* lp = ld + c * Tn * dd;
+  const T* sp = ls ? ls + c * (Tn - 1) * dd : nullptr;
+  T* odp = od + c * Tn * dd;
+  T* osp = os ? os + c * (Tn - 1) * dd : nullptr;
+  for (int64_t k = Tn - 1; k >= 0; --k) {
+    mid_load<T>(L, lp + k * dd, d, lane);
+    mid_diag_rcp<T>(L, rinv, d, lane);
+    mid_chol_inverse<T>(loc, L, rinv, W, d, lane);
+    if (sp && k + 1 < Tn) {
+      mid_load<T>(J, sp + k * dd, d, lane);
+      mid_trsm_right_l<T>(J, L, rinv, d, lane);          // J = Ls Ld^{-1}
+      mid_gemm<T, false, false, 0>(ssub, sig, J, d, lane);  // Sigma_{k+1,k+1} J
+      mid_scale<T>(ssub, T(-1), d, lane);
+      if (osp) mid_store<T>(osp + k * dd, ssub, d, lane);
+      mid_gemm<T, true, false, -1>(loc, J, ssub, d, lane);  // loc -= J^T ssub
+      mid_mirror_lower<T>(loc, d, lane);
+    }
+    mid_store<T>(odp + k * dd, loc, d, lane);
+    mid_copy<T>(sig, loc, d, lane);
+  }
+}
+
+// ---- U D U^T (btd_direct.cuh::btd_udu_direct_kernel): backward, warp per chain --------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(32)
+mid_udu_kernel(const T* __restrict__ diag, const T* __restrict__ sub, T* ou, T* ocd, int32_t* __restrict__ info,
+               int64_t B, int64_t Tn, int d) {
+  extern __shared__ __align__(16) unsigned char mid_raw[];
+  const MidSmem<T> sm{reinterpret_cast<T*>(mid_raw)};
+  constexpr int NM = 3;
+  T *C = sm.mat(0), *K = sm.mat(1), *X = sm.mat(2);
+  T* rinv = sm.vec(NM, 0);
+  const int lane = threadIdx.x;
+  const int64_t c = blockIdx.x;
+  const int dd = d * d;
+  const T* dp = diag + c * Tn * dd;
+  const T* sp = sub + c * (Tn - 1) * dd;
+  T* oup = ou + c * (Tn - 1) * dd;
+  T* ocp = ocd + c * Tn * dd;
+  int32_t fail = 0;
+  mid_load<T>(C, dp + (Tn - 1) * dd, d, lane);
+  bool ok = mid_chol<T>(C, rinv, d, lane);
+  if (!ok) fail = (int32_t)Tn;
+  mid_store_lower<T>(ocp + (Tn - 1) * dd, C, d, lane);
+  for (int64_t k = Tn - 2; k >= 0; --k) {
+    mid_load<T>(K, sp + k * dd, d, lane);
+    mid_copy<T>(X, K, d, lane);
+    mid_trsm_l<T>(C, rinv, X, d, lane);
+    mid_trsm_lt<T>(C, rinv, X, d, lane);  // X = D_{k+1}^{-1} K_{k+1,k}
+    mid_store<T>(oup + k * dd, X, d, lane);
+    mid_load<T>(C, dp + k * dd, d, lane);
+    mid_gemm<T, true, false, -1>(C, K, X, d, lane);
+    ok = mid_chol<T>(C, rinv, d, lane);
+    if (!ok && fail == 0) fail = (int32_t)(k + 1);
+    mid_store_lower<T>(ocp + k * dd, C, d, lane);
+  }
+  if (info && lane == 0) info[c] = fail;
+}
+
+// ---- affine recurrence (ssm_kernels.cuh::ssm_affine_scan_kernel): marginal means / sample, warp per trajectory -----
+template <typename T>
+__global__ void __launch_bounds__(32)
+mid_affine_scan_kernel(const T* __restrict__ mu0, const T* __restrict__ chol_p0, const T* __restrict__ a,
+                       const T* __restrict__ b, const T* __restrict__ chol_q, const T* __restrict__ eps,
+                       T* __restrict__ out, int64_t n, int64_t Bm, int64_t Tn, int d) {
+  extern __shared__ __align__(16) unsigned char mid_raw[];
+  const MidSmem<T> sm{reinterpret_cast<T*>(mid_raw)};
+  T *A = sm.mat(0), *L = sm.mat(1);
+  const int lane = threadIdx.x;
+  const int64_t c = blockIdx.x, cm = c % Bm;
+  const int dd = d * d;
+  const T* ep = eps ? eps + c * Tn * d : nullptr;
+  T x = lane < d ? mu0[cm * d + lane] : T(0);
+  if (ep) {
+    mid_load<T>(L, chol_p0 + cm * dd, d, lane);
+    const T e = lane < d ? ep[lane] : T(0);
+    x = mid_gemv<T, false, 1>(L, e, x, d, lane);
+  }
+  if (lane < d) out[c * Tn * d + lane] = x;
+  for (int64_t k = 1; k < Tn; ++k) {
+    mid_load<T>(A, a + (cm * (Tn - 1) + k - 1) * dd, d, lane);
+    const T bk = lane < d ? b[(cm * (Tn - 1) + k - 1) * d + lane] : T(0);
+    x = mid_gemv<T, false, 1>(A, x, bk, d, lane);
+    if (ep) {
+      mid_load<T>(L, chol_q + (cm * (Tn - 1) + k - 1) * dd, d, lane);
+      const T e = lane < d ? ep[k * d + lane] : T(0);
+      x = mid_gemv<T, false, 1>(L, e, x, d, lane);
+    }
+    if (lane < d) out[(c * Tn + k) * d + lane] = x;
+  }
+}
+
+// ---- Kalman log-likelihood, classical filter with scalar absorption (kalman_kernels.cuh::kalman_walk + FilterSink):
+//      warp per series.  Arguments as KalmanArgs; first step is the prior.
+template <typename T>
+__global__ void __launch_bounds__(32)
+mid_kalman_loglik_kernel(const T* __restrict__ mu0, const T* __restrict__ chol_p0, const T* __restrict__ a,
+                         const T* __restrict__ b, const T* __restrict__ chol_q, const T* __restrict__ h,
+                         const T* __restrict__ obs, const T* __restrict__ chol_r, T* __restrict__ out, int64_t B,
+                         int64_t Tn, int d, int m, int64_t Bh, int64_t Tr) {
+  extern __shared__ __align__(16) unsigned char mid_raw[];
+  const MidSmem<T> sm{reinterpret_cast<T*>(mid_raw)};
+  T *P = sm.mat(0), *F = sm.mat(1), *L = sm.mat(2), *FP = sm.mat(3);
+  const int lane = threadIdx.x;
+  const int64_t c = blockIdx.x;
+  const int dd = d * d;
+  const int64_t nt = Tn - 1;
+  const T* hp = h + (Bh == 1 ? 0 : c) * Tn * (int64_t)m * d;
+  const T* yp = obs + c * Tn * (int64_t)m;
+  Whitener<T> wh;
+  LogProd<T> wdet, det;
+  wdet.init();
+  det.init();
+  T quad = T(0);
+  int64_t nobs = 0;
+  if (Tr == 1) wh.set(chol_r, m);
+  T x = lane < d ? mu0[c * d + lane] : T(0);
+  mid_load<T>(L, chol_p0 + c * dd, d, lane);
+  mid_gemm<T, false, true, 0>(P, L, L, d, lane);
+  for (int64_t k = 0; k < Tn; ++k) {
+    if (k > 0) {
+      mid_load<T>(F, a + (c * nt + k - 1) * dd, d, lane);
+      mid_load<T>(L, chol_q + (c * nt + k - 1) * dd, d, lane);
+      const T u = lane < d ? b[(c * nt + k - 1) * d + lane] : T(0);
+      x = mid_gemv<T, false, 1>(F, x, u, d, lane);
+      mid_gemm<T, false, false, 0>(FP, F, P, d, lane);
+      mid_gemm<T, false, true, 0>(P, L, L, d, lane);
+      mid_gemm<T, false, true, 1>(P, FP, F, d, lane);
+      mid_mirror_lower<T>(P, d, lane);
+    }
+    if (Tr != 1) wh.set(chol_r + k * (int64_t)m * m, m);
+    const T* hk = hp + k * (int64_t)m * d;
+    const T* yk = yp + k * (int64_t)m;
+    for (int i = 0; i < m; ++i) {
+      const T wii = wh.W[i * kMaxObsDim + i];
+      if (m == 1 && wii == T(0)) continue;  // an infinite noise scale marks a step without observation
+      T hv = T(0), y = T(0);
+      for (int j = 0; j <= i; ++j) {
+        const T wij = wh.W[i * kMaxObsDim + j];
+        y = Num<T>::fma(wij, yk[j], y);
+        if (lane < d) hv = Num<T>::fma(wij, hk[j * d + lane], hv);
+      }
+      wdet.mul(wii);
+      // absorb the whitened scalar observation y = hv . x + N(0, 1)
+      const T g = mid_gemv<T, false, 0>(P, hv, T(0), d, lane);
+      const T s = mid_dot<T>(hv, g, T(1), d);
+      const T v = -mid_dot<T>(hv, x, -y, d);
+      const T rs = Num<T>::rcp(s);
+      const T vs = v * rs;
+      quad = Num<T>::fma(v, vs, quad);
+      det.mul_lazy(s);
+      x = Num<T>::fma(g, vs, x);
+      const T ki = g * rs;
+      __syncwarp();
+      for (int j = 0; j < d; ++j) {
+        const T gj = __shfl_sync(0xffffffffu, g, j);
+        if (lane < d && j <= lane) P[lane * MID_LD + j] = Num<T>::fma(-ki, gj, P[lane * MID_LD + j]);
+      }
+      mid_mirror_lower<T>(P, d, lane);
+      ++nobs;
+    }
+    det.peel();
+  }
+  if (lane == 0)
+    out[c] = T(-0.5) * (quad + det.log_abs()) + wdet.log_abs() - T(0.5 * 1.8378770664093454836) * T(nobs);
+}
+
+// ---- dense_mult (btd_direct.cuh::btd_dense_mult_kernel): warp per (rhs chain, block row) --------------------------
+template <typename T>
+__global__ void __launch_bounds__(32)
+mid_dense_mult_kernel(const T* __restrict__ diag, const T* __restrict__ sub, const T* __restrict__ right,
+                      T* __restrict__ out, int64_t n_rhs, int64_t Bm, int64_t Tn, int d, int transpose,
+                      int symmetric) {
+  extern __shared__ __align__(16) unsigned char mid_raw[];
+  const MidSmem<T> sm{reinterpret_cast<T*>(mid_raw)};
+  T* M = sm.mat(0);
+  const int lane = threadIdx.x;
+  const int64_t idx = blockIdx.x;
+  const int64_t c = idx / Tn, k = idx % Tn;
+  const int64_t cm = c % Bm;
+  const int dd = d * d;
+  const T* xp = right + (c * Tn + k) * d;
+  mid_load<T>(M, diag + (cm * Tn + k) * dd, d, lane);
+  T x = lane < d ? xp[lane] : T(0);
+  T y;
+  if (symmetric) {
+    mid_mirror_lower<T>(M, d, lane);
+    y = mid_gemv<T, false, 0>(M, x, T(0), d, lane);
+  } else {
+    __syncwarp();
+    if (lane < d)
+      for (int j = lane + 1; j < d; ++j) M[lane * MID_LD + j] = T(0);
+    y = transpose ? mid_gemv<T, true, 0>(M, x, T(0), d, lane) : mid_gemv<T, false, 0>(M, x, T(0), d, lane);
+  }
+  if (sub) {
+    const T* sp = sub + cm * (Tn - 1) * dd;
+    if ((symmetric || !transpose) && k > 0) {  // + A_{k-1} x_{k-1}
+      mid_load<T>(M, sp + (k - 1) * dd, d, lane);
+      x = lane < d ? xp[lane - d] : T(0);
+      y = mid_gemv<T, false, 1>(M, x, y, d, lane);
+    }
+    if ((symmetric || transpose) && k + 1 < Tn) {  // + A_k^T x_{k+1}
+      mid_load<T>(M, sp + k * dd, d, lane);
+      x = lane < d ? xp[lane + d] : T(0);
+      y = mid_gemv<T, true, 1>(M, x, y, d, lane);
+    }
+  }
+  if (lane < d) out[(c * Tn + k) * d + lane] = y;
+}
+
+// ---- log_pdf (ssm_kernels.cuh::ssm_log_pdf_kernel): warp per trajectory, the factors summed in time order ---------
+template <typename T>
+__global__ void __launch_bounds__(32)
+mid_log_pdf_kernel(const T* __restrict__ mu0, const T* __restrict__ chol_p0, const T* __restrict__ a,
+                   const T* __restrict__ b, const T* __restrict__ chol_q, const T* __restrict__ states,
+                   T* __restrict__ out, int64_t n, int64_t Bm, int64_t Tn, int d) {
+  extern __shared__ __align__(16) unsigned char mid_raw[];
+  const MidSmem<T> sm{reinterpret_cast<T*>(mid_raw)};
+  T *L = sm.mat(0), *A = sm.mat(1);
+  T* rinv = sm.vec(2, 0);
+  const int lane = threadIdx.x;
+  const int64_t c = blockIdx.x, cm = c % Bm;
+  const int dd = d * d;
+  const T* xp = states + c * Tn * d;
+  T acc = T(0);
+  T xprev = T(0);
+  for (int64_t k = 0; k < Tn; ++k) {
+    const T xk = lane < d ? xp[k * d + lane] : T(0);
+    T r;
+    if (k == 0) {
+      r = xk - (lane < d ? mu0[cm * d + lane] : T(0));
+      mid_load<T>(L, chol_p0 + cm * dd, d, lane);
+    } else {
+      mid_load<T>(A, a + (cm * (Tn - 1) + k - 1) * dd, d, lane);
+      r = xk - (lane < d ? b[(cm * (Tn - 1) + k - 1) * d + lane] : T(0));
+      r = mid_gemv<T, false, -1>(A, xprev, r, d, lane);
+      mid_load<T>(L, chol_q + (cm * (Tn - 1) + k - 1) * dd, d, lane);
+    }
+    mid_diag_rcp<T>(L, rinv, d, lane);
+    r = mid_trsv_l<T>(L, rinv, r, d, lane);
+    const T q = mid_dot<T>(r, r, T(0), d);
+    T dprod = T(1);
+    for (int i = 0; i < d; ++i) dprod *= L[i * MID_LD + i];
+    acc += T(-0.5) * q - Num<T>::log(Num<T>::abs(dprod)) - T(0.5 * 1.8378770664093454836) * T(d);
+    xprev = xk;
+  }
+  if (lane == 0) out[c] = acc;
 }
 
 }  // namespace mf

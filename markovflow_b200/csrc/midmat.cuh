@@ -157,6 +157,27 @@ __device__ __forceinline__ void mid_trsm_lt(const T* __restrict__ l, const T* __
   }
   __syncwarp();
 }
+// B <- B L^{-1}: lane = row of B, backward over the columns
+template <typename T>
+__device__ __forceinline__ void mid_trsm_right_l(T* __restrict__ b, const T* __restrict__ l, const T* __restrict__ rinv,
+                                                 int d, int lane) {
+  __syncwarp();
+  if (lane < d) {
+    for (int j = d - 1; j >= 0; --j) {
+      T v = b[lane * MID_LD + j];
+      for (int q = j + 1; q < d; ++q) v = Num<T>::fma(-b[lane * MID_LD + q], l[q * MID_LD + j], v);
+      b[lane * MID_LD + j] = v * rinv[j];
+    }
+  }
+  __syncwarp();
+}
+// sum_q x_q y_q, accumulated in ascending order on top of `init` (identical on every lane)
+template <typename T>
+__device__ __forceinline__ T mid_dot(T x, T y, T init, int d) {
+  T s = init;
+  for (int q = 0; q < d; ++q) s = Num<T>::fma(__shfl_sync(0xffffffffu, x, q), __shfl_sync(0xffffffffu, y, q), s);
+  return s;
+}
 // x <- L^{-1} x, x <- L^{-T} x for a vector held one element per lane
 template <typename T>
 __device__ __forceinline__ T mid_trsv_l(const T* __restrict__ l, const T* __restrict__ rinv, T x, int d, int lane) {

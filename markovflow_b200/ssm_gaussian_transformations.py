@@ -65,15 +65,20 @@ def _ssm_outputs(entry: str, lin, diag, sub, *extra) -> Tuple[Tensor, Tensor, Te
 
 @boundary
 def _ssm_outputs_diff(entry: str, lin, diag, sub, batch, t, d, *extra):
-    """The same outputs with reverse mode (autograd.py): the CUDA kernel runs forward, the torch restatement
-    of the per-step map is differentiated backward.  ``naturals_to_ssm_params`` (a backward recursion) has no
-    adjoint sweep yet."""
-    from .autograd import _RecomputeFn, expectations_to_ssm_torch
+    """The same outputs with reverse mode (autograd.py).  ``expectations_to_ssm_params`` (a per-step map): the CUDA
+    kernel runs forward, the torch restatement of the map is differentiated backward.  ``naturals_to_ssm_params``
+    (a backward recursion): the block Cholesky + forward substitution of the time-reversed precision on the CUDA
+    sweeps and their adjoint sweeps (``autograd.naturals_to_ssm_diff``)."""
+    from .autograd import _RecomputeFn, expectations_to_ssm_torch, naturals_to_ssm_diff
 
+    if entry == "mf_nat_to_ssm":
+        a, off, chol = naturals_to_ssm_diff(lin, diag, sub, smoothing=bool(extra[0]))
+        a = a.reshape(batch + (t - 1, d, d))
+        off = off.reshape(batch + (t, d))
+        chol = chol.reshape(batch + (t, d, d))
+        return a, off[..., 1:, :], chol[..., 0, :, :], chol[..., 1:, :, :], off[..., 0, :]
     if entry != "mf_expectations_to_ssm":
-        raise NotImplementedError(
-            "naturals_to_ssm_params has no reverse mode yet; expectations_to_ssm_params, ssm_to_expectations, "
-            "ssm_to_naturals, the marginals, kl_divergence and the Kalman log-likelihood are differentiable")
+        raise NotImplementedError(f"{entry} has no reverse mode")
 
     def cuda_fn(lin_, diag_, sub_):
         a_ = torch.empty_like(sub_)

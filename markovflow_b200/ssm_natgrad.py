@@ -11,8 +11,9 @@ One step (``_natgrad_step``, reference :121-218):
 4. ``ssm <- naturals_to_ssm_params(theta_new)``, written in place into the model's parameters.
 
 Every piece runs on the CUDA operators: the forward sweeps, the adjoint sweeps behind ``autograd.py`` for (1)-(2),
-and the backward ``U D U^T`` sweep of ``mf_nat_to_ssm`` for (4).  The momentum variant of the reference (:173-203)
-needs ``dL/d(theta)`` through ``naturals_to_ssm_params``, whose adjoint sweep does not exist yet.
+and the backward ``U D U^T`` sweep of ``mf_nat_to_ssm`` for (4).  The momentum variant (:173-203, Adam-style
+moving averages of the natural gradient and of its norm ``<dL/d(eta), dL/d(theta)>``) takes ``dL/d(theta)``
+through the differentiable ``naturals_to_ssm_params`` (``autograd.naturals_to_ssm_diff``).
 """
 from __future__ import annotations
 
@@ -35,11 +36,13 @@ class SSMNaturalGradient:
 
     def __init__(self, gamma: float = 0.1, momentum: bool = False, beta1: float = 0.9, beta2: float = 0.99,
                  epsilon: float = 1e-8, name: str = "SSMNaturalGradient") -> None:
-        if momentum:
-            raise NotImplementedError(
-                "momentum needs dL/d(theta) through naturals_to_ssm_params (ssm_natgrad.py:173-176), whose "
-                "adjoint sweep is not built; momentum=False is the reference's own integration-test setting")
         self.gamma, self._name = float(gamma), name
+        self._momentum = bool(momentum)
+        self._beta1, self._beta2, self._epsilon = float(beta1), float(beta2), float(epsilon)
+        self._ms = None      # moving averages of dL/d(eta) (reference :68-71, 104-108)
+        self._v = 0.0        # moving average of the natural-gradient norm
+        self._step_counter = 1
+        self._effective_lr = None
 
     def minimize(self, loss_fn: Callable[[], torch.Tensor], ssm: StateSpaceModel) -> None:
         self._natgrad_step(loss_fn, ssm)
@@ -59,9 +62,31 @@ class SSMNaturalGradient:
             etas = [e.detach().requires_grad_(True) for e in ssm_to_expectations(ssm)]
             ssm_params = expectations_to_ssm_params(*etas)
             dl_detas = torch.autograd.grad(ssm_params, etas, grad_outputs=dl_dssm, allow_unused=True)
+            dl_detas = [torch.zeros_like(e) if g is None else g for e, g in zip(etas, dl_detas)]
+            dl_dthetas = None
+            if self._momentum:  # dL/d(theta) by the chain rule through naturals_to_ssm_params (:173-176, 190)
+                thetas_g = [th.detach().requires_grad_(True) for th in ssm_to_naturals(_detached(ssm))]
+                ssm_params_2 = naturals_to_ssm_params(*thetas_g)
+                dl_dthetas = torch.autograd.grad(ssm_params_2, thetas_g, grad_outputs=dl_dssm, allow_unused=True)
+                dl_dthetas = [torch.zeros_like(t) if g is None else g for t, g in zip(thetas_g, dl_dthetas)]
         with torch.no_grad():
             thetas = ssm_to_naturals(_detached(ssm))
-            thetas_new = [th - self.gamma * g for th, g in zip(thetas, dl_detas)]
+            if self._momentum:
+                if self._ms is None:
+                    self._ms = [torch.zeros_like(g) for g in dl_detas]
+                lr = (self.gamma * (1.0 - self._beta2 ** self._step_counter) ** 0.5
+                      / (1.0 - self._beta1 ** self._step_counter))
+                ms_new = [m * self._beta1 + (1.0 - self._beta1) * g for m, g in zip(self._ms, dl_detas)]
+                comps = [torch.sum(g * gt) for g, gt in zip(dl_detas, dl_dthetas)]
+                comps[-1] = comps[-1] * 2.0  # the sub-diagonal blocks appear twice in the symmetric precision
+                v_new = self._v * self._beta2 + (1.0 - self._beta2) * float(sum(comps))
+                denom = v_new ** 0.5 + self._epsilon
+                thetas_new = [th - lr * m / denom for th, m in zip(thetas, ms_new)]
+                self._ms, self._v = ms_new, v_new
+                self._step_counter += 1
+                self._effective_lr = lr / denom
+            else:
+                thetas_new = [th - self.gamma * g for th, g in zip(thetas, dl_detas)]
             new = naturals_to_ssm_params(*thetas_new)
             for p, v in zip(params, new):
                 p.copy_(v)

@@ -205,9 +205,7 @@ class StateSpaceModel(GaussMarkovDistribution):
     def _affine(self, eps: Optional[torch.Tensor], sample_shape) -> torch.Tensor:
         mu0, l0, a, b, lq, bsz, t, d = self._flat()
         if eps is not None and needs_grad(mu0, l0, a, b, lq, eps):
-            raise NotImplementedError(
-                "StateSpaceModel.sample has no reverse mode yet (draw with torch.no_grad(), or detach the "
-                "parameters); marginals, log_pdf, kl_divergence and the Kalman log-likelihood are differentiable")
+            return self._affine_diff(eps, sample_shape)
         n = _prod(sample_shape) * bsz
         out = torch.empty(n, t, d, dtype=a.dtype, device=a.device)
         if eps is not None:
@@ -219,6 +217,24 @@ class StateSpaceModel(GaussMarkovDistribution):
             "mf_ssm_affine_scan",
         )
         return out.reshape(tuple(sample_shape) + tuple(self.batch_shape) + (t, d))
+
+    def _affine_diff(self, eps: torch.Tensor, sample_shape) -> torch.Tensor:
+        """Reparameterised trajectories with reverse mode (reference :298-324 under a gradient tape):
+        ``x = A_inv^-1 [mu0 + L0 e_0, b_k + Lq_k e_k]`` -- the right-hand side in torch ops, the unit-diagonal
+        block solve on the CUDA sweep with its adjoint sweep (``autograd.SolveFn``)."""
+        from .autograd import SolveFn
+
+        mu0, l0, a, b, lq, bsz, t, d = self._flat()
+        s = _prod(sample_shape)
+        e = eps.reshape(s, bsz, t, d)
+        first = mu0 + (torch.tril(l0) @ e[:, :, 0, :, None])[..., 0]
+        if t > 1:
+            rest = b + (torch.tril(lq) @ e[:, :, 1:, :, None])[..., 0]
+            rhs = torch.cat([first[:, :, None, :], rest], dim=2)
+        else:
+            rhs = first[:, :, None, :]
+        x = SolveFn.apply(None, -a if t > 1 else None, rhs.reshape(s * bsz, t, d).contiguous(), False)
+        return x.reshape(tuple(sample_shape) + tuple(self.batch_shape) + (t, d))
 
     @boundary
     def sample(self, sample_shape, generator: Optional[torch.Generator] = None,
@@ -241,8 +257,19 @@ class StateSpaceModel(GaussMarkovDistribution):
             return self._affine(eps, sample_shape)
         mu0, l0, a, b, lq, bsz, t, d = self._flat()
         if needs_grad(mu0, l0, a, b, lq):
-            raise NotImplementedError(
-                "StateSpaceModel.sample has no reverse mode yet (draw with torch.no_grad(), or detach the parameters)")
+            # reverse mode: the same Philox draws, written out once, then the differentiable affine solve
+            if seed is None:
+                seed = int(torch.randint(0, 2 ** 62, (), dtype=torch.int64).item())
+            return self._affine_diff(self.sample_epsilons(sample_shape, seed), sample_shape)
+        if d > 8:
+            # the in-kernel generator is built for blocks held in registers (D <= 8); above, the draws come from
+            # torch (seeded with `seed` when given) and go through the warp-per-trajectory affine scan
+            gen = None
+            if seed is not None:
+                gen = torch.Generator(device=a.device)
+                gen.manual_seed(int(seed))
+            eps = torch.randn(full, dtype=a.dtype, device=a.device, generator=gen)
+            return eps if eps.numel() == 0 else self._affine(eps, sample_shape)
         n = _prod(sample_shape) * bsz
         out = torch.empty(n, t, d, dtype=a.dtype, device=a.device)
         if n == 0:

@@ -318,3 +318,154 @@ def test_natgrad_gets_the_optimal_elbo_in_one_iteration():
     with torch.no_grad():
         qm, qc = q.marginals
     assert rel(qm, pm) < 1e-7 and rel(qc, pc) < 1e-7
+
+
+def _nat_to_ssm_torch_loop(th_lin, th_diag, th_sub):
+    """The backward U D U^T recursion of naturals_to_ssm_params, step by step in torch (dense autograd reference)."""
+    bsz, t, d = th_lin.shape
+    offs, chols, a_s = [None] * t, [None] * t, [None] * (t - 1)
+    z = c = None
+    for k in range(t - 1, -1, -1):
+        dk = -2.0 * th_diag[:, k]
+        dk = torch.tril(dk) + torch.tril(dk, -1).transpose(-1, -2)
+        th = th_lin[:, k]
+        if k + 1 < t:
+            a = torch.cholesky_solve(th_sub[:, k], c)
+            dk = dk - th_sub[:, k].transpose(-1, -2) @ a
+            dk = torch.tril(dk) + torch.tril(dk, -1).transpose(-1, -2)
+            th = th + (a.transpose(-1, -2) @ z[..., None])[..., 0]
+            a_s[k] = a
+        z = th
+        c = torch.linalg.cholesky(dk)
+        offs[k] = torch.cholesky_solve(z[..., None], c)[..., 0]
+        q = torch.cholesky_inverse(c)
+        chols[k] = torch.linalg.cholesky(torch.tril(q) + torch.tril(q, -1).transpose(-1, -2))
+    return torch.stack(a_s, 1), torch.stack(offs, 1), torch.stack(chols, 1)
+
+
+@pytest.mark.parametrize("smoothing", [True, False])
+@pytest.mark.parametrize("b,t,d", [(2, 6, 1), (3, 5, 2), (2, 7, 3), (1, 4, 5)])
+def test_naturals_to_ssm_params_reverse_mode(b, t, d, smoothing):
+    """naturals_to_ssm_params under autograd (ssm_natgrad.py:173-176 needs it): values equal the forward kernel,
+    gradients equal torch's reverse mode through the step-by-step recursion."""
+    import markovflow_b200 as mf
+    from oracle import np_oracle as O
+
+    arrays = random_ssm_arrays((b,), t - 1, d, scale_a=0.6 / np.sqrt(d))
+    to_nat = O.ssm_to_naturals if smoothing else O.ssm_to_naturals_no_smoothing
+    th_np = to_nat(O.SSM(*arrays))
+    fn = mf.naturals_to_ssm_params if smoothing else mf.naturals_to_ssm_params_no_smoothing
+    th1 = [tt(x, True) for x in th_np]
+    th2 = [tt(x, True) for x in th_np]
+    got = fn(*th1)  # (As, offsets, chol_P0, chol_Qs, mu0)
+    with torch.no_grad():
+        fwd = fn(*(x.detach() for x in th1))
+    for g, f in zip(got, fwd):
+        assert rel(g, f) < 1e-11
+    if smoothing:
+        a, off, chol = _nat_to_ssm_torch_loop(*th2)
+    else:
+        dk = -2.0 * th2[1]
+        dk = torch.tril(dk) + torch.tril(dk, -1).transpose(-1, -2)
+        c = torch.linalg.cholesky(dk)
+        off = torch.cholesky_solve(th2[0][..., None], c)[..., 0]
+        a = torch.cholesky_solve(th2[2], c[:, 1:])
+        q = torch.cholesky_inverse(c)
+        chol = torch.linalg.cholesky(torch.tril(q) + torch.tril(q, -1).transpose(-1, -2))
+    want = (a, off[:, 1:], chol[:, 0], chol[:, 1:], off[:, 0])
+    rng = np.random.default_rng(b + t + d)
+    ws = [tt(rng.standard_normal(tuple(o.shape))) for o in got]
+    ws[2], ws[3] = torch.tril(ws[2]), torch.tril(ws[3])
+    sum(((w * o).sum() for w, o in zip(ws, got))).backward()
+    sum(((w * o).sum() for w, o in zip(ws, want))).backward()
+    for x1, x2, name in zip(th1, th2, ("theta_lin", "theta_diag", "theta_sub")):
+        g1, g2 = x1.grad, x2.grad
+        if name == "theta_diag":  # symmetric parameter: compare the symmetrised gradients
+            g1, g2 = g1 + g1.transpose(-1, -2), g2 + g2.transpose(-1, -2)
+        assert rel(g1, g2) < GTOL, name
+
+
+@pytest.mark.parametrize("b,t,d", [(2, 6, 1), (3, 5, 2), (2, 4, 4)])
+def test_sample_reverse_mode(b, t, d):
+    """Reparameterised samples are differentiable in the model's parameters and in the draws: gradients equal
+    torch's reverse mode through the step-by-step affine recursion; sample(seed=...) under grad returns the
+    same trajectories as without."""
+    import markovflow_b200 as mf
+
+    arrays = random_ssm_arrays((b,), t - 1, d, scale_a=0.6 / np.sqrt(d))  # mu0, chol_p0, a, b, chol_q
+    rng = np.random.default_rng(3 * b + t + d)
+    eps_np = rng.standard_normal((4, b, t, d))
+    p1 = [tt(x, True) for x in arrays]
+    p2 = [tt(x, True) for x in arrays]
+    e1, e2 = tt(eps_np, True), tt(eps_np, True)
+    x1 = mf.StateSpaceModel(*p1).sample_from_epsilons(e1)
+    mu0, l0, a, bb, lq = p2
+    xs = [mu0 + (torch.tril(l0) @ e2[:, :, 0, :, None])[..., 0]]
+    for k in range(1, t):
+        xs.append((a[:, k - 1] @ xs[-1][..., None])[..., 0] + bb[:, k - 1]
+                  + (torch.tril(lq[:, k - 1]) @ e2[:, :, k, :, None])[..., 0])
+    x2 = torch.stack(xs, dim=2)
+    assert rel(x1, x2) < 1e-12
+    w = tt(rng.standard_normal(tuple(x1.shape)))
+    (w * x1).sum().backward()
+    (w * x2).sum().backward()
+    for q1, q2 in zip(p1 + [e1], p2 + [e2]):
+        assert rel(q1.grad, q2.grad) < GTOL
+    ssm = mf.StateSpaceModel(*(tt(x, True) for x in arrays))
+    s_grad = ssm.sample((3,), seed=11)
+    with torch.no_grad():
+        s_plain = mf.StateSpaceModel(*(tt(x) for x in arrays)).sample((3,), seed=11)
+    assert s_grad.requires_grad and rel(s_grad, s_plain) < 1e-12
+
+
+def test_natgrad_with_momentum_follows_the_reference_update():
+    """ssm_natgrad.py:173-203: Adam-style step in the naturals.  One step is compared with the update computed
+    from the formulas with dense-autograd gradients; a few steps on a Gaussian-likelihood ELBO increase it."""
+    import markovflow_b200 as mf
+
+    rng = np.random.default_rng(9)
+    bsz, t = 2, 8
+    tp = tt(np.linspace(0.0, 1.0, t))
+    noise_var = 0.05
+    prior_arrays = _matern32_ssm_torch(tt(0.3), tt(0.5), tp)
+    prior = mf.StateSpaceModel(*(x.detach().expand((bsz,) + tuple(x.shape)).contiguous() for x in prior_arrays))
+    y = tt(rng.standard_normal((bsz, t, 1)))
+    h = torch.zeros(t, 1, 2, dtype=torch.float64, device=dev())
+    h[..., 0] = 1.0
+    em = mf.EmissionModel(h)
+    q = prior.create_trainable_copy()
+
+    def elbo():
+        mean, cov = q.marginals
+        f_mean, f_var = em.project_state_marginals_to_f(mean, cov)
+        ve = -0.5 * math.log(2 * math.pi * noise_var) - 0.5 * ((y - f_mean) ** 2 + f_var) / noise_var
+        return ve.sum((-1, -2)) - q.kl_divergence(prior)
+
+    # expected first step, from the formulas
+    gamma, b1, b2, eps_ = 0.1, 0.9, 0.99, 1e-8
+    loss = -elbo().sum()
+    params = q.trainable_variables
+    dl = list(torch.autograd.grad(loss, params))
+    dl[2], dl[3] = torch.tril(dl[2]), torch.tril(dl[3])
+    det = lambda s: mf.StateSpaceModel(s._mu_0.detach(), s._chol_P_0.detach(), s._A_s.detach(), s._b_s.detach(),
+                                       s._chol_Q_s.detach())
+    etas = [e.detach().requires_grad_(True) for e in mf.ssm_to_expectations(det(q))]
+    g_eta = torch.autograd.grad(mf.expectations_to_ssm_params(*etas), etas, grad_outputs=dl)
+    thetas = [th.detach().requires_grad_(True) for th in mf.ssm_to_naturals(det(q))]
+    a_, off_, chol_ = _nat_to_ssm_torch_loop(*thetas)
+    g_theta = torch.autograd.grad((a_, off_[:, 1:], chol_[:, 0], chol_[:, 1:], off_[:, 0]), thetas, grad_outputs=dl)
+    lr = gamma * math.sqrt(1 - b2) / (1 - b1)
+    comps = [float((g * gt).sum()) for g, gt in zip(g_eta, g_theta)]
+    comps[-1] *= 2.0
+    v = (1 - b2) * sum(comps)
+    theta_new = [th.detach() - lr * (1 - b1) * g / (math.sqrt(v) + eps_) for th, g in zip(thetas, g_eta)]
+    want = mf.naturals_to_ssm_params(*theta_new)
+
+    opt = mf.SSMNaturalGradient(gamma=gamma, momentum=True, beta1=b1, beta2=b2, epsilon=eps_)
+    before = float(elbo().sum())
+    opt.minimize(lambda: -elbo().sum(), q)
+    for p, w in zip(q.trainable_variables, want):
+        assert rel(p.detach(), w) < 1e-8
+    for _ in range(5):
+        opt.minimize(lambda: -elbo().sum(), q)
+    assert float(elbo().sum()) > before

@@ -152,3 +152,126 @@ def test_natural_transformations_no_smoothing_d30_t1001(sum_of_matern52_ssm):
 
     ssm, params = sum_of_matern52_ssm
     _round_trip(params, mf.naturals_to_ssm_params_no_smoothing(*mf.ssm_to_naturals_no_smoothing(ssm)))
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("b,n,d", [(3, 6, 9), (2, 5, 17), (2, 4, 32)])
+def test_block_operators_above_eight_dimensions(b, n, d, dtype):
+    """block_diagonal_of_inverse / upper_diagonal_lower / _build_precision / marginal_means / sample_from_epsilons
+    (block_tri_diag.py:331,438-545; state_space_model.py:231-251,298-324,431-483) on the warp-per-chain kernels."""
+    import markovflow_b200 as mf
+
+    arrays = case(b, n, d, dtype, 300 * d + n)
+    ref = O.SSM(*arrays)
+    ssm = mf.StateSpaceModel(*(tt(a, dtype) for a in arrays))
+    tol = TOL[dtype]
+    hi = O.SSM(*ld(*arrays))
+    lo = O.SSM(*(a.astype(np.float32) for a in arrays))
+
+    def kw(fn):
+        return dict(truth=lambda: fn(hi)) if dtype == torch.float64 else dict(peer=lambda: fn(lo))
+
+    prec = ssm.precision
+    pd_, ps_ = O.ssm_build_precision(ref)
+    assert_parity(npy(prec.block_diagonal), pd_, tol, what=f"precision diag D={d}",
+                  **kw(lambda s: O.ssm_build_precision(s)[0]))
+    assert_parity(npy(prec.block_sub_diagonal), ps_, tol, what=f"precision sub D={d}",
+                  **kw(lambda s: O.ssm_build_precision(s)[1]))
+    assert_parity(npy(ssm.marginal_means), O.ssm_marginal_means(ref), tol, what=f"marginal means D={d}",
+                  **kw(O.ssm_marginal_means))
+    # inverse subset of the precision's Cholesky factor = marginal covariances
+    chol = prec.cholesky
+    want_cov = O.ssm_marginal_covariances(ref)
+    got_cov = chol.block_diagonal_of_inverse()
+    assert_parity(npy(got_cov), want_cov, max(tol, 1e-9) if dtype == torch.float64 else tol,
+                  what=f"block_diagonal_of_inverse D={d}", **kw(O.ssm_marginal_covariances))
+    # U D U^T of the precision: U^T = A^{-1} has -A_k below the diagonal ... checked through the identity
+    # K = U D U^T on dense matrices
+    u, chol_d = prec.upper_diagonal_lower()
+    dense_k = npy(prec.to_dense())
+    ut = npy(u.to_dense())
+    cd = npy(chol_d.to_dense())
+    rebuilt = np.swapaxes(ut, -1, -2) @ (cd @ np.swapaxes(cd, -1, -2)) @ ut
+    scale = np.abs(dense_k).max()
+    assert np.abs(rebuilt - dense_k).max() <= (1e-10 if dtype == torch.float64 else 2e-4) * scale
+    # sampling from given draws
+    eps = np.random.default_rng(d).standard_normal((2, b, n + 1, d))
+    if dtype == torch.float32:
+        eps = eps.astype(np.float32).astype(np.float64)
+    got = ssm.sample_from_epsilons(tt(eps, dtype))
+    assert_parity(npy(got), O.ssm_sample_from_epsilons(ref, eps), tol, what=f"sample D={d}",
+                  **kw(lambda s: O.ssm_sample_from_epsilons(s, eps.astype(s.a_s.dtype))))
+    assert tuple(ssm.sample((3,), seed=5).shape) == (3, b, n + 1, d)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("b,n,d,m", [(3, 8, 9, 1), (2, 6, 17, 2), (1, 5, 30, 1)])
+def test_kalman_log_likelihood_above_eight_dimensions(b, n, d, m, dtype):
+    import markovflow_b200 as mf
+
+    rng = np.random.default_rng(10 * d + m)
+    arrays = case(b, n, d, dtype, 400 * d + n)
+    h = rng.standard_normal((n + 1, m, d))
+    y = rng.standard_normal((b, n + 1, m))
+    lr = np.tril(rng.standard_normal((m, m))) * 0.3 + np.eye(m)
+    if dtype == torch.float32:
+        h, y, lr = f32r((h, y, lr))
+    want = O.kalman_log_likelihood(O.SSM(*arrays), h, y, O._r_inv_from_chol(lr), per_chain=True)
+    ssm = mf.StateSpaceModel(*(tt(a, dtype) for a in arrays))
+    got = mf.kalman_log_likelihood(ssm, tt(h, dtype), tt(y, dtype), tt(lr, dtype))
+    kw = (dict(truth=lambda: O.kalman_log_likelihood(O.SSM(*ld(*arrays)), *ld(h, y), O._r_inv_from_chol(ld(lr)[0]),
+                                                     per_chain=True))
+          if dtype == torch.float64 else
+          dict(peer=lambda: O.kalman_log_likelihood(O.SSM(*(a.astype(np.float32) for a in arrays)),
+                                                    h.astype(np.float32), y.astype(np.float32),
+                                                    O._r_inv_from_chol(lr.astype(np.float32)), per_chain=True)))
+    assert_parity(npy(got), want, TOL[dtype], what=f"Kalman log-likelihood D={d} m={m}", **kw)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("b,n,d", [(2, 6, 9), (2, 5, 17), (1, 4, 32)])
+def test_log_pdf_dense_mult_and_posterior_above_eight_dimensions(b, n, d, dtype):
+    """log_pdf (state_space_model.py:485-526), dense_mult (block_tri_diag.py:189) and the posterior state-space
+    model of the Kalman filter (kalman_filter.py:109-182: U D U^T + dense_mult + solves + block maps)."""
+    import markovflow_b200 as mf
+
+    rng = np.random.default_rng(d)
+    arrays = case(b, n, d, dtype, 500 * d + n)
+    ref = O.SSM(*arrays)
+    ssm = mf.StateSpaceModel(*(tt(a, dtype) for a in arrays))
+    tol = TOL[dtype]
+    hi = O.SSM(*ld(*arrays))
+    lo = O.SSM(*(a.astype(np.float32) for a in arrays))
+    states = rng.standard_normal((3, b, n + 1, d))
+    if dtype == torch.float32:
+        states = states.astype(np.float32).astype(np.float64)
+    kw = (dict(truth=lambda: O.ssm_log_pdf(hi, ld(states)[0])) if dtype == torch.float64 else
+          dict(peer=lambda: O.ssm_log_pdf(lo, states.astype(np.float32))))
+    assert_parity(npy(ssm.log_pdf(tt(states, dtype))), O.ssm_log_pdf(ref, states), tol, what=f"log_pdf D={d}", **kw)
+    # dense_mult of the precision with a vector = K^{-1} x on dense matrices
+    prec = ssm.precision
+    x = rng.standard_normal((b, n + 1, d))
+    if dtype == torch.float32:
+        x = x.astype(np.float32).astype(np.float64)
+    dense = npy(prec.to_dense())
+    want = np.einsum("bij,bj->bi", dense, x.reshape(b, -1)).reshape(b, n + 1, d)
+    got = npy(prec.dense_mult(tt(x, dtype)))
+    assert np.abs(got - want).max() <= (1e-10 if dtype == torch.float64 else 1e-4) * np.abs(want).max()
+    # posterior SSM: marginal means / covariances equal the oracle's smoothed moments
+    m = 1
+    h = rng.standard_normal((n + 1, m, d))
+    y = rng.standard_normal((b, n + 1, m))
+    lr = np.array([[0.7]])
+    if dtype == torch.float32:
+        h, y = f32r((h, y))
+    kf = mf.KalmanFilter(ssm, mf.EmissionModel(tt(h, dtype)), tt(y, dtype), tt(lr, dtype))
+    post = kf.posterior_state_space_model()
+    o_post = O.kalman_posterior_ssm(ref, h, y, O._r_inv_from_chol(lr))
+    ptol = 1e-9 if dtype == torch.float64 else 1e-3
+    mu, cov = post.marginals
+    assert_parity(npy(mu), O.ssm_marginal_means(o_post), ptol, what=f"posterior means D={d}",
+                  **(dict(truth=lambda: O.ssm_marginal_means(O.kalman_posterior_ssm(hi, *ld(h, y), O._r_inv_from_chol(ld(lr)[0]))))
+                     if dtype == torch.float64 else {}))
+    assert_parity(npy(cov), O.ssm_marginal_covariances(o_post), ptol, what=f"posterior covariances D={d}",
+                  **(dict(truth=lambda: O.ssm_marginal_covariances(O.kalman_posterior_ssm(hi, *ld(h, y), O._r_inv_from_chol(ld(lr)[0]))))
+                     if dtype == torch.float64 else {}))
