@@ -1331,7 +1331,8 @@ template <> struct PrefersShortTiles<NatToSsmCore<double, 2>> { static constexpr
 // Cores that describe their streams for the tensor-map engine (sweep_tm.cuh) try it first; it declines
 // (cudaErrorNotSupported) geometries it cannot map and the 1-D engine below takes over.  Records of up to
 // 4 elements (D <= 2) only: those are the sweeps bound by bulk-copy issue.  Knob 13 = 1: off;
-// knob 14: tile geometry (0 default, 1: K=8, 2: K=4 with one output stage, 3: K=2).
+// knob 14: tile geometry (0 default: K=4 in float64, K=8 in float32; 1: K=8, 2: K=4 with one output stage,
+// 3: K=2, 4: K=4).
 template <class Core, class = void>
 struct HasTm : std::false_type {};
 template <class Core>
@@ -1360,6 +1361,12 @@ struct TmAuto {
       }
       if constexpr (fits<2, 2, 2>()) {
         if (g == 3) return launch_chain_sweep_tm<Core, 64, 2, 2, 2, 4>(prm, s);
+      }
+      if (g == 4) return launch_chain_sweep_tm<Core, 64, 4, 2, 2, 4>(prm, s);
+      // float32 rows are half as wide: 8-step tiles keep two CTAs per SM and halve the tile overheads
+      // (config 5, naturals -> SSM: 0.51 -> 0.41 ms); float64 loses a resident CTA to them (0.67 -> 0.85 ms)
+      if constexpr (sizeof(typename Core::T) == 4 && fits<8, 2, 2>()) {
+        if (g == 0) return launch_chain_sweep_tm<Core, 64, 8, 2, 2, 4>(prm, s);
       }
       return launch_chain_sweep_tm<Core, 64, 4, 2, 2, 4>(prm, s);
     } else {
