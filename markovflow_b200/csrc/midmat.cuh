@@ -3,7 +3,8 @@
 //
 // A matrix is stored row-major with leading dimension MID_LD = 33 elements (odd: lanes walking a column hit
 // different banks).  One WARP owns the matrices it works on; every primitive is called by all 32 lanes and
-// ends with __syncwarp() so that the next primitive may read what this one wrote.  Work split: lane = row
+// starts and ends with __syncwarp(): it may overwrite what earlier primitives read and the next one may read what
+// it wrote.  Work split: lane = row
 // (products, factorisation) or lane = column (triangular solves of matrices: the columns are independent, so
 // a solve needs no synchronisation inside).  The operation ORDER inside every dot product is that of the
 // one-thread-per-chain primitives of smallmat.cuh (ascending index, fused multiply-add), so both paths
@@ -22,6 +23,7 @@ __device__ __forceinline__ T& mid_at(T* m, int i, int j) { return m[i * MID_LD +
 // global (row-major d x d, contiguous) -> shared
 template <typename T>
 __device__ __forceinline__ void mid_load(T* __restrict__ m, const T* __restrict__ g, int d, int lane) {
+  __syncwarp();  // earlier reads of the slot (e.g. by a vector solve, which ends on a shuffle) are done
   for (int idx = lane; idx < d * d; idx += 32) m[(idx / d) * MID_LD + (idx % d)] = g[idx];
   __syncwarp();
 }
