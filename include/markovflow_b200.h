@@ -43,7 +43,7 @@ extern "C" {
 #define MF_BIG_D_MAX 32  /* warp-per-chain kernels (blocks in shared memory / spread over lanes): mf_btd_cholesky,
                           * mf_btd_solve, mf_btd_inverse_subset, mf_btd_upper_diagonal_lower, mf_btd_dense_mult,
                           * mf_btd_abs_log_det, mf_ssm_build_precision, mf_ssm_marginals, mf_ssm_affine_scan,
-                          * mf_ssm_log_pdf, mf_nat_to_ssm, mf_ssm_to_naturals, mf_ssm_to_expectations,
+                          * mf_ssm_log_pdf, mf_ssm_kl_divergence, mf_nat_to_ssm, mf_ssm_to_naturals, mf_ssm_to_expectations,
                           * mf_expectations_to_ssm, mf_block_cholesky_or_zero, mf_block_chol_of_inverse,
                           * mf_kalman_log_likelihood */
 

@@ -222,6 +222,19 @@ int mid_log_pdf(int dtype, const void* mu0, const void* chol_p0, const void* a, 
   });
 }
 
+int mid_kl_divergence(int dtype, const void* q_mu0, const void* q_chol_p0, const void* q_a, const void* q_b,
+                      const void* q_chol_q, const void* p_mu0, const void* p_chol_p0, const void* p_a,
+                      const void* p_b, const void* p_chol_q, void* out, int64_t B, int64_t T, int64_t D,
+                      cudaStream_t s) {
+  if (!mid_dim(D) || B > 0x7fffffffLL) return MF_ERR_UNSUPPORTED;
+  return dispatch_dtype(dtype, [&](auto tt) {
+    using Tp = typename decltype(tt)::type;
+    MF_MID_LAUNCH(mid_kl_kernel, B, 8, 1, (const Tp*)q_mu0, (const Tp*)q_chol_p0, (const Tp*)q_a, (const Tp*)q_b,
+                  (const Tp*)q_chol_q, (const Tp*)p_mu0, (const Tp*)p_chol_p0, (const Tp*)p_a, (const Tp*)p_b,
+                  (const Tp*)p_chol_q, (Tp*)out, B, T, (int)D);
+  });
+}
+
 #undef MF_MID_LAUNCH
 
 }  // namespace mf

@@ -148,6 +148,9 @@ int mf_ssm_kl_divergence(int dtype, const void* q_mu0, const void* q_chol_p0, co
   if (!q_mu0 || !q_chol_p0 || !p_mu0 || !p_chol_p0 || !out) return MF_ERR_BAD_ARG;
   if (T > 1 && (!q_a || !q_b || !q_chol_q || !p_a || !p_b || !p_chol_q)) return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (mid_dim(D))
+    return mid_kl_divergence(dtype, q_mu0, q_chol_p0, q_a, q_b, q_chol_q, p_mu0, p_chol_p0, p_a, p_b, p_chol_q, out, B,
+                             T, D, s);
   if (D <= kSsmSweepMaxD && T > 1 && tuning(4) != 1) {
     const int rc = ssm_sweep_kl(dtype, D, q_mu0, q_chol_p0, q_a, q_b, q_chol_q, p_mu0, p_chol_p0,
                                 p_a, p_b, p_chol_q, out, B, T, s);

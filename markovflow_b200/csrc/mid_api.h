@@ -46,4 +46,9 @@ int mid_dense_mult(int dtype, const void* diag, const void* sub, const void* rig
 int mid_log_pdf(int dtype, const void* mu0, const void* chol_p0, const void* a, const void* b, const void* chol_q,
                 const void* states, void* out, int64_t n, int64_t Bm, int64_t T, int64_t D, cudaStream_t s);
 
+int mid_kl_divergence(int dtype, const void* q_mu0, const void* q_chol_p0, const void* q_a, const void* q_b,
+                      const void* q_chol_q, const void* p_mu0, const void* p_chol_p0, const void* p_a,
+                      const void* p_b, const void* p_chol_q, void* out, int64_t B, int64_t T, int64_t D,
+                      cudaStream_t s);
+
 }  // namespace mf

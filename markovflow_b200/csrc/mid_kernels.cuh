@@ -615,4 +615,89 @@ mid_log_pdf_kernel(const T* __restrict__ mu0, const T* __restrict__ chol_p0, con
   if (lane == 0) out[c] = acc;
 }
 
+// ---- KL(q || p), chain-rule form (ssm_kernels.cuh::ssm_kl_kernel): warp per chain --------------------------------
+// sum of squares of the d x d entries of m, accumulated row by row (lane = row), then over the rows in order
+template <typename T>
+__device__ __forceinline__ T mid_sumsq(const T* __restrict__ m, int d, int lane, bool lower_only) {
+  __syncwarp();
+  T s = T(0);
+  if (lane < d)
+    for (int j = 0; j < (lower_only ? lane + 1 : d); ++j) s = Num<T>::fma(m[lane * MID_LD + j], m[lane * MID_LD + j], s);
+  T tot = T(0);
+  for (int q = 0; q < d; ++q) tot += __shfl_sync(0xffffffffu, s, q);
+  return tot;
+}
+
+// 0.5 [ |Lp^-1 Lq|_F^2 + tr(G P G^T) + |Lp^-1 dmean|^2 - d ],  G = Lp^-1 dA ; log-dets go to `ratio`
+template <typename T>
+__device__ __forceinline__ T mid_kl_term(const T* __restrict__ Lp, const T* __restrict__ Lq, T* __restrict__ dA,
+                                         T dmean, const T* __restrict__ P, T* __restrict__ W, T* __restrict__ GP,
+                                         T* __restrict__ rinv, LogProd<T>& ratio, int d, int lane) {
+  mid_diag_rcp<T>(Lp, rinv, d, lane);
+  __syncwarp();
+  if (lane < d)
+    for (int j = 0; j < d; ++j) W[lane * MID_LD + j] = j <= lane ? Lq[lane * MID_LD + j] : T(0);
+  mid_trsm_l<T>(Lp, rinv, W, d, lane);
+  T s = mid_sumsq<T>(W, d, lane, false);
+  const T e = mid_trsv_l<T>(Lp, rinv, dmean, d, lane);
+  s = mid_dot<T>(e, e, s, d);
+  if (dA) {
+    mid_trsm_l<T>(Lp, rinv, dA, d, lane);  // G
+    mid_gemm<T, false, false, 0>(GP, dA, P, d, lane);
+    __syncwarp();
+    T t = T(0);
+    if (lane < d)
+      for (int j = 0; j < d; ++j) t = Num<T>::fma(GP[lane * MID_LD + j], dA[lane * MID_LD + j], t);
+    for (int q = 0; q < d; ++q) s += __shfl_sync(0xffffffffu, t, q);
+  }
+  for (int i = 0; i < d; ++i) ratio.mul(Lp[i * MID_LD + i] * Num<T>::rcp(Lq[i * MID_LD + i]));
+  return T(0.5) * (s - T(d));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32)
+mid_kl_kernel(const T* __restrict__ q_mu0, const T* __restrict__ q_chol_p0, const T* __restrict__ q_a,
+              const T* __restrict__ q_b, const T* __restrict__ q_chol_q, const T* __restrict__ p_mu0,
+              const T* __restrict__ p_chol_p0, const T* __restrict__ p_a, const T* __restrict__ p_b,
+              const T* __restrict__ p_chol_q, T* __restrict__ out, int64_t B, int64_t Tn, int d) {
+  extern __shared__ __align__(16) unsigned char mid_raw[];
+  const MidSmem<T> sm{reinterpret_cast<T*>(mid_raw)};
+  constexpr int NM = 8;
+  T *P = sm.mat(0), *Lq = sm.mat(1), *Lp = sm.mat(2), *Aq = sm.mat(3), *dA = sm.mat(4), *W = sm.mat(5),
+    *GP = sm.mat(6), *AP = sm.mat(7);
+  T* rinv = sm.vec(NM, 0);
+  const int lane = threadIdx.x;
+  const int64_t c = blockIdx.x;
+  const int dd = d * d;
+  LogProd<T> ratio;
+  ratio.init();
+  T mu = lane < d ? q_mu0[c * d + lane] : T(0);
+  mid_load<T>(Lq, q_chol_p0 + c * dd, d, lane);
+  mid_load<T>(Lp, p_chol_p0 + c * dd, d, lane);
+  T dm = mu - (lane < d ? p_mu0[c * d + lane] : T(0));
+  T kl = mid_kl_term<T>(Lp, Lq, nullptr, dm, nullptr, W, GP, rinv, ratio, d, lane);
+  mid_gemm<T, false, true, 0>(P, Lq, Lq, d, lane);
+  const int64_t off = c * (Tn - 1);
+  for (int64_t k = 0; k + 1 < Tn; ++k) {
+    mid_load<T>(Aq, q_a + (off + k) * dd, d, lane);
+    mid_load<T>(dA, p_a + (off + k) * dd, d, lane);
+    mid_load<T>(Lq, q_chol_q + (off + k) * dd, d, lane);
+    mid_load<T>(Lp, p_chol_q + (off + k) * dd, d, lane);
+    const T bq = lane < d ? q_b[(off + k) * d + lane] : T(0);
+    const T bp = lane < d ? p_b[(off + k) * d + lane] : T(0);
+    __syncwarp();
+    if (lane < d)
+      for (int j = 0; j < d; ++j) dA[lane * MID_LD + j] = Aq[lane * MID_LD + j] - dA[lane * MID_LD + j];
+    dm = mid_gemv<T, false, 1>(dA, mu, bq - bp, d, lane);  // dA mu + db
+    kl += mid_kl_term<T>(Lp, Lq, dA, dm, P, W, GP, rinv, ratio, d, lane);
+    // advance q's marginal
+    mid_gemm<T, false, false, 0>(AP, Aq, P, d, lane);
+    mid_gemm<T, false, true, 0>(P, Lq, Lq, d, lane);
+    mid_gemm<T, false, true, 1>(P, AP, Aq, d, lane);
+    mid_mirror_lower<T>(P, d, lane);
+    mu = mid_gemv<T, false, 1>(Aq, mu, bq, d, lane);
+  }
+  if (lane == 0) out[c] = kl + ratio.log_abs();
+}
+
 }  // namespace mf

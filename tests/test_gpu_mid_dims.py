@@ -275,3 +275,22 @@ def test_log_pdf_dense_mult_and_posterior_above_eight_dimensions(b, n, d, dtype)
     assert_parity(npy(cov), O.ssm_marginal_covariances(o_post), ptol, what=f"posterior covariances D={d}",
                   **(dict(truth=lambda: O.ssm_marginal_covariances(O.kalman_posterior_ssm(hi, *ld(h, y), O._r_inv_from_chol(ld(lr)[0]))))
                      if dtype == torch.float64 else {}))
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("b,n,d", [(3, 6, 9), (2, 5, 17), (1, 4, 32)])
+def test_kl_divergence_above_eight_dimensions(b, n, d, dtype):
+    """kl_divergence (state_space_model.py:528-593) between two random models, chain-rule form on the warp-per-chain
+    kernel; KL(q || q) = 0."""
+    import markovflow_b200 as mf
+
+    qa = case(b, n, d, dtype, 600 * d + n)
+    pa = case(b, n, d, dtype, 700 * d + n)
+    q = mf.StateSpaceModel(*(tt(a, dtype) for a in qa))
+    p = mf.StateSpaceModel(*(tt(a, dtype) for a in pa))
+    want = O.ssm_kl_divergence(O.SSM(*qa), O.SSM(*pa))
+    kw = (dict(truth=lambda: O.ssm_kl_divergence(O.SSM(*ld(*qa)), O.SSM(*ld(*pa)))) if dtype == torch.float64 else
+          dict(peer=lambda: O.ssm_kl_divergence(O.SSM(*(a.astype(np.float32) for a in qa)),
+                                                O.SSM(*(a.astype(np.float32) for a in pa)))))
+    assert_parity(npy(q.kl_divergence(p)), want, TOL[dtype], what=f"KL D={d}", **kw)
+    assert float(q.kl_divergence(q).abs().max()) <= (1e-9 if dtype == torch.float64 else 1e-2)
