@@ -1363,6 +1363,8 @@ struct TmAuto {
         if (g == 3) return launch_chain_sweep_tm<Core, 64, 2, 2, 2, 4>(prm, s);
       }
       if (g == 4) return launch_chain_sweep_tm<Core, 64, 4, 2, 2, 4>(prm, s);
+      // (measured on config 5, float64: 32-row CTAs with 3 input stages 0.81 / 0.56 ms, with 8-step tiles
+      //  0.82 / 0.53 ms, with the default stages 0.68 / 0.52 ms against 0.66 / 0.53 ms for this default)
       // float32 rows are half as wide: 8-step tiles keep two CTAs per SM and halve the tile overheads
       // (config 5, naturals -> SSM: 0.51 -> 0.41 ms); float64 loses a resident CTA to them (0.67 -> 0.85 ms)
       if constexpr (sizeof(typename Core::T) == 4 && fits<8, 2, 2>()) {
