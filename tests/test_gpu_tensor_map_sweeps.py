@@ -208,3 +208,34 @@ def test_tensor_map_engine_declines_unaligned_views():
     assert n1 - n0 == 2 and n2 == n1
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+def test_tensor_map_engine_equals_the_1d_engine_on_random_geometries():
+    """Seeded random (chains, steps, segment length) triples, D = 2, float64: whatever geometry the launcher picks or
+    declines, both passes of naturals_to_ssm_params and of ssm_to_expectations return bit-identical results on the
+    two engines (same arithmetic, different data movement), and the tensor-map engine serves most of them."""
+    import markovflow_b200 as mf
+
+    rng = np.random.default_rng(2026)
+    served = 0
+    for case_id in range(24):
+        b = int(rng.integers(1, 40))
+        t = int(rng.integers(40, 1500))
+        seg = int(rng.integers(8, 64)) if case_id % 4 else 0
+        arrays, th_np = naturals_case(b, t, 2, torch.float64, 31 * case_id + 7)
+        th = tuple(tt(x) for x in th_np)
+        kw = dict(k3=seg) if seg else dict(k2=1)
+        with knobs(**kw):
+            n0 = tm_count()
+            got = mf.naturals_to_ssm_params(*th)
+            q = mf.StateSpaceModel(got[4], got[2], got[0], got[1], got[3])
+            exp = mf.ssm_to_expectations(q)
+            served += tm_count() - n0
+        with knobs(k13=1, **kw):
+            ref = mf.naturals_to_ssm_params(*th)
+            q1 = mf.StateSpaceModel(ref[4], ref[2], ref[0], ref[1], ref[3])
+            exp1 = mf.ssm_to_expectations(q1)
+        for g, r in zip(list(got) + list(exp), list(ref) + list(exp1)):
+            assert torch.equal(g, r), (case_id, b, t, seg)
+        check_nat(got, th_np, torch.float64, f"random geometry {case_id}: b={b} t={t} seg={seg}")
+    assert served >= 24  # at least a quarter of the 96 sweeps ran on tensor maps
