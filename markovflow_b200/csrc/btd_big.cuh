@@ -131,7 +131,7 @@ btd_chol_big_kernel(const T* __restrict__ diag, const T* __restrict__ sub,
     for (int j = 0; j < D; ++j) {
       const T piv = __shfl_sync(0xffffffffu, S[j], j);
       if (!(piv > T(0)) && fail == 0) fail = (int32_t)(k + 1);
-      const T rinv = Num<T>::rsqrt(piv);
+      const T rinv = Num<T>::rsqrt_seq(piv);
       det.mul(piv);
       const T lij = S[j] * rinv;  // L_ij (i >= j); lane j: sqrt(piv)
       const T lsij = A[j] * rinv;

@@ -88,7 +88,7 @@ __device__ __forceinline__ bool big2_step(Big2Rows<T, D>& R, T* col, int h, T* o
     T* cl = col + (j & 1) * 32;  // [0,16): column j of L, [16,32): column j of Ls
     const T piv = __shfl_sync(0xffffffffu, R.S[j], j, 16);
     ok = ok && (piv > T(0));
-    const T rinv = Num<T>::rsqrt(piv);
+    const T rinv = Num<T>::rsqrt_seq(piv);
     if (DET) det->mul(piv);
     const T lij = R.S[j] * rinv, lsij = R.A[j] * rinv;
     const T xj = __shfl_sync(0xffffffffu, R.r, j, 16) * rinv;
@@ -147,7 +147,7 @@ __device__ __forceinline__ bool big2_step(Big2Rows<T, D>& R, T* col, int h, T* o
     T* cl = col + (DM & 1) * 32;
     const T piv = R.sbb;
     ok = ok && (piv > T(0));
-    const T rinv = Num<T>::rsqrt(piv);
+    const T rinv = Num<T>::rsqrt_seq(piv);
     if (DET) det->mul(piv);
     const T ls = R.A[16] * rinv;  // Ls[h][16]
     R.abb = R.abb * rinv;         // Ls[16][16]
@@ -487,7 +487,7 @@ big2_element_kernel(const T* __restrict__ diag, const T* __restrict__ sub, const
     for (int j = 0; j < DM; ++j) {
       const T piv = __shfl_sync(0xffffffffu, S[j], j, 16);
       ok = ok && (piv > T(0));
-      const T rinv = Num<T>::rsqrt(piv);
+      const T rinv = Num<T>::rsqrt_seq(piv);
       const T lij = S[j] * rinv, lsij = A[j] * rinv, vtij = V[j] * rinv;
       A[j] = lsij;
       V[j] = vtij;
@@ -541,7 +541,7 @@ big2_element_kernel(const T* __restrict__ diag, const T* __restrict__ sub, const
     if constexpr (BORDER) {  // border pivot: column 16 of Ls / Vt
       const T piv = sbb;
       ok = ok && (piv > T(0));
-      const T rinv = Num<T>::rsqrt(piv);
+      const T rinv = Num<T>::rsqrt_seq(piv);
       A[16] = A[16] * rinv;
       V[16] = V[16] * rinv;
       abb = abb * rinv;

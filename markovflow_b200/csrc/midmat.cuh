@@ -113,7 +113,7 @@ __device__ __forceinline__ bool mid_chol(T* __restrict__ s, T* __restrict__ rinv
     }
     const T p = __shfl_sync(0xffffffffu, v, j);
     ok = ok && (p > T(0));
-    const T r = Num<T>::rsqrt(p);
+    const T r = Num<T>::rsqrt_seq(p);
     if (lane == j) {
       s[j * MID_LD + j] = p * r;
       rinv[j] = r;

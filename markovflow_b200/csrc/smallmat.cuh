@@ -24,6 +24,9 @@ template <> struct Num<double> {
     // x = 0, inf (seed inf, 0: h is NaN) and NaN seeds fall through as the seed itself -- a select, not a branch
     return ::fabs(e) < 0.5 ? ::fma(y * e, t, y) : y;
   }
+  // the library routine, for pivots that depend on each other anyway (large-block kernels: one rsqrt per
+  // column, nothing to overlap it with): its special-case test is an integer compare off the FP64 chain
+  static __device__ __forceinline__ double rsqrt_seq(double x) { return ::rsqrt(x); }
   static __device__ __forceinline__ double log(double x) { return ::log(x); }
   static __device__ __forceinline__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
   static __device__ __forceinline__ double abs(double x) { return ::fabs(x); }
@@ -38,6 +41,7 @@ template <> struct Num<double> {
 };
 template <> struct Num<float> {
   static __device__ __forceinline__ float rsqrt(float x) { return ::rsqrtf(x); }
+  static __device__ __forceinline__ float rsqrt_seq(float x) { return ::rsqrtf(x); }
   static __device__ __forceinline__ float log(float x) { return ::logf(x); }
   static __device__ __forceinline__ float fma(float a, float b, float c) { return ::fmaf(a, b, c); }
   static __device__ __forceinline__ float abs(float x) { return ::fabsf(x); }

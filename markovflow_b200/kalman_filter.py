@@ -146,7 +146,9 @@ class BaseKalmanFilter(abc.ABC):
     @boundary
     def log_likelihood(self) -> torch.Tensor:
         """Marginal log-likelihood, summed over the batch (reference :184-255)."""
-        return torch.sum(self.log_likelihood_per_chain())
+        per_chain = self.log_likelihood_per_chain()
+        # one series: the sum is the value itself (no reduction launch behind a 0.2 ms kernel)
+        return per_chain.reshape(()) if per_chain.numel() == 1 else torch.sum(per_chain)
 
     @boundary
     def posterior_state_space_model(self) -> StateSpaceModel:
