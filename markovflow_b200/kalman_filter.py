@@ -152,7 +152,26 @@ class BaseKalmanFilter(abc.ABC):
 
     @boundary
     def posterior_state_space_model(self) -> StateSpaceModel:
-        """The posterior as a state-space model (reference :109-182)."""
+        """The posterior as a state-space model (reference :109-182).
+
+        The reference's chain -- ``K_post^-1 = U D U^T``, ``A^-T`` solve, two triangular solves, Cholesky of the
+        block inverses -- is exactly ``naturals_to_ssm_params`` applied to the posterior's natural parameters
+        ``theta_lin = H^T R^-1 y + K^-1 mu_prior``, ``theta_diag = -1/2 diag(K_post^-1)``,
+        ``theta_sub = -sub(K_post^-1)`` (``ssm_gaussian_transformations.py:332-511`` states the same recursion),
+        which is ONE backward sweep here (``mf_nat_to_ssm``): a handful of launches instead of ~25.  Under
+        autograd the operator-by-operator composition below is kept (its pieces have adjoint sweeps)."""
+        from .autograd import needs_grad
+        from .ssm_gaussian_transformations import naturals_to_ssm_params, ssm_to_naturals
+
+        prior = self.prior_ssm
+        if not needs_grad(prior._A_s, prior._b_s, prior._chol_Q_s, prior._chol_P_0, prior._mu_0,
+                          self.emission.emission_matrix, as_torch(self.observations), self._r_inv):
+            post = self._k_inv_post
+            theta_lin = ssm_to_naturals(prior)[0] + self._back_project_y_to_state(self.observations)
+            a_s, offsets, chol_p0, chol_qs, mu0 = naturals_to_ssm_params(
+                theta_lin, -0.5 * post.block_diagonal, -post.block_sub_diagonal)
+            return StateSpaceModel(initial_mean=mu0, chol_initial_covariance=chol_p0, state_transitions=a_s,
+                                   state_offsets=offsets, chol_process_covariances=chol_qs)
         a_inv_post, chol_q_inv_post = self._k_inv_post.upper_diagonal_lower()
         obs_proj = self._back_project_y_to_state(self.observations)
         k_inv_mu_prior = self._k_inv_prior.dense_mult(self.prior_ssm.marginal_means)
