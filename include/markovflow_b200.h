@@ -65,7 +65,7 @@ const char* mf_last_cuda_error(void);
  * that many segments, 2 the round-1 warp-per-chain kernel; knob 12: 1 = ring producers wait for their element
  * cp.async themselves and arrive with a plain mbarrier arrive (the completion path compute-sanitizer's
  * racecheck models; default: cp.async.mbarrier.arrive.noinc); knob 13: 1 = no tensor-map (cp.async.bulk.tensor)
- * sweeps, always one 1-D bulk copy per chain; knob 14: tensor-map tile geometry (0 auto: 4-step tiles, 1: 8-step,
+ * sweeps, always one 1-D bulk copy per chain, 2 = tensor-map sweeps also below their minimum problem size; knob 14: tensor-map tile geometry (0 auto: 4-step tiles, 1: 8-step,
  * 2: 4-step with one output stage, 3: 2-step, 4: 4-step; auto = 4-step tiles in float64, 8-step in float32). */
 int mf_set_tuning(int knob, int value);
 /* Number of sweeps launched on the tensor-map engine (csrc/sweep_tm.cuh) since the library was loaded; the tests

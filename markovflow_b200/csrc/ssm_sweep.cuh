@@ -1350,6 +1350,10 @@ struct TmAuto {
   template <int K, int NSI, int NSO>
   static constexpr bool fits() { return SweepTmCfg<Core, 64, K, NSI, NSO, 4>::FITS; }
   static constexpr bool ok = small && fits<4, 2, 2>();
+  // (D = 3 records, 72 bytes: chains of T - 1 entries are 8 bytes off a 16-byte stride for even T, so the
+  //  sub-diagonal streams cannot be mapped; the block-tridiagonal solve / inverse-subset / U D U^T cores, two
+  //  or three 32-byte streams at D = 2, were measured on this engine and are 20-30 % slower than on 8-step 1-D
+  //  tiles (tools/btd_tm_ab.py) -- they stay on the 1-D engine)
   static cudaError_t launch(const typename Core::Params& prm, cudaStream_t s) {
     if constexpr (ok) {
       const int g = tuning(14);

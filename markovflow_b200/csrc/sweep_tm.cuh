@@ -518,6 +518,11 @@ inline cudaError_t launch_chain_sweep_tm(const typename Core::Params& prm, cudaS
   int cpb = tm_rows_per_cta(P, C, NX);
   if (cpb <= 0) return cudaErrorNotSupported;
   const int64_t nrows = B * P;
+  // The engine pays off where the 1-D engine is bound by bulk-copy ISSUE: every SM busy with full CTAs.  With
+  // fewer rows than 148 CTAs' worth a sweep is bound by the latency of one warp's steps, and the 1-D engine's
+  // longer tiles win (measured, 4096 chains x 1e4 steps, D = 2: 1.84 ms against 2.30 ms).  Knob 13 = 2 lifts
+  // the threshold (tests).
+  if (nrows < (int64_t)148 * C && tuning(13) != 2) return cudaErrorNotSupported;
   if (P == 1 && nrows < (int64_t)148 * C) {  // few chains: spread over the SMs
     cpb = (int)((nrows + 147) / 148);
     if (cpb < 1) cpb = 1;

@@ -40,6 +40,8 @@ class knobs:
         from markovflow_b200 import _lib
 
         self.lib = _lib.lib()
+        # knob 13 = 2: no minimum problem size for the tensor-map engine (it is selected from 148 x 64 rows on)
+        self.kv.setdefault(13, 2)
         for k, v in self.kv.items():
             self.lib.mf_set_tuning(k, v)
         return self.lib
