@@ -14,7 +14,7 @@
 #include "dispatch.cuh"
 #include "nat_kernels.cuh"
 #include "smallrng.cuh"
-#include "sweep_tm.cuh"
+#include "sweep_tmi.cuh"
 
 namespace mf {
 
@@ -139,6 +139,8 @@ struct SsmMomentsCore {
     if (i == 2) return vgeom_incoming<T>(p.o_sub, c, p.Tn, DD, k0, n);
     return vgeom_states<T>(i == 0 ? p.o_vec : p.o_diag, c, p.Tn, eout(i), k0, n);
   }
+  // in-place stages (sweep_tmi.cuh): a -> lag-one block, b -> mean, chol_q -> covariance of the same step
+  static constexpr int tm_alias(int i) { return i == 0 ? 2 : (i == 1 ? 0 : 1); }
   // host-side description of the same streams for the tensor-map engine (sweep_tm.cuh)
   static void tm_describe(const Params& p, TmStream* in, TmStream* out) {
     in[0] = TmStream{p.a, p.Tn - 1, -1};
@@ -993,6 +995,8 @@ struct NatToSsmCore : NatGeomBase<T_, D> {
   static constexpr int DD = D * D;
   static constexpr int NIN = 3, NOUT = 3;
   static constexpr int eout(int i) { return i == 1 ? D : DD; }
+  // in-place stages (sweep_tmi.cuh): theta_lin -> offset, theta_diag -> chol Q, theta_sub -> A of the same step
+  static constexpr int tm_alias(int i) { return i == 0 ? 1 : (i == 1 ? 2 : 0); }
   static __device__ __forceinline__ StreamGeom out_geom(const Params& p, int i, int64_t v) {
     const int64_t c = v / p.P, k0 = (v % p.P) * p.L;
     const int64_t n = seg_steps(p.Tn, k0, p.L);
@@ -1014,15 +1018,83 @@ struct NatToSsmCore : NatGeomBase<T_, D> {
     if (n_ > 0 && k0_ + n_ < p.Tn) {  // not the last segment: factor the seed D entering it
       load_vec_rw<T, DD>(S, p.out_chol + (c * p.Tn + k0_) * DD);
       load_vec_rw<T, D>(z, p.out_off + (c * p.Tn + k0_) * D);
-      const bool ok = chol_lower<T, D>(S, rinv);
+      bool ok;
+      if constexpr (D == 2) {
+        ok = prep2(S[0], S[2], S[3], S, rinv);
+      } else {
+        ok = chol_lower<T, D>(S, rinv);
+      }
       if (!ok) fail = (int32_t)(k0_ + n_ + 1);
     }
+  }
+  // ---- D = 2: closed forms instead of factor + substitutions -----------------------------------------------
+  // For a 2 x 2 block D = [[d00, d10], [d10, d11]] everything a step needs follows from TWO INDEPENDENT
+  // reciprocal square roots, ra = rsqrt(d11) and rb = rsqrt(det D):
+  //     D^-1 = rb^2 adj(D),      chol(D^-1) = [[d11 ra rb, 0], [-d10 ra rb, ra]]
+  // (check: c00^2 = d11 / det, c10 c00 = -d10 / det, c10^2 + c11^2 = d00 / det), against two dependent rsqrt's
+  // for chol(D), two triangular solves per right-hand side, an explicit inverse and two more dependent rsqrt's
+  // for its factor in the general path.  det = d00 d11 - d10^2 carries the same cancellation as the second
+  // Cholesky pivot det / d00.  State: s = (d00, d10, d11, rb^2), r = (ra, rb).
+  static __device__ __forceinline__ bool prep2(T d00, T d10, T d11, T* __restrict__ s, T* __restrict__ r) {
+    const T det = Num<T>::fma(d00, d11, -(d10 * d10));
+    r[0] = Num<T>::rsqrt(d11);
+    r[1] = Num<T>::rsqrt(det);
+    s[0] = d00;
+    s[1] = d10;
+    s[2] = d11;
+    s[3] = r[1] * r[1];
+    return (d00 > T(0)) && (det > T(0));
+  }
+  __device__ __forceinline__ void emit2(T* const* out, int j) {
+    const T d00 = S[0], d10 = S[1], d11 = S[2], idet = S[3], ra = rinv[0], rb = rinv[1];
+    T off[2], Qc[4];
+    off[0] = idet * Num<T>::fma(d11, z[0], -(d10 * z[1]));
+    off[1] = idet * Num<T>::fma(d00, z[1], -(d10 * z[0]));
+    st_s<T, 2>(out[1] + j * 2, off);
+    const T rab = ra * rb;
+    Qc[0] = d11 * rab;
+    Qc[1] = T(0);
+    Qc[2] = -(d10 * rab);
+    Qc[3] = ra;
+    st_s<T, 4>(out[2] + j * 4, Qc);
+  }
+  __device__ __forceinline__ void advance2(const T* const* in, T* const* out, int j, int64_t k) {
+    T th[2], Dk[4];
+    ld_s<T, 2>(th, in[0] + j * 2);
+    ld_s<T, 4>(Dk, in[1] + j * 4);
+    T d00 = T(-2) * Dk[0], d10 = T(-2) * Dk[2], d11 = T(-2) * Dk[3];
+    if (k + 1 < Tn_) {
+      T Th[4], A[4];
+      ld_s<T, 4>(Th, in[2] + j * 4);
+      const T n00 = S[0], n10 = S[1], n11 = S[2], idet = S[3];
+      // A_k = D_{k+1}^-1 theta_sub_k = rb^2 adj(D_{k+1}) theta_sub_k
+      A[0] = idet * Num<T>::fma(n11, Th[0], -(n10 * Th[2]));
+      A[1] = idet * Num<T>::fma(n11, Th[1], -(n10 * Th[3]));
+      A[2] = idet * Num<T>::fma(n00, Th[2], -(n10 * Th[0]));
+      A[3] = idet * Num<T>::fma(n00, Th[3], -(n10 * Th[1]));
+      st_s<T, 4>(out[0] + j * 4, A);
+      // D_k = -2 theta_diag_k - theta_sub_k^T A_k  (lower triangle)
+      d00 = Num<T>::fma(-Th[2], A[2], Num<T>::fma(-Th[0], A[0], d00));
+      d10 = Num<T>::fma(-Th[3], A[2], Num<T>::fma(-Th[1], A[0], d10));
+      d11 = Num<T>::fma(-Th[3], A[3], Num<T>::fma(-Th[1], A[1], d11));
+      // z_k = theta_lin_k + A_k^T z_{k+1}
+      th[0] = Num<T>::fma(A[2], z[1], Num<T>::fma(A[0], z[0], th[0]));
+      th[1] = Num<T>::fma(A[3], z[1], Num<T>::fma(A[1], z[0], th[1]));
+    }
+    const bool ok = prep2(d00, d10, d11, S2_, r2_);
+    if (!ok && fail == 0) fail = (int32_t)(k + 1);
+    z2_[0] = th[0];
+    z2_[1] = th[1];
   }
   // Outputs of a step that are NOT on the recursion's dependent path (offsets, chol of the inverse):
   // they only need the step's own factor S, so they are evaluated one iteration late, in the same
   // basic block as the next step's dependent chain -- the two interleave instead of queueing up
   // behind each other in the in-order pipeline.
   __device__ __forceinline__ void emit(T* const* out, int j) {
+    if constexpr (D == 2) {
+      emit2(out, j);
+      return;
+    }
     T off[D], Qc[DD], r2[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) off[i] = z[i];
@@ -1036,6 +1108,10 @@ struct NatToSsmCore : NatGeomBase<T_, D> {
   }
   // dependent chain of step k: D_k, its factor and z_k from the factor of step k+1
   __device__ __forceinline__ void advance(const T* const* in, T* const* out, int j, int64_t k) {
+    if constexpr (D == 2) {
+      advance2(in, out, j, k);
+      return;
+    }
     T Dk[DD], th[D], S2[DD], rinv2[D];
     ld_s<T, D>(th, in[0] + j * D);
     ld_s<T, DD>(Dk, in[1] + j * DD);
@@ -1338,6 +1414,11 @@ struct HasTm : std::false_type {};
 template <class Core>
 struct HasTm<Core, std::void_t<decltype(&Core::tm_describe)>> : std::true_type {};
 
+template <class Core, class = void>
+struct HasAlias : std::false_type {};
+template <class Core>
+struct HasAlias<Core, std::void_t<decltype(&Core::tm_alias)>> : std::true_type {};
+
 template <class Core>
 struct TmAuto {
   static constexpr int max_e() {
@@ -1357,6 +1438,19 @@ struct TmAuto {
   static cudaError_t launch(const typename Core::Params& prm, cudaStream_t s) {
     if constexpr (ok) {
       const int g = tuning(14);
+      // cores that pair their streams run on in-place stages (one ring of 4, the loader two tiles ahead);
+      // knob 14 = 8: separate rings as below
+      if constexpr (HasAlias<Core>::value) {
+        constexpr int KI = sizeof(typename Core::T) == 4 ? 8 : 4;  // the same bytes per stage in either dtype
+        // (measured on config 5: three stages and three CTAs per SM with one chain per CTA, 0.64 / 0.55 ms
+        //  against 0.60 / 0.51 ms for four stages and two CTAs)
+        if constexpr (SweepTmiCfg<Core, 64, KI, 4, 4>::FITS) {
+          if (g == 0) {
+            const cudaError_t e = launch_chain_sweep_tmi<Core, 64, KI, 4, 4>(prm, s);
+            if (e != cudaErrorNotSupported) return e;
+          }
+        }
+      }
       if constexpr (fits<8, 2, 2>()) {
         if (g == 1) return launch_chain_sweep_tm<Core, 64, 8, 2, 2, 4>(prm, s);
       }

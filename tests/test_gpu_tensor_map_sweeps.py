@@ -137,7 +137,7 @@ def test_tensor_map_engine_serves_the_config5_shapes():
     for dtype in (torch.float64, torch.float32):
         arrays, th_np = naturals_case(b, t, d, dtype, 5)
         th = tuple(tt(x, dtype) for x in th_np)
-        for geom in (0, 1, 2, 3, 4):
+        for geom in (0, 1, 2, 3, 4, 8):
             with knobs(k14=geom):
                 n0 = tm_count()
                 got = mf.naturals_to_ssm_params(*th)

@@ -1,5 +1,5 @@
 """Config-5 transforms (B=1024 x M=1e4, D=2): time per call for the 1-D engine (knob 13 = 1) and every tile
-geometry of the tensor-map engine (knob 14)."""
+geometry of the tensor-map engine (knob 14; 0 = in-place stages, 8 = separate rings)."""
 import os
 import sys
 
@@ -33,15 +33,17 @@ if __name__ == "__main__":
         th = tuple(x.to(dtype) for x in bench_inputs.cvi_naturals_config5(B, T, dev, dtype=torch.float64))
         got = mf.naturals_to_ssm_params(*th)
         q = mf.StateSpaceModel(*(g.contiguous() for g in (got[4], got[2], got[0], got[1], got[3])))
-        for k13, k14 in ((1, 0), (0, 0), (0, 1), (0, 2), (0, 3), (0, 4)):
+        for k13, k14, k3 in ((1, 0, 0), (0, 0, 0), (0, 8, 0), (0, 1, 0), (0, 0, 160)):
             lib.mf_set_tuning(13, k13)
             lib.mf_set_tuning(14, k14)
+            lib.mf_set_tuning(3, k3)
             t_nat = timed(lambda: mf.naturals_to_ssm_params(*th))
             t_exp = timed(lambda: mf.ssm_to_expectations(q))
             t_mar = timed(lambda: mf.StateSpaceModel(*(g for g in (got[4], got[2], got[0], got[1], got[3]))).marginals)
             es = 8 if dtype == torch.float64 else 4
             gb = B * T * 20 * es / 1e9
-            print(f"{str(dtype):14s} knob13={k13} knob14={k14}  nat->ssm {t_nat:.3f} ms ({gb / t_nat:.2f} TB/s)  "
+            print(f"{str(dtype):14s} knob13={k13} knob14={k14} seg={k3}  nat->ssm {t_nat:.3f} ms ({gb / t_nat:.2f} TB/s)  "
                   f"ssm->exp {t_exp:.3f} ms ({gb / t_exp:.2f} TB/s)  marginals {t_mar:.3f} ms", flush=True)
         lib.mf_set_tuning(13, 0)
         lib.mf_set_tuning(14, 0)
+        lib.mf_set_tuning(3, 0)
