@@ -42,10 +42,9 @@ int run(const typename Core::Params& p, int64_t nchains, cudaStream_t s) {
 
 // Segments per chain for the parallel-in-time evaluation of an exact (affine) recurrence: enough
 // virtual chains to occupy the GPU, segments of at least 64 steps.
-static void plan_segments(int64_t B, int64_t T, int64_t* P, int64_t* L) {
+static void plan_segments(int64_t B, int64_t T, int64_t* P, int64_t* L, int64_t target = (int64_t)148 * 192) {
   // The three passes move ~1.5-2x the bytes of the sequential sweep, whose cost is T x (latency of a
   // step) whatever B: parallel in time pays off below ~2000 chains (measured: B = 4096 is slower).
-  const int64_t target = (int64_t)148 * 192;
   int64_t p = B > 2048 ? 1 : (target + B - 1) / B;
   if (p > T / 64) p = T / 64;
   if (p < 1) p = 1;
@@ -68,7 +67,10 @@ int ssm_sweep_moments(int dtype, int64_t D, int expectations, const void* mu0, c
     SsmMomentsParams<Tp> p{(const Tp*)mu0, (const Tp*)chol_p0, (const Tp*)a, (const Tp*)b,
                            (const Tp*)chol_q, (Tp*)o_vec, (Tp*)o_diag, (Tp*)o_sub, B, T, 1, T,
                            (Tp*)o_vec, (Tp*)o_diag, 0};
-    if (tuning(2) != 1 && o_diag && (o_vec || !expectations)) plan_segments(B, T, &p.P, &p.L);
+    // float32 forward sweeps stay on the 1-D engine (`b`: [B, T-1, 2] floats, chains 8 bytes off a 16-byte stride,
+    // cannot be tensor-mapped); there twice the segments pack the CTAs better (config 5: 0.396 -> 0.349 ms)
+    const int64_t target = (int64_t)148 * (sizeof(Tp) == 4 ? 384 : 192);
+    if (tuning(2) != 1 && o_diag && (o_vec || !expectations)) plan_segments(B, T, &p.P, &p.L, target);
     if (p.P > 1) {
       int rc = run<SsmMomSummaryCore<Tp, kD>>(p, B * p.P, s);
       if (rc != MF_OK) return rc;

@@ -33,7 +33,7 @@ if __name__ == "__main__":
         th = tuple(x.to(dtype) for x in bench_inputs.cvi_naturals_config5(B, T, dev, dtype=torch.float64))
         got = mf.naturals_to_ssm_params(*th)
         q = mf.StateSpaceModel(*(g.contiguous() for g in (got[4], got[2], got[0], got[1], got[3])))
-        for k13, k14, k3 in ((1, 0, 0), (0, 0, 0), (0, 8, 0), (0, 1, 0), (0, 0, 160)):
+        for k13, k14, k3 in [(1, 0, 0), (0, 0, 0), (0, 8, 0)] + [(0, 0, int(x)) for x in os.environ.get('C5_SEGS', '').split(',') if x]:
             lib.mf_set_tuning(13, k13)
             lib.mf_set_tuning(14, k14)
             lib.mf_set_tuning(3, k3)
