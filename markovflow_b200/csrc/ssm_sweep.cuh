@@ -1444,6 +1444,8 @@ struct TmAuto {
         constexpr int KI = sizeof(typename Core::T) == 4 ? 8 : 4;  // the same bytes per stage in either dtype
         // (measured on config 5: three stages and three CTAs per SM with one chain per CTA, 0.64 / 0.55 ms
         //  against 0.60 / 0.51 ms for four stages and two CTAs)
+        // (two stages of twice the steps -- 256-byte pieces per row instead of 128: 0.635 / 0.500 ms against
+        //  0.642 / 0.513 ms in the same run: within the run-to-run spread, not adopted)
         if constexpr (SweepTmiCfg<Core, 64, KI, 4, 4>::FITS) {
           if (g == 0) {
             const cudaError_t e = launch_chain_sweep_tmi<Core, 64, KI, 4, 4>(prm, s);
