@@ -45,6 +45,7 @@ extern "C" {
                           * mf_btd_abs_log_det, mf_ssm_build_precision, mf_ssm_marginals, mf_ssm_affine_scan,
                           * mf_ssm_log_pdf, mf_ssm_kl_divergence, mf_nat_to_ssm, mf_ssm_to_naturals, mf_ssm_to_expectations,
                           * mf_expectations_to_ssm, mf_block_cholesky_or_zero, mf_block_chol_of_inverse,
+                          * mf_pairwise_marginals, mf_conditional_statistics, mf_conditional_predict,
                           * mf_kalman_log_likelihood */
 
 /* Library / build information. */

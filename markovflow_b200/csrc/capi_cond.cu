@@ -3,6 +3,7 @@
 // states, conditional statistics p(x_t | x_-, x_+) from transition statistics, and the prediction at
 // new time points.  All three are per-(chain, point) maps without recursion.
 #include "dispatch.cuh"
+#include "mid_api.h"
 #include "smallmat.cuh"
 
 using namespace mf;
@@ -210,6 +211,8 @@ int mf_pairwise_marginals(int dtype, const void* mean, const void* cov, const vo
   if (!mean || !cov || (T > 1 && !sub) || !init_mean || !init_cov || !out_mean || !out_cov)
     return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (mid_dim(D))
+    return mid_pairwise_marginals(dtype, mean, cov, sub, init_mean, init_cov, init_batch, out_mean, out_cov, B, T, D, s);
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
@@ -227,6 +230,8 @@ int mf_conditional_statistics(int dtype, const void* a_mt, const void* q_mt, con
   if (N == 0) return MF_OK;
   if (!a_mt || !q_mt || !a_tp || !q_tp || !out_p || !out_t) return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (mid_dim(D))
+    return mid_conditional_statistics(dtype, a_mt, q_mt, a_tp, q_tp, out_p, out_t, info, return_precision, N, D, s);
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;
@@ -245,6 +250,8 @@ int mf_conditional_predict(int dtype, const void* proj, const void* tcov, const 
   if (!proj || !tcov || !pair_means || !out_mean || !out_cov) return MF_ERR_BAD_ARG;
   if (!indices && N != M) return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (mid_dim(D))
+    return mid_conditional_predict(dtype, proj, tcov, pair_means, pair_covs, indices, out_mean, out_cov, B, N, M, D, s);
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;

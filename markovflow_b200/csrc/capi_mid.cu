@@ -235,6 +235,41 @@ int mid_kl_divergence(int dtype, const void* q_mu0, const void* q_chol_p0, const
   });
 }
 
+int mid_pairwise_marginals(int dtype, const void* mean, const void* cov, const void* sub, const void* init_mean,
+                           const void* init_cov, int64_t init_batch, void* out_mean, void* out_cov, int64_t B,
+                           int64_t T, int64_t D, cudaStream_t s) {
+  if (!mid_dim(D) || B * (T + 1) > 0x7fffffffLL) return MF_ERR_UNSUPPORTED;
+  return dispatch_dtype(dtype, [&](auto tt) {
+    using Tp = typename decltype(tt)::type;
+    mid_pairwise_marginals_kernel<Tp><<<(unsigned)(B * (T + 1)), 128, 0, s>>>(
+        (const Tp*)mean, (const Tp*)cov, (const Tp*)sub, (const Tp*)init_mean, (const Tp*)init_cov, init_batch,
+        (Tp*)out_mean, (Tp*)out_cov, B, T, (int)D);
+    return check_launch();
+  });
+}
+
+int mid_conditional_statistics(int dtype, const void* a_mt, const void* q_mt, const void* a_tp, const void* q_tp,
+                               void* out_p, void* out_t, int32_t* info, int return_precision, int64_t N, int64_t D,
+                               cudaStream_t s) {
+  if (!mid_dim(D) || N > 0x7fffffffLL) return MF_ERR_UNSUPPORTED;
+  return dispatch_dtype(dtype, [&](auto tt) {
+    using Tp = typename decltype(tt)::type;
+    MF_MID_LAUNCH(mid_conditional_statistics_kernel, N, 9, 2, (const Tp*)a_mt, (const Tp*)q_mt, (const Tp*)a_tp,
+                  (const Tp*)q_tp, (Tp*)out_p, (Tp*)out_t, info, return_precision, N, (int)D);
+  });
+}
+
+int mid_conditional_predict(int dtype, const void* proj, const void* tcov, const void* pair_means,
+                            const void* pair_covs, const int64_t* indices, void* out_mean, void* out_cov, int64_t B,
+                            int64_t N, int64_t M, int64_t D, cudaStream_t s) {
+  if (!mid_dim(D) || B * N > 0x7fffffffLL) return MF_ERR_UNSUPPORTED;
+  return dispatch_dtype(dtype, [&](auto tt) {
+    using Tp = typename decltype(tt)::type;
+    MF_MID_LAUNCH(mid_conditional_predict_kernel, B * N, 5, 0, (const Tp*)proj, (const Tp*)tcov,
+                  (const Tp*)pair_means, (const Tp*)pair_covs, indices, (Tp*)out_mean, (Tp*)out_cov, B, N, M, (int)D);
+  });
+}
+
 #undef MF_MID_LAUNCH
 
 }  // namespace mf

@@ -51,4 +51,14 @@ int mid_kl_divergence(int dtype, const void* q_mu0, const void* q_chol_p0, const
                       const void* p_b, const void* p_chol_q, void* out, int64_t B, int64_t T, int64_t D,
                       cudaStream_t s);
 
+int mid_pairwise_marginals(int dtype, const void* mean, const void* cov, const void* sub, const void* init_mean,
+                           const void* init_cov, int64_t init_batch, void* out_mean, void* out_cov, int64_t B,
+                           int64_t T, int64_t D, cudaStream_t s);
+int mid_conditional_statistics(int dtype, const void* a_mt, const void* q_mt, const void* a_tp, const void* q_tp,
+                               void* out_p, void* out_t, int32_t* info, int return_precision, int64_t N, int64_t D,
+                               cudaStream_t s);
+int mid_conditional_predict(int dtype, const void* proj, const void* tcov, const void* pair_means,
+                            const void* pair_covs, const int64_t* indices, void* out_mean, void* out_cov, int64_t B,
+                            int64_t N, int64_t M, int64_t D, cudaStream_t s);
+
 }  // namespace mf

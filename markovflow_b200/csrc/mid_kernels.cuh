@@ -700,4 +700,120 @@ mid_kl_kernel(const T* __restrict__ q_mu0, const T* __restrict__ q_chol_p0, cons
   if (lane == 0) out[c] = kl + ratio.log_abs();
 }
 
+// ---- conditionals (capi_cond.cu kernels, conditionals.py:29-205,380-485) for 8 < D <= 32 ---------------------------
+// pairwise marginals: pure assembly, one block per (chain, pair)
+template <typename T>
+__global__ void __launch_bounds__(128)
+mid_pairwise_marginals_kernel(const T* __restrict__ mean, const T* __restrict__ cov, const T* __restrict__ sub,
+                              const T* __restrict__ init_mean, const T* __restrict__ init_cov, int64_t init_batch,
+                              T* __restrict__ o_mean, T* __restrict__ o_cov, int64_t B, int64_t Tn, int d) {
+  const int64_t idx = blockIdx.x;
+  const int64_t c = idx / (Tn + 1), k = idx % (Tn + 1);
+  const int64_t ci = init_batch == 1 ? 0 : c;
+  const int dd = d * d, d2 = 2 * d;
+  const T* m0 = k == 0 ? init_mean + ci * d : mean + (c * Tn + k - 1) * d;
+  const T* S0 = k == 0 ? init_cov + ci * dd : cov + (c * Tn + k - 1) * dd;
+  const T* m1 = k == Tn ? init_mean + ci * d : mean + (c * Tn + k) * d;
+  const T* S1 = k == Tn ? init_cov + ci * dd : cov + (c * Tn + k) * dd;
+  const T* C = (k >= 1 && k < Tn) ? sub + (c * (Tn - 1) + k - 1) * dd : nullptr;
+  T* om = o_mean + idx * d2;
+  T* oc = o_cov + idx * (int64_t)d2 * d2;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    om[i] = m0[i];
+    om[d + i] = m1[i];
+  }
+  for (int i = threadIdx.x; i < dd; i += blockDim.x) {
+    const int r = i / d, q = i % d;
+    oc[r * d2 + q] = S0[i];
+    oc[r * d2 + d + q] = C ? C[q * d + r] : T(0);
+    oc[(d + r) * d2 + q] = C ? C[i] : T(0);
+    oc[(d + r) * d2 + d + q] = S1[i];
+  }
+}
+
+// conditional statistics: warp per point
+template <typename T>
+__global__ void __launch_bounds__(32)
+mid_conditional_statistics_kernel(const T* __restrict__ a_mt, const T* __restrict__ q_mt, const T* __restrict__ a_tp,
+                                  const T* __restrict__ q_tp, T* __restrict__ o_p, T* __restrict__ o_t,
+                                  int32_t* __restrict__ info, int return_precision, int64_t N, int d) {
+  extern __shared__ __align__(16) unsigned char mid_raw[];
+  const MidSmem<T> sm{reinterpret_cast<T*>(mid_raw)};
+  constexpr int NM = 9;
+  T *Am = sm.mat(0), *Qm = sm.mat(1), *Ap = sm.mat(2), *Qp = sm.mat(3), *AQ = sm.mat(4), *L = sm.mat(5),
+    *V = sm.mat(6), *E = sm.mat(7), *W = sm.mat(8);
+  T *rinv = sm.vec(NM, 0), *r2 = sm.vec(NM, 1);
+  const int lane = threadIdx.x;
+  const int64_t n = blockIdx.x;
+  const int dd = d * d, d2 = 2 * d;
+  mid_load<T>(Am, a_mt + n * dd, d, lane);
+  mid_load<T>(Qm, q_mt + n * dd, d, lane);
+  mid_load<T>(Ap, a_tp + n * dd, d, lane);
+  mid_load<T>(Qp, q_tp + n * dd, d, lane);
+  mid_gemm<T, false, false, 0>(AQ, Ap, Qm, d, lane);  // A_tp Q_mt
+  mid_gemm<T, false, true, 0>(L, AQ, Ap, d, lane);    // A_tp Q_mt A_tp^T
+  mid_axpy<T, 1>(L, Qp, d, lane);
+  bool ok = mid_chol<T>(L, rinv, d, lane);
+  mid_copy<T>(V, AQ, d, lane);
+  mid_trsm_l<T>(L, rinv, V, d, lane);  // V = L^-1 A_tp Q_mt
+  mid_copy<T>(W, V, d, lane);
+  mid_trsm_lt<T>(L, rinv, W, d, lane);  // L^-T V = E^T
+  mid_transpose<T>(E, W, d, lane);
+  mid_gemm<T, false, false, 0>(W, E, Ap, d, lane);   // E A_tp
+  mid_gemm<T, false, false, 0>(AQ, W, Am, d, lane);  // E A_tp A_mt
+  mid_axpy<T, 0>(AQ, Am, d, lane);                   // D = A_mt - E A_tp A_mt
+  mid_store_pitched<T>(o_p + n * (int64_t)d * d2, AQ, d, d2, lane);
+  mid_store_pitched<T>(o_p + n * (int64_t)d * d2 + d, E, d, d2, lane);
+  if (return_precision) {
+    ok = mid_chol<T>(Qm, rinv, d, lane) && ok;
+    ok = mid_chol<T>(Qp, r2, d, lane) && ok;
+    mid_chol_inverse<T>(L, Qm, rinv, W, d, lane);  // Q_mt^-1
+    mid_trsm_l<T>(Qp, r2, Ap, d, lane);            // L_tp^-1 A_tp
+    mid_gemm<T, true, false, 1>(L, Ap, Ap, d, lane);
+    mid_store<T>(o_t + n * dd, L, d, lane);
+  } else {
+    mid_gemm<T, true, false, -1>(Qm, V, V, d, lane);  // T = Q_mt - V^T V
+    mid_store<T>(o_t + n * dd, Qm, d, lane);
+  }
+  if (info && lane == 0) info[n] = ok ? 0 : 1;
+}
+
+// conditional prediction: warp per (chain, point);  mean = P m[idx],  cov = T (+ P S[idx] P^T), P = [P0 | P1]
+template <typename T>
+__global__ void __launch_bounds__(32)
+mid_conditional_predict_kernel(const T* __restrict__ proj, const T* __restrict__ tcov,
+                               const T* __restrict__ pair_means, const T* __restrict__ pair_covs,
+                               const int64_t* __restrict__ indices, T* __restrict__ o_mean, T* __restrict__ o_cov,
+                               int64_t B, int64_t N, int64_t M, int d) {
+  extern __shared__ __align__(16) unsigned char mid_raw[];
+  const MidSmem<T> sm{reinterpret_cast<T*>(mid_raw)};
+  T *P0 = sm.mat(0), *P1 = sm.mat(1), *S = sm.mat(2), *W = sm.mat(3), *Cv = sm.mat(4);
+  const int lane = threadIdx.x;
+  const int64_t idx = blockIdx.x;
+  const int64_t c = idx / N;
+  int64_t j = indices ? indices[idx] : idx % N;
+  if (j < 0) j = 0;
+  if (j > M - 1) j = M - 1;
+  const int dd = d * d, d2 = 2 * d;
+  const T* P = proj + idx * (int64_t)d * d2;
+  const T* m = pair_means + (c * M + j) * d2;
+  mid_load_pitched<T>(P0, P, d, d2, lane);
+  mid_load_pitched<T>(P1, P + d, d, d2, lane);
+  const T m0 = lane < d ? m[lane] : T(0), m1 = lane < d ? m[d + lane] : T(0);
+  T mean = mid_gemv<T, false, 0>(P0, m0, T(0), d, lane);
+  mean = mid_gemv<T, false, 1>(P1, m1, mean, d, lane);
+  if (lane < d) o_mean[idx * d + lane] = mean;
+  mid_load<T>(Cv, tcov + idx * dd, d, lane);
+  if (pair_covs) {
+    const T* Sg = pair_covs + (c * M + j) * (int64_t)d2 * d2;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        mid_load_pitched<T>(S, Sg + (int64_t)a * d * d2 + b * d, d, d2, lane);
+        mid_gemm<T, false, false, 0>(W, a == 0 ? P0 : P1, S, d, lane);
+        mid_gemm<T, false, true, 1>(Cv, W, b == 0 ? P0 : P1, d, lane);
+      }
+  }
+  mid_store<T>(o_cov + idx * dd, Cv, d, lane);
+}
+
 }  // namespace mf

@@ -32,6 +32,31 @@ __device__ __forceinline__ void mid_store(T* __restrict__ g, const T* __restrict
   __syncwarp();
   for (int idx = lane; idx < d * d; idx += 32) g[idx] = m[(idx / d) * MID_LD + (idx % d)];
 }
+// the same with a row pitch on the global side (a d x d window of a wider row-major matrix)
+template <typename T>
+__device__ __forceinline__ void mid_load_pitched(T* __restrict__ m, const T* __restrict__ g, int d, int pitch,
+                                                 int lane) {
+  __syncwarp();
+  for (int idx = lane; idx < d * d; idx += 32) m[(idx / d) * MID_LD + (idx % d)] = g[(idx / d) * pitch + (idx % d)];
+  __syncwarp();
+}
+template <typename T>
+__device__ __forceinline__ void mid_store_pitched(T* __restrict__ g, const T* __restrict__ m, int d, int pitch,
+                                                  int lane) {
+  __syncwarp();
+  for (int idx = lane; idx < d * d; idx += 32) g[(idx / d) * pitch + (idx % d)] = m[(idx / d) * MID_LD + (idx % d)];
+}
+// a (op)= b, elementwise: SIGN +1 / -1;  a = b - a for SIGN 0
+template <typename T, int SIGN>
+__device__ __forceinline__ void mid_axpy(T* __restrict__ a, const T* __restrict__ b, int d, int lane) {
+  __syncwarp();
+  if (lane < d)
+    for (int j = 0; j < d; ++j) {
+      const T x = a[lane * MID_LD + j], y = b[lane * MID_LD + j];
+      a[lane * MID_LD + j] = SIGN > 0 ? x + y : (SIGN < 0 ? x - y : y - x);
+    }
+  __syncwarp();
+}
 // lower triangle only, zeros above (Cholesky factors as the reference returns them)
 template <typename T>
 __device__ __forceinline__ void mid_store_lower(T* __restrict__ g, const T* __restrict__ m, int d, int lane) {

@@ -294,3 +294,59 @@ def test_kl_divergence_above_eight_dimensions(b, n, d, dtype):
                                                 O.SSM(*(a.astype(np.float32) for a in pa)))))
     assert_parity(npy(q.kl_divergence(p)), want, TOL[dtype], what=f"KL D={d}", **kw)
     assert float(q.kl_divergence(q).abs().max()) <= (1e-9 if dtype == torch.float64 else 1e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("d", [9, 17, 32])
+def test_conditionals_above_eight_dimensions(d, dtype):
+    """pairwise_marginals, conditional statistics and conditional prediction (conditionals.py:29-205,380-485): the
+    bodies of tests/test_gpu_conditionals.py at state dimensions served by the warp-per-point kernels."""
+    from tests import test_gpu_conditionals as tc
+
+    tc.test_pairwise_marginals((2,), 7, d, dtype)
+    tc.test_pairwise_marginals((), 3, d, dtype)
+    tc.test_conditional_statistics_and_predict(d, dtype)
+
+
+def test_posterior_process_with_the_config4_kernel():
+    """ConditionalProcess.predict_f for the D = 17 Sum(Matern52 + 7 harmonics)-like kernel of BASELINE config 4 against
+    the dense GP posterior at new time points (posterior.py:207-258 on top of conditionals.py)."""
+    import markovflow_b200 as mf
+    from markovflow_b200.kernels import HarmonicOscillator, Matern52, Sum
+
+    rng = np.random.default_rng(4)
+    # (the jitter -- 1e-6 on every Q_k and on P0 -- keeps the oscillators' process noise factorisable; it is part of
+    #  the model the operators see, hence the tolerances below, as in tests/test_gpu_posterior.py)
+    kern = Sum([Matern52(lengthscale=0.7, variance=1.1)] +
+               [HarmonicOscillator(variance=0.3 / (i + 1), period=1.0 / (i + 1)) for i in range(7)], jitter=1e-6)
+    assert kern.state_dim == 17
+    x = torch.as_tensor(np.sort(rng.uniform(0.0, 3.0, size=25)), device="cuda:0")
+    y = torch.as_tensor(rng.standard_normal((25, 1)), device="cuda:0")
+    noise = 0.2
+    ssm = kern.state_space_model(x)
+    em = kern.generate_emission_model(x)
+    kf = mf.KalmanFilter(ssm, em, y, torch.as_tensor([[noise ** 0.5]], device="cuda:0", dtype=torch.float64))
+    post = mf.ConditionalProcess(kf.posterior_state_space_model(), kern, x)
+    xs = torch.as_tensor(np.sort(rng.uniform(0.2, 2.8, size=9)), device="cuda:0")
+    mean, var = post.predict_f(xs)
+    # dense GP regression with the same covariance function
+    xn, xsn, yn = x.cpu().numpy(), xs.cpu().numpy(), y.cpu().numpy()
+
+    def k(a, b):
+        r = np.abs(a[:, None] - b[None, :])
+        s5 = np.sqrt(5.0) * r / 0.7
+        out = 1.1 * (1 + s5 + s5 ** 2 / 3.0) * np.exp(-s5)
+        for i in range(7):
+            out = out + (0.3 / (i + 1)) * np.cos(2 * np.pi * (i + 1) * r)
+        return out
+
+    kxx = k(xn, xn) + noise * np.eye(25)
+    ksx = k(xsn, xn)
+    want_mean = ksx @ np.linalg.solve(kxx, yn)
+    want_var = np.diag(k(xsn, xsn) - ksx @ np.linalg.solve(kxx, ksx.T))
+    inside = (xsn > xn[0]) & (xsn < xn[-1])
+    assert inside.sum() >= 5
+    got_mean, got_var = npy(mean).reshape(-1), npy(var).reshape(-1)
+    # eight components each carry the jitter: the dense answer (no jitter) is matched to 1e-3
+    assert np.abs(got_mean - want_mean[:, 0])[inside].max() < 1e-3 * max(1.0, np.abs(want_mean).max())
+    assert np.abs(got_var - want_var)[inside].max() < 1e-3 * max(1.0, np.abs(want_var).max())
