@@ -61,6 +61,16 @@ int mf_ssm_sample(int dtype, const void* mu0, const void* chol_p0, const void* a
   if (n == 0) return MF_OK;
   if (!mu0 || !chol_p0 || !out || (T > 1 && (!a || !b || !chol_q))) return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (mid_dim(D)) {
+    // blocks in shared memory: the Philox stream is written to a stream-ordered scratch array first
+    const size_t es = dtype == MF_F64 ? 8 : 4;
+    void* eps = nullptr;
+    if (cudaMallocAsync(&eps, (size_t)n * T * D * es, s) != cudaSuccess) return check_launch();
+    int rc = mf_philox_normal(dtype, seed, eps, n, T, D, stream);
+    if (rc == MF_OK) rc = mid_affine_scan(dtype, mu0, chol_p0, a, b, chol_q, eps, out, n, Bm, T, D, s);
+    cudaFreeAsync(eps, s);
+    return rc;
+  }
   if (D <= kSsmSweepMaxD && T > 1 && tuning(4) != 1) {
     const int rc = ssm_sweep_affine(dtype, D, mu0, chol_p0, a, b, chol_q, nullptr, out, n, Bm, T, s, 1, seed);
     if (rc != MF_ERR_UNSUPPORTED) return rc;
@@ -80,6 +90,13 @@ int mf_philox_normal(int dtype, uint64_t seed, void* out, int64_t n, int64_t T, 
   if (n == 0) return MF_OK;
   if (!out) return MF_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (mid_dim(D))
+    return dispatch_dtype(dtype, [&](auto tt) {
+      using Tp = typename decltype(tt)::type;
+      philox_normal_dyn_kernel<Tp><<<grid_for(n * T, 128), 128, 0, s>>>((Tp*)out, n, T, (int)D,
+                                                                        (unsigned long long)seed);
+      return check_launch();
+    });
   return dispatch_small(dtype, D, [&](auto tt, auto dd) {
     using Tp = typename decltype(tt)::type;
     constexpr int kD = decltype(dd)::value;

@@ -144,6 +144,21 @@ philox_normal_kernel(T* __restrict__ out, int64_t n, int64_t Tn, unsigned long l
   store_vec<T, D>(out + idx * D, e);
 }
 
+// the same stream for a run-time state dimension (8 < D <= 32: the draws of mf_ssm_sample above the register kernels)
+template <typename T>
+__global__ void __launch_bounds__(128)
+philox_normal_dyn_kernel(T* __restrict__ out, int64_t n, int64_t Tn, int d, unsigned long long seed) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= n * Tn) return;
+  ChainRng rng;
+  rng.init(seed, idx / Tn, idx % Tn, d);
+  for (int i = 0; i < d; i += 2) {
+    const double2 z = curand_normal2_double(&rng.st);
+    out[idx * d + i] = (T)z.x;
+    if (i + 1 < d) out[idx * d + i + 1] = (T)z.y;
+  }
+}
+
 template <typename T, int D>
 __global__ void __launch_bounds__(32)
 ssm_affine_scan_kernel(const T* __restrict__ mu0, const T* __restrict__ chol_p0,

@@ -261,15 +261,6 @@ class StateSpaceModel(GaussMarkovDistribution):
             if seed is None:
                 seed = int(torch.randint(0, 2 ** 62, (), dtype=torch.int64).item())
             return self._affine_diff(self.sample_epsilons(sample_shape, seed), sample_shape)
-        if d > 8:
-            # the in-kernel generator is built for blocks held in registers (D <= 8); above, the draws come from
-            # torch (seeded with `seed` when given) and go through the warp-per-trajectory affine scan
-            gen = None
-            if seed is not None:
-                gen = torch.Generator(device=a.device)
-                gen.manual_seed(int(seed))
-            eps = torch.randn(full, dtype=a.dtype, device=a.device, generator=gen)
-            return eps if eps.numel() == 0 else self._affine(eps, sample_shape)
         n = _prod(sample_shape) * bsz
         out = torch.empty(n, t, d, dtype=a.dtype, device=a.device)
         if n == 0:

@@ -201,7 +201,11 @@ def test_block_operators_above_eight_dimensions(b, n, d, dtype):
     got = ssm.sample_from_epsilons(tt(eps, dtype))
     assert_parity(npy(got), O.ssm_sample_from_epsilons(ref, eps), tol, what=f"sample D={d}",
                   **kw(lambda s: O.ssm_sample_from_epsilons(s, eps.astype(s.a_s.dtype))))
-    assert tuple(ssm.sample((3,), seed=5).shape) == (3, b, n + 1, d)
+    # the same Philox stream as below eight dimensions: sample(seed) == sample_from_epsilons(sample_epsilons(seed))
+    draws = ssm.sample_epsilons((3,), 5)
+    assert tuple(draws.shape) == (3, b, n + 1, d)
+    assert torch.equal(ssm.sample((3,), seed=5), ssm.sample_from_epsilons(draws))
+    assert abs(float(draws.mean())) < 0.2 and abs(float(draws.std()) - 1.0) < 0.2
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
