@@ -1244,10 +1244,24 @@ struct NatSummaryCore : NatGeomBase<T_, D> {
           W[i] = Q[i];
           A[i] = Ths[i];
         }
-        trsm_left_lower<T, D>(S, rinv, W);
-        trsm_left_lower_t<T, D>(S, rinv, W);
-        trsm_left_lower<T, D>(S, rinv, A);
-        trsm_left_lower_t<T, D>(S, rinv, A);
+        if constexpr (D == 2) {
+          // S holds P^{-1} = adj(P) / det(P) of the previous step (i00, i10, i11)
+          const T q0 = W[0], q1 = W[1], q2 = W[2], q3 = W[3];
+          W[0] = Num<T>::fma(S[0], q0, S[1] * q2);
+          W[1] = Num<T>::fma(S[0], q1, S[1] * q3);
+          W[2] = Num<T>::fma(S[1], q0, S[2] * q2);
+          W[3] = Num<T>::fma(S[1], q1, S[2] * q3);
+          const T a0 = A[0], a1 = A[1], a2 = A[2], a3 = A[3];
+          A[0] = Num<T>::fma(S[0], a0, S[1] * a2);
+          A[1] = Num<T>::fma(S[0], a1, S[1] * a3);
+          A[2] = Num<T>::fma(S[1], a0, S[2] * a2);
+          A[3] = Num<T>::fma(S[1], a1, S[2] * a3);
+        } else {
+          trsm_left_lower<T, D>(S, rinv, W);
+          trsm_left_lower_t<T, D>(S, rinv, W);
+          trsm_left_lower<T, D>(S, rinv, A);
+          trsm_left_lower_t<T, D>(S, rinv, A);
+        }
         // r' = r + W^T p,  R' = R - Q^T W,  Q' = Ths^T W,  p' = th + A^T p,  P' = Th - Ths^T A
         gemv_t_add<T, D>(rv, W, pv);
         T Qn[DD];
@@ -1282,11 +1296,20 @@ struct NatSummaryCore : NatGeomBase<T_, D> {
           }
       }
 #pragma unroll
-      for (int i = 0; i < DD; ++i) {
-        Pm[i] = Dk[i];
-        S[i] = Dk[i];
+      for (int i = 0; i < DD; ++i) Pm[i] = Dk[i];
+      bool ok;
+      if constexpr (D == 2) {
+        const T det = Num<T>::fma(-Dk[2], Dk[2], Dk[0] * Dk[3]);
+        const T rd = Num<T>::rcp(det);
+        S[0] = Dk[3] * rd;
+        S[1] = -Dk[2] * rd;
+        S[2] = Dk[0] * rd;
+        ok = Dk[0] > T(0) && det > T(0);
+      } else {
+#pragma unroll
+        for (int i = 0; i < DD; ++i) S[i] = Dk[i];
+        ok = chol_lower<T, D>(S, rinv);
       }
-      const bool ok = chol_lower<T, D>(S, rinv);
       if (!ok && fail == 0) fail = (int32_t)(k + 1);
     }
   }
