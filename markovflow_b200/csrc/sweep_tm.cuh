@@ -79,6 +79,15 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, int x, int 
                : "memory");
 }
 
+// p as a T*, known to the compiler as aligned to min(16, largest power of two dividing the record size)
+template <typename T>
+__device__ __forceinline__ T* tm_assume_aligned(const void* p, int record_bytes) {
+  void* q = const_cast<void*>(p);
+  if (record_bytes % 16 == 0) return reinterpret_cast<T*>(__builtin_assume_aligned(q, 16));
+  if (record_bytes % 8 == 0) return reinterpret_cast<T*>(__builtin_assume_aligned(q, 8));
+  return reinterpret_cast<T*>(q);
+}
+
 template <class Core, int C, int K, int NSI, int NSO, int NX>
 struct SweepTmCfg {
   using T = typename Core::T;
@@ -390,7 +399,11 @@ chain_sweep_tm_kernel(const __grid_constant__ TmPack<Core::NIN + 2 * Core::NOUT>
       const T* in[NIN > 0 ? NIN : 1];
       T* out[NOUT > 0 ? NOUT : 1];
 #pragma unroll
-      for (int i = 0; i < NIN; ++i) in[i] = reinterpret_cast<const T*>(ist + in_off[i]);
+      for (int i = 0; i < NIN; ++i) {
+        // records of a mapped stream start on multiples of min(16, record size) bytes (tm_make_map checks the
+        // global side): 128-bit shared-memory loads
+        in[i] = tm_assume_aligned<T>(ist + in_off[i], Core::ein(i) * ES);
+      }
 #pragma unroll
       for (int i = 0; i < NOUT; ++i) {
         int o = out_off[i];

@@ -269,8 +269,11 @@ chain_sweep_tmi_kernel(const __grid_constant__ TmPack<Core::NIN + 2 * Core::NOUT
             o += pb;
           }
         }
-        in[i] = reinterpret_cast<const T*>(st + o);
-        out[Core::tm_alias(i)] = reinterpret_cast<T*>(st + o);
+        // every record of a mapped stream starts on a multiple of min(16, record size) bytes, in global memory
+        // (tm_make_map checks bases and strides) and here: let the compiler use 128-bit shared-memory accesses
+        T* slot = tm_assume_aligned<T>(st + o, E * ES);
+        in[i] = slot;
+        out[Core::tm_alias(i)] = slot;
       }
       core.tile(prm, in, out, j0, ns);
       if (sidx < 0) {
