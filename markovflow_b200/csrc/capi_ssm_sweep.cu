@@ -42,10 +42,13 @@ int run(const typename Core::Params& p, int64_t nchains, cudaStream_t s) {
 
 // Segments per chain for the parallel-in-time evaluation of an exact (affine) recurrence: enough
 // virtual chains to occupy the GPU, segments of at least 64 steps.
-static void plan_segments(int64_t B, int64_t T, int64_t* P, int64_t* L, int64_t target = (int64_t)148 * 192) {
+static void plan_segments(int64_t B, int64_t T, int64_t* P, int64_t* L, int64_t target = (int64_t)148 * 192,
+                          bool whole_waves = false) {
   // The three passes move ~1.5-2x the bytes of the sequential sweep, whose cost is T x (latency of a
   // step) whatever B: parallel in time pays off below ~2000 chains (measured: B = 4096 is slower).
-  int64_t p = B > 2048 ? 1 : (target + B - 1) / B;
+  // whole_waves: `target` is the number of rows the resident CTAs hold at once -- never plan more (a few CTAs
+  // spilling into one more wave cost a whole wave)
+  int64_t p = B > 2048 ? 1 : (whole_waves ? target / B : (target + B - 1) / B);
   if (p > T / 64) p = T / 64;
   if (p < 1) p = 1;
   if (tuning(3) > 0 && tuning(3) < T) p = (T + tuning(3) - 1) / tuning(3);
@@ -68,9 +71,13 @@ int ssm_sweep_moments(int dtype, int64_t D, int expectations, const void* mu0, c
                            (const Tp*)chol_q, (Tp*)o_vec, (Tp*)o_diag, (Tp*)o_sub, B, T, 1, T,
                            (Tp*)o_vec, (Tp*)o_diag, 0};
     // float32 forward sweeps stay on the 1-D engine (`b`: [B, T-1, 2] floats, chains 8 bytes off a 16-byte stride,
-    // cannot be tensor-mapped); there twice the segments pack the CTAs better (config 5: 0.396 -> 0.349 ms)
-    const int64_t target = (int64_t)148 * (sizeof(Tp) == 4 ? 384 : 192);
-    if (tuning(2) != 1 && o_diag && (o_vec || !expectations)) plan_segments(B, T, &p.P, &p.L, target);
+    // cannot be tensor-mapped).  At D <= 2 its CTAs hold 64 rows and two are resident per SM: 148 x 128 rows are
+    // ONE wave, and the segment count is rounded DOWN to stay inside it.  Measured on config 5 (1024 chains):
+    // 18 segments (288 CTAs, one wave) 0.309 ms, 36 (two waves) 0.320 ms, 55 (three) 0.325 ms -- against
+    // 0.372 ms for the 56 segments (896 CTAs: three waves and 8 CTAs) the rounded-up 148 x 384 rows gave.
+    const bool one_wave = sizeof(Tp) == 4 && kD <= 2;
+    const int64_t target = (int64_t)148 * (one_wave ? 128 : (sizeof(Tp) == 4 ? 384 : 192));
+    if (tuning(2) != 1 && o_diag && (o_vec || !expectations)) plan_segments(B, T, &p.P, &p.L, target, one_wave);
     if (p.P > 1) {
       int rc = run<SsmMomSummaryCore<Tp, kD>>(p, B * p.P, s);
       if (rc != MF_OK) return rc;
