@@ -500,8 +500,8 @@ inline bool tm_make_map(CUtensorMap* map, int* xshift, const TmStream& st, int E
   if (box[0] > 256 || box[1] > 256 || box[2] > 256) return false;
   const CUtensorMapDataType dt = ES == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   // L2 promotion 256 B: a box row is 144-160 bytes and the sweep walks along x, so the promoted line is the
-  // next tile's data (measured, config 5 float64: ssm_to_expectations 0.504 -> 0.476 ms, marginals 0.625 ->
-  // 0.603 ms, naturals_to_ssm_params 0.581 -> 0.578 ms against 128 B; 64 B: 0.568 / 0.688 / 0.622 ms)
+  // next tile's data (measured, config 5 float64: ssm_to_expectations 0.504 -> 0.476 ms,
+  // naturals_to_ssm_params 0.581 -> 0.578 ms against 128 B; 64 B: 0.568 / 0.622 ms)
   const CUresult rc = enc(map, dt, 3, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

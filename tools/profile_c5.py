@@ -27,5 +27,8 @@ if __name__ == "__main__":
     for _ in range(reps):
         mf.naturals_to_ssm_params(*th)
         mf.ssm_to_expectations(q)
+        if os.environ.get("C5_MARGINALS"):
+            q.marginals
+            q.covariance_blocks()
     torch.cuda.synchronize()
     torch.cuda.cudart().cudaProfilerStop()
